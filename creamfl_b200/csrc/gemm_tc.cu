@@ -1,0 +1,359 @@
+// Dense bf16 GEMM on 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+//   D[M,N] = epilogue( alpha * sum_k A(m,k) * B(n,k) )
+//
+// Both operands are plain row-major 2-D arrays in HBM and either may be "K-major" (stored [rows, K]) or
+// "MN-major" (stored [K, rows]); the same kernel therefore serves the three GEMMs of a linear layer without any
+// transposition pass:   fwd  Y = X W^T      (A=X  K-major,  B=W  K-major)
+//                       dgrad dX = dY W     (A=dY K-major,  B=W  MN-major)
+//                       wgrad dW = dY^T X   (A=dY MN-major, B=X  MN-major, split-K + fp32 atomics)
+// It replaces the cuBLAS calls reached from the reference through nn.Linear / HF BertModel
+// (reference: src/networks/models/pcme.py:31-44, pie_model.py:18-19,51, image_encoder.py:30,57) and the 1x1
+// convolutions of torchvision ResNet in NHWC (image_encoder.py:24).
+//
+// Structure (one CTA per SM, persistent over output tiles):
+//   warp 0   : TMA producer    (one elected lane)            smem ring of kStages x {A 128x64, B BNx64} bf16
+//   warp 1   : MMA issuer      (one elected lane)            tcgen05.mma 128 x BN x 16, fp32 accum in TMEM
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue        (thread = one accumulator row) tcgen05.ld -> bias/act/residual -> global
+// TMEM holds two accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace cfl {
+
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_erf(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tfull = bars + 2 * Cfg::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (p.M + kBM - 1) / kBM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int nkb = (p.K + kBK - 1) / kBK;
+  const int kb_per = (nkb + p.split_k - 1) / p.split_k;
+  const int units = num_m * num_n * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int m_blk = u % num_m;
+        const int n_blk = (u / num_m) % num_n;
+        const int ks = u / (num_m * num_n);
+        const int kb0 = ks * kb_per;
+        const int kb1 = min(nkb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          if constexpr (!A_MN) {
+            tma_load_2d(&tmA, &full[stage], sa, kb * kBK, m_blk * kBM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBM / 64; ++j)
+              tma_load_2d(&tmA, &full[stage], sa + j * 8192, m_blk * kBM + j * 64, kb * kBK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(&tmB, &full[stage], sb, kb * kBK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(&tmB, &full[stage], sb + j * 8192, n_blk * BN + j * 64, kb * kBK);
+          }
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(1, kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        const int ks = u / (num_m * num_n);
+        const int kb0 = ks * kb_per;
+        const int kb1 = min(nkb, kb0 + kb_per);
+        const int buf = it & 1;
+        const uint32_t bphase = (it >> 1) & 1;
+        mbar_wait(&tempty[buf], bphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+            umma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    int it = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+      const int m_blk = u % num_m;
+      const int n_blk = (u / num_m) % num_n;
+      const int ks = u / (num_m * num_n);
+      const int buf = it & 1;
+      const uint32_t bphase = (it >> 1) & 1;
+      const bool has_k = ks * kb_per < nkb;
+      mbar_wait(&tfull[buf], bphase);
+      tc_fence_after();
+      const int row = m_blk * kBM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (row < p.M && col0 < p.N && has_k) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+          const bool full_chunk = (col0 + 32 <= p.N);
+          if (p.bias != nullptr && ks == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (full_chunk || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+          }
+          if (p.add != nullptr && ks == 0) {
+            if (p.add_bf16) {
+              const __nv_bfloat16* ar = reinterpret_cast<const __nv_bfloat16*>(p.add) + (long long)row * p.ld_add + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (full_chunk || col0 + j < p.N) f[j] += __bfloat162float(ar[j]);
+            } else {
+              const float* ar = reinterpret_cast<const float*>(p.add) + (long long)row * p.ld_add + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (full_chunk || col0 + j < p.N) f[j] += ar[j];
+            }
+          }
+          if (p.out2 != nullptr) {
+            __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + (long long)row * p.ldo + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (full_chunk || col0 + j < p.N) o2[j] = __float2bfloat16(f[j]);
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          } else if (p.act == 3) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+          } else if (p.act == 6) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 1.0f / (1.0f + __expf(-f[j]));
+          } else if (p.act == 4 || p.act == 5) {
+            const __nv_bfloat16* xr = p.aux + (long long)row * p.ld_aux + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (full_chunk || col0 + j < p.N) {
+                const float x = __bfloat162float(xr[j]);
+                f[j] *= (p.act == 4) ? dgelu_erf(x) : (x > 0.0f ? 1.0f : 0.0f);
+              }
+            }
+          }
+          if (p.split_k > 1) {
+            float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (full_chunk || col0 + j < p.N) atomicAdd(o + j, f[j]);
+          } else if (p.out_bf16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0;
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j + 0], f[j + 1]);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(o + j) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) o[j] = __float2bfloat16(f[j]);
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) o[j] = f[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc: cudaFuncSetAttribute(%d B smem): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return CFL_ECUDA;
+    }
+    attr_set = true;
+  }
+  const int num_m = (p.M + kBM - 1) / kBM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int units = num_m * num_n * p.split_k;
+  const int grid = units < sm_count() ? units : sm_count();
+  kern<<<grid, 256, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+// Host entry shared by the C ABI wrappers.  a/b are bf16.  a_mn / b_mn select the storage order (see top).
+int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, GemmParams p,
+              cudaStream_t stream) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) {
+    set_error("gemm_bf16: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+    return CFL_EINVAL;
+  }
+  const int nkb = (p.K + kBK - 1) / kBK;
+  if (p.split_k < 1) p.split_k = 1;
+  if (p.split_k > nkb) p.split_k = nkb;
+  {
+    // every split must own at least one k-block
+    const int per = (nkb + p.split_k - 1) / p.split_k;
+    p.split_k = (nkb + per - 1) / per;
+  }
+  if (p.split_k > 1 && (p.out_bf16 || p.act != 0 || p.out2 != nullptr)) {
+    set_error("gemm_bf16: split-K requires fp32 output without activation");
+    return CFL_EINVAL;
+  }
+  if ((p.act == 4 || p.act == 5) && p.aux == nullptr) {
+    set_error("gemm_bf16: act %d needs aux", p.act);
+    return CFL_EINVAL;
+  }
+  // Narrow outputs waste MMA columns: pick the tile width from N.
+  const int BN = (p.N <= 64) ? 64 : 128;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn)
+    rc = make_tmap_2d(&ta, a, 2, p.M, p.K, lda, kBK, kBM);
+  else
+    rc = make_tmap_2d(&ta, a, 2, p.K, p.M, lda, 64, kBK);
+  if (rc) return rc;
+  if (!b_mn)
+    rc = make_tmap_2d(&tb, b, 2, p.N, p.K, ldb, kBK, BN);
+  else
+    rc = make_tmap_2d(&tb, b, 2, p.K, p.N, ldb, 64, kBK);
+  if (rc) return rc;
+
+#define CFL_DISPATCH(BNV)                                                                      \
+  do {                                                                                         \
+    if (!a_mn && !b_mn) return launch_gemm<BNV, false, false>(ta, tb, p, stream);              \
+    if (!a_mn && b_mn) return launch_gemm<BNV, false, true>(ta, tb, p, stream);                \
+    if (a_mn && !b_mn) return launch_gemm<BNV, true, false>(ta, tb, p, stream);                \
+    return launch_gemm<BNV, true, true>(ta, tb, p, stream);                                    \
+  } while (0)
+  if (BN == 64) CFL_DISPATCH(64);
+  CFL_DISPATCH(128);
+#undef CFL_DISPATCH
+}
+
+}  // namespace cfl

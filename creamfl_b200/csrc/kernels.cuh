@@ -1,0 +1,51 @@
+// Internal host-side entry points of the kernel translation units (shared by capi.cu).
+#pragma once
+#include "common.cuh"
+
+namespace cfl {
+// gemm_tc.cu
+struct GemmParams {
+  int M, N, K;
+  int split_k;
+  void* out;
+  long long ldo;
+  int out_bf16;
+  void* out2;
+  const float* bias;
+  int act;
+  float alpha;
+  const void* add;
+  long long ld_add;
+  int add_bf16;
+  const __nv_bfloat16* aux;
+  long long ld_aux;
+};
+int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, GemmParams p,
+              cudaStream_t stream);
+// sim_tc.cu
+size_t rowlse_workspace_bytes(int M, int N);
+int rowlse_bf16(const void* Q, const void* G, const long long* labels, int M, int N, int D, float scale,
+                float* score, float* lse2, void* workspace, size_t ws_bytes, cudaStream_t stream);
+int softmax_emit_bf16(const void* Q, const void* G, const long long* labels, const float* lse2, int M, int N,
+                      int D, float scale, void* P, long long ldp, cudaStream_t stream);
+// loss_ops.cu
+int pcme_fwd(const float*, const float*, int, int, const float*, const float*, float*, float*, float*, size_t,
+             cudaStream_t);
+int pcme_bwd(const float*, const float*, const float*, int, int, const float*, const float*, const float*,
+             float*, float*, float*, float*, float*, size_t, cudaStream_t);
+int moon_fwd(const float*, const float*, const float*, const long long*, int, int, float, float, float*, float*,
+             float*, cudaStream_t);
+int moon_bwd(const float*, const float*, const long long*, const float*, const float*, int, int, float*,
+             cudaStream_t);
+int mse_gather_fwd(const float*, const float*, const long long*, int, int, float*, float*, size_t, cudaStream_t);
+int mse_gather_bwd(const float*, const float*, const long long*, const float*, int, int, float*, cudaStream_t);
+int l2norm_fwd(const float*, int, int, float*, void*, float*, cudaStream_t);
+int l2norm_bwd(const float*, const float*, const float*, int, int, float*, cudaStream_t);
+int cast_f32_bf16(const float*, long long, void*, cudaStream_t);
+int scale_by_scalar(float*, long long, const float*, float, cudaStream_t);
+__global__ void sum_finish_kernel(const float* in, int n, float scale, float* out);
+// agg_ops.cu
+int conw_reduce(const float* const*, const float*, int, int, int, float*, float*, cudaStream_t);
+int recall_ranks(const float*, const float*, const long long*, const long long*, int, int, int, int*, void*,
+                 size_t, cudaStream_t);
+}  // namespace cfl

@@ -1,0 +1,116 @@
+/* creamfl_b200 - C ABI of the B200-native hot path of CreamFL.
+ *
+ * The reference (FLAIR-THU/CreamFL) has no FFI layer: its hot path is reached through Python factories
+ * (get_model / get_criterion / losses.create) and inline torch code in the trainers.  Every entry point below
+ * replaces one of those library call sites; the comment on each names the reference lines it stands in for.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host
+ *   - the caller owns all memory, including workspaces (size from the matching *_workspace_bytes function)
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *   - row-major contiguous tensors; bf16 operands of tensor-core kernels must be 16-byte aligned
+ *   - return value: 0 ok, -1 bad argument, -2 workspace too small, -3 CUDA error; text from creamfl_last_error()
+ *   - no CPU fallback exists: on a machine without an sm_100a GPU the calls fail with -3
+ */
+#ifndef CREAMFL_B200_H
+#define CREAMFL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CREAMFL_OK 0
+#define CREAMFL_EINVAL (-1)
+#define CREAMFL_EWORKSPACE (-2)
+#define CREAMFL_ECUDA (-3)
+
+/* activation codes of creamfl_gemm_bf16 */
+#define CREAMFL_ACT_NONE 0
+#define CREAMFL_ACT_GELU 1      /* erf GELU (HF BertIntermediate) */
+#define CREAMFL_ACT_RELU 2
+#define CREAMFL_ACT_TANH 3      /* PIENet w_1 (pie_model.py:30) */
+#define CREAMFL_ACT_DGELU 4     /* out = acc * gelu'(aux)   (backward of GELU) */
+#define CREAMFL_ACT_DRELU 5     /* out = acc * (aux > 0)    (backward of ReLU) */
+#define CREAMFL_ACT_SIGMOID 6   /* PIENet residual gate (pie_model.py:63) */
+
+const char* creamfl_last_error(void);
+int creamfl_abi_version(void);
+
+/* ---- dense contraction on tcgen05 ---------------------------------------------------------------------
+ * out[M,N] = act(alpha * sum_k A(m,k) B(n,k) + bias[n] + add[m,n]).
+ * a_mn/b_mn = 0: operand stored [rows, K] (K contiguous); = 1: stored [K, rows].
+ * Replaces cuBLAS behind nn.Linear / HF BertModel (src/networks/models/pcme.py:31-44,
+ * pie_model.py:18-19,51, image_encoder.py:30,57) and 1x1 convolutions of torchvision ResNet
+ * (image_encoder.py:24) in NHWC.  split_k > 1 accumulates with fp32 atomics into a pre-zeroed fp32 `out`. */
+int creamfl_gemm_bf16(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn, int M, int N,
+                      int K, void* out, int64_t ldo, int out_bf16, void* out_preact_bf16, const float* bias,
+                      int act, float alpha, const void* add, int64_t ld_add, int add_bf16, const void* aux_bf16,
+                      int64_t ld_aux, int split_k, void* stream);
+
+/* ---- inter-modal InfoNCE (MMClientTrainer.py:193-201,301-308; ClientTrainer.py:388-401,493-502) ------
+ * logits = inv_tau * Q G^T  (never materialised in fp32), CE against column labels[i], mean over rows.
+ * q_bf16 [B,D], g_bf16 [N,D], labels int64 [B] (distill_dict positions), D in {64,128,192,256}.
+ * Outputs: loss[1]; row_score[B] = logit_pos - logsumexp (= -CE per row); lse2[B] (log2 domain, for bwd). */
+size_t creamfl_rowlse_workspace_bytes(int M, int N);
+int creamfl_infonce_fwd(const void* q_bf16, const void* g_bf16, const int64_t* labels, int B, int N, int D,
+                        float inv_tau, float* loss, float* row_score, float* lse2, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* dQ[B,D] (fp32) = gout[0] * inv_tau / B * (softmax(logits) - onehot) G */
+size_t creamfl_infonce_bwd_workspace_bytes(int B, int N);
+int creamfl_infonce_bwd(const void* q_bf16, const void* g_bf16, const int64_t* labels, const float* lse2, int B,
+                        int N, int D, float inv_tau, const float* gout, float* dq, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* ---- con_w aggregation (MMFL.py:298-335) --------------------------------------------------------------
+ * score[n] = <V[n],G[n]> - log sum_j exp <V[n],G[j]>   (MMFL.py:304-307): v_bf16, g_bf16 [N,D]. */
+int creamfl_conw_score(const void* v_bf16, const void* g_bf16, int N, int D, float* score, void* workspace,
+                       size_t workspace_bytes, void* stream);
+/* out[n,:] = sum_c softmax_c(scores[:,n])[c] * vecs[c][n,:]   (MMFL.py:311-314).  vecs_host: HOST array of C
+ * device pointers to fp32 [N,D]; scores fp32 [C,N]; weights (optional) fp32 [C,N]. */
+int creamfl_conw_reduce(const float* const* vecs_host, const float* scores, int C, int N, int D, float* out,
+                        float* weights, void* stream);
+
+/* ---- PCME soft-contrastive loss (src/criterions/probemb.py:185-256) -----------------------------------
+ * img, txt fp32 [N,D]; shift, neg_scale: device scalars (learnable).  out3 = {loss, pos part, neg part} where
+ * loss = i2t + t2i and the parts are per direction; dist [N,N] is kept for the backward. */
+size_t creamfl_pcme_workspace_bytes(int N);
+int creamfl_pcme_fwd(const float* img, const float* txt, int N, int D, const float* shift,
+                     const float* neg_scale, float* dist, float* out3, void* workspace, size_t workspace_bytes,
+                     void* stream);
+int creamfl_pcme_bwd(const float* img, const float* txt, const float* dist, int N, int D, const float* shift,
+                     const float* neg_scale, const float* gout, float* d_img, float* d_txt, float* d_shift,
+                     float* d_neg_scale, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- intra-modal (MOON) contrast (MMClientTrainer.py:169-191; ClientTrainer.py:404-414) ---------------
+ * row r: CE([<z,bank[idx]>, <z,zold>] * inv_tau, 0) / denom.  loss (optional) = sum of loss_rows. */
+int creamfl_moon_fwd(const float* z, const float* zold, const float* bank, const int64_t* idx, int R, int D,
+                     float inv_tau, float denom, float* loss_rows, float* coef, float* loss, void* stream);
+int creamfl_moon_bwd(const float* zold, const float* bank, const int64_t* idx, const float* coef,
+                     const float* gout, int R, int D, float* dz, void* stream);
+
+/* ---- distillation MSE against aggregated rows (MMFL.py:296,355-378) ----------------------------------- */
+size_t creamfl_mse_workspace_bytes(void);
+int creamfl_mse_gather_fwd(const float* x, const float* bank, const int64_t* idx, int R, int D, float* loss,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int creamfl_mse_gather_bwd(const float* x, const float* bank, const int64_t* idx, const float* gout, int R,
+                           int D, float* dx, void* stream);
+
+/* ---- L2 normalisation (src/utils/tensor_utils.py:25-27) and casts ------------------------------------- */
+int creamfl_l2norm_fwd(const float* x, int R, int D, float* y, void* y_bf16, float* inv_norm, void* stream);
+int creamfl_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, int R, int D, float* dx,
+                       void* stream);
+int creamfl_cast_f32_bf16(const float* x, int64_t n, void* y_bf16, void* stream);
+
+/* ---- Recall@K ranks (src/algorithms/eval_coco.py:273-334) ---------------------------------------------
+ * ranks[q] = #{g : <Q_q,G_g> > max_{g': g_lab[g'] == q_lab[q]} <Q_q,G_g'>}  (0-based best-positive rank). */
+size_t creamfl_recall_workspace_bytes(int Nq);
+int creamfl_recall_ranks(const float* q, const float* g, const int64_t* q_lab, const int64_t* g_lab, int Nq,
+                         int Ng, int D, int32_t* ranks, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CREAMFL_B200_H */

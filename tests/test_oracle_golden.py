@@ -1,0 +1,166 @@
+"""CPU tests: the oracle (oracle/creamfl_oracle.py) against golden vectors produced by the reference's own code
+(tests/golden/make_golden.py).  These pin the oracle; the GPU parity tests then pin the CUDA path to the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import creamfl_oracle as O
+from conftest import conw_inputs
+
+T = lambda a: torch.from_numpy(np.asarray(a))
+
+
+@pytest.mark.parametrize('tag', ['a', 'b', 'c'])
+def test_pcme_loss_and_grads(golden, tag):
+    g = golden('pcme')
+    img = T(g[f'{tag}_img']).requires_grad_(True)
+    txt = T(g[f'{tag}_txt']).requires_grad_(True)
+    shift = torch.tensor(float(g[f'{tag}_shift']), dtype=torch.float64, requires_grad=True)
+    scale = torch.tensor(float(g[f'{tag}_scale']), dtype=torch.float64, requires_grad=True)
+    loss, info = O.pcme_loss(img, txt, shift, scale)
+    loss.backward()
+    assert loss.item() == pytest.approx(float(g[f'{tag}_loss']), rel=1e-12)
+    assert info['i2t_pos_loss'] == pytest.approx(float(g[f'{tag}_i2t_pos']), rel=1e-12)
+    assert info['i2t_neg_loss'] == pytest.approx(float(g[f'{tag}_i2t_neg']), rel=1e-12)
+    assert info['t2i_loss'] == pytest.approx(float(g[f'{tag}_t2i_loss']), rel=1e-12)
+    np.testing.assert_allclose(img.grad.numpy(), g[f'{tag}_d_img'], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(txt.grad.numpy(), g[f'{tag}_d_txt'], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(shift.grad.numpy(), g[f'{tag}_d_shift'][0], rtol=1e-9)
+    np.testing.assert_allclose(scale.grad.numpy(), g[f'{tag}_d_scale'][0], rtol=1e-9)
+
+
+def test_pcme_closed_form_identity(golden):
+    """loss = 2 * sum softplus(-2 m (-s d + b))."""
+    g = golden('pcme')
+    img, txt = T(g['a_img']), T(g['a_txt'])
+    d = O.pcme_pair_distance(img, txt)
+    m = 2 * torch.eye(len(img), dtype=torch.float64) - 1
+    l = -float(g['a_scale']) * d + float(g['a_shift'])
+    closed = 2 * torch.nn.functional.softplus(-2 * m * l).sum()
+    assert closed.item() == pytest.approx(float(g['a_loss']), rel=1e-12)
+
+
+def test_pcme_rejects_ragged():
+    with pytest.raises(RuntimeError):
+        O.pcme_loss(torch.zeros(3, 4), torch.zeros(2, 4), torch.tensor(1.0), torch.tensor(1.0))
+
+
+@pytest.mark.parametrize('tag', ['both', 'intra', 'inter', 'both_scaled'])
+def test_mm_client_contrast(golden, tag):
+    g = golden('mm_contrast')
+    rows = g['rows']
+    oi = T(g['cur_img'][rows]).requires_grad_(True)
+    ot = T(g['cur_txt'][rows]).requires_grad_(True)
+    old_i, old_t = T(g['old_img'][rows]), T(g['old_txt'][rows])
+    g_img, g_txt = T(g['g_img']), T(g['g_txt'])
+    lookup = {int(b): a for a, b in enumerate(g['distill_index'])}
+    d_idx = [lookup[int(i)] for i in g['batch_index']]
+    assert d_idx == list(rows)
+    parts = O.mm_client_contrast_loss(oi, ot, old_i, old_t, g_img, g_txt, d_idx, 0.5, tag == 'both_scaled')
+    if tag == 'intra':
+        loss = parts['intra']          # MMClientTrainer.py:264 - no interintra_weight on this branch
+    elif tag == 'inter':
+        loss = parts['inter']          # MMClientTrainer.py:308
+    else:
+        loss = parts['loss']
+    loss.backward()
+    assert loss.item() == pytest.approx(float(g[f'{tag}_loss']), rel=1e-12)
+    np.testing.assert_allclose(oi.grad.numpy(), g[f'{tag}_d_img'], rtol=1e-9, atol=1e-14)
+    np.testing.assert_allclose(ot.grad.numpy(), g[f'{tag}_d_txt'], rtol=1e-9, atol=1e-14)
+
+
+@pytest.mark.parametrize('dset', ['Cifar100', 'AG_NEWS'])
+@pytest.mark.parametrize('tag', ['both', 'intra', 'inter', 'both_scaled'])
+def test_unimodal_contrast(golden, dset, tag):
+    g, s = golden('uni_contrast'), golden('mm_contrast')
+    # uni_contrast used seed 11: regenerate the same tensors through the shared recipe
+    gen = torch.Generator().manual_seed(11)
+    unit = lambda x: x / x.norm(dim=-1, keepdim=True)
+    n_pub, d, b = 96, 32, 8
+    g_img = unit(torch.randn(n_pub, d, generator=gen, dtype=torch.float64))
+    g_txt = unit(0.7 * g_img + 0.5 * torch.randn(n_pub, d, generator=gen, dtype=torch.float64))
+    cur_img = unit(g_img + 0.4 * torch.randn(n_pub, d, generator=gen, dtype=torch.float64))
+    cur_txt = unit(g_txt + 0.4 * torch.randn(n_pub, d, generator=gen, dtype=torch.float64))
+    old_img = unit(cur_img + 0.2 * torch.randn(n_pub, d, generator=gen, dtype=torch.float64))
+    old_txt = unit(cur_txt + 0.2 * torch.randn(n_pub, d, generator=gen, dtype=torch.float64))
+    _ = torch.randperm(10 * n_pub, generator=gen)
+    rows = torch.randperm(n_pub, generator=gen)[:b].tolist()
+    is_img = dset == 'Cifar100'
+    feat = (cur_img if is_img else cur_txt)[rows].clone().requires_grad_(True)
+    old = (old_img if is_img else old_txt)[rows]
+    parts = O.unimodal_contrast_loss(feat, old, g_img if is_img else g_txt, g_txt if is_img else g_img, rows,
+                                     0.5, tag == 'both_scaled')
+    loss = {'intra': parts['intra'], 'inter': parts['inter']}.get(tag, parts['loss'])
+    loss.backward()
+    assert loss.item() == pytest.approx(float(g[f'{dset}_{tag}_loss']), rel=1e-12)
+    np.testing.assert_allclose(feat.grad.numpy(), g[f'{dset}_{tag}_d_feat'], rtol=1e-9, atol=1e-14)
+
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_recall_matches_reference_evaluator(golden, tag):
+    g = golden('recall')
+    img, cap = T(g[f'{tag}_img']), T(g[f'{tag}_cap'])
+    il, cl = g[f'{tag}_img_lab'], g[f'{tag}_cap_lab']
+    for name, (q, gal, ql, gl) in {'i2t': (img, cap, il, cl), 't2i': (cap, img, cl, il)}.items():
+        sorted_ranks = O.recall_ranks_sorted(q, gal, ql, gl)
+        count_ranks = O.recall_ranks_count(q, gal, ql, gl)
+        np.testing.assert_array_equal(sorted_ranks, count_ranks)
+        sc = O.recall_scores(count_ranks)
+        for k in ('recall_1', 'recall_5', 'recall_10', 'rsum', 'medr', 'meanr'):
+            assert sc[k] == pytest.approx(float(g[f'{tag}_{name}_{k}']), rel=1e-12), (name, k)
+
+
+@pytest.mark.parametrize('tag', ['synth', 'cifar', 'agnews'])
+def test_hetero_partition_bit_exact(golden, tag):
+    g = golden('partition')
+    n, k, nets, seed = (int(v) for v in g[f'{tag}_args'])
+    name = {'synth': 'synth', 'cifar': 'cifar100', 'agnews': 'AG_NEWS'}[tag]
+    part = O.hetero_partition(name, n, nets, float(g[f'{tag}_alpha']), np.arange(n) % k, seed=seed)
+    assert [len(part[j]) for j in range(nets)] == list(g[f'{tag}_sizes'])
+    np.testing.assert_array_equal(np.asarray([part[j][:8] for j in range(nets)]), g[f'{tag}_head'])
+    assert O.partition_digest(part) == str(g[f'{tag}_sha256'])
+    flat = np.sort(np.concatenate([np.asarray(part[j]) for j in range(nets)]))
+    np.testing.assert_array_equal(flat, np.arange(n))  # disjoint and complete
+
+
+def test_survey_partition_kat():
+    """SURVEY.md section 4 item 5 known answer."""
+    part = O.hetero_partition('synth', 50000, 4, 0.1, np.arange(50000) % 100, seed=2021)
+    assert [len(part[j]) for j in range(4)] == [12562, 12621, 12162, 12655]
+    assert part[0][:5] == [15037, 46424, 20641, 12533, 4243]
+    assert O.partition_digest(part).startswith('c5b16d61cd6565da')
+
+
+def test_flickr_shard_partition_bit_exact(golden):
+    g = golden('partition')
+    part = O.shard_partition(145000, 15, 150, seed=2021)
+    assert [len(part[j]) for j in range(15)] == list(g['f30k_sizes'])
+    np.testing.assert_array_equal(np.asarray([part[j][:8] for j in range(15)]), g['f30k_head'])
+    assert O.partition_digest(part) == str(g['f30k_sha256'])
+    assert list(g['f30k_sizes']) == [9660] * 14 + [9760]
+
+
+def test_conw_closed_form_small():
+    """s_c[n] = <V_c[n],G[n]> - logsumexp_j <V_c[n],G[j]>."""
+    g_img, g_txt, i_vecs, _ = conw_inputs(3, 512, 64, 3)
+    vecs = [T(v).double() for v in i_vecs]
+    G = T(g_txt).double()
+    agg, w = O.conw_aggregate(vecs, G, chunk=100)
+    s = torch.stack([(v * G).sum(1) - torch.logsumexp(v @ G.T, dim=1) for v in vecs])
+    np.testing.assert_allclose(w.numpy(), torch.softmax(s, 0).numpy(), rtol=1e-9)
+    np.testing.assert_allclose(agg.numpy(), sum(v * torch.softmax(s, 0)[c][:, None] for c, v in enumerate(vecs)).numpy(),
+                               rtol=1e-9)
+
+
+def test_conw_full_size_against_reference(golden):
+    """The reference's aggregation() only runs at N = 50000 (hard-coded); compare the oracle on the same inputs."""
+    g = golden('conw')
+    n, d, c = int(g['n']), int(g['d']), int(g['c'])
+    g_img, g_txt, i_vecs, t_vecs = conw_inputs(int(g['seed']), n, d, c)
+    agg_i, _ = O.conw_aggregate([T(v) for v in i_vecs], T(g_txt))
+    agg_t, _ = O.conw_aggregate([T(v) for v in t_vecs], T(g_img))
+    rows = g['rows']
+    np.testing.assert_allclose(agg_i.numpy()[rows], g['img_rows'], rtol=2e-5, atol=2e-7)
+    np.testing.assert_allclose(agg_t.numpy()[rows], g['txt_rows'], rtol=2e-5, atol=2e-7)
+    assert agg_i.double().abs().sum().item() == pytest.approx(float(g['img_abs_sum']), rel=1e-6)
+    assert agg_t.double().abs().sum().item() == pytest.approx(float(g['txt_abs_sum']), rel=1e-6)
