@@ -35,7 +35,18 @@ int sm_count() {
   return n;
 }
 
+// The driver-API encoder needs a current context on the calling thread; PyTorch's autograd worker threads may
+// reach us before any runtime call has bound the primary context to them.
+static void bind_context() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  bind_context();
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
     void* p = nullptr;
