@@ -6,6 +6,7 @@ library's own message is raised.
 from __future__ import annotations
 
 import ctypes as C
+import re
 from pathlib import Path
 
 _LIB_PATH = Path(__file__).resolve().parent / "libcreamfl_b200.so"
@@ -13,32 +14,32 @@ _lib = None
 
 vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 
-# name -> (restype, argtypes); mirrors include/creamfl_b200.h one to one
-_SIGNATURES = {
-    "creamfl_last_error": (C.c_char_p, []),
-    "creamfl_abi_version": (i32, []),
-    "creamfl_gemm_bf16": (i32, [vp, i64, i32, vp, i64, i32, i32, i32, i32, vp, i64, i32, vp, vp, i32, f32, vp, i64,
-                                i32, vp, i64, i32, vp]),
-    "creamfl_rowlse_workspace_bytes": (sz, [i32, i32]),
-    "creamfl_infonce_fwd": (i32, [vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, sz, vp]),
-    "creamfl_infonce_bwd_workspace_bytes": (sz, [i32, i32]),
-    "creamfl_infonce_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, sz, vp]),
-    "creamfl_conw_score": (i32, [vp, vp, i32, i32, vp, vp, sz, vp]),
-    "creamfl_conw_reduce": (i32, [C.POINTER(vp), vp, i32, i32, i32, vp, vp, vp]),
-    "creamfl_pcme_workspace_bytes": (sz, [i32]),
-    "creamfl_pcme_fwd": (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp, sz, vp]),
-    "creamfl_pcme_bwd": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
-    "creamfl_moon_fwd": (i32, [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp]),
-    "creamfl_moon_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, vp, vp]),
-    "creamfl_mse_workspace_bytes": (sz, []),
-    "creamfl_mse_gather_fwd": (i32, [vp, vp, vp, i32, i32, vp, vp, sz, vp]),
-    "creamfl_mse_gather_bwd": (i32, [vp, vp, vp, vp, i32, i32, vp, vp]),
-    "creamfl_l2norm_fwd": (i32, [vp, i32, i32, vp, vp, vp, vp]),
-    "creamfl_l2norm_bwd": (i32, [vp, vp, vp, i32, i32, vp, vp]),
-    "creamfl_cast_f32_bf16": (i32, [vp, i64, vp, vp]),
-    "creamfl_recall_workspace_bytes": (sz, [i32]),
-    "creamfl_recall_ranks": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp, sz, vp]),
-}
+_HEADER = Path(__file__).resolve().parent.parent / "include" / "creamfl_b200.h"
+_SCALARS = {"int": i32, "int64_t": i64, "float": f32, "size_t": sz, "int32_t": i32}
+_PROTO = re.compile(r"^(size_t|int|const char\*)\s+(creamfl_\w+)\s*\(([^;{]*)\)\s*;", re.M | re.S)
+
+
+def _parse_header() -> dict:
+    """name -> (restype, argtypes), read from include/creamfl_b200.h so the binding cannot drift from the ABI.
+    Every pointer (of any pointee type) travels as c_void_p; scalars map one to one."""
+    text = re.sub(r"/\*.*?\*/", "", _HEADER.read_text(), flags=re.S)
+    sigs = {}
+    for ret, name, args in _PROTO.findall(text):
+        res = {"size_t": sz, "int": i32, "const char*": C.c_char_p}[ret]
+        argtypes = []
+        args = " ".join(args.split())
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    argtypes.append(vp)
+                else:
+                    argtypes.append(_SCALARS[a.replace("const ", "").split()[0]])
+        sigs[name] = (res, argtypes)
+    return sigs
+
+
+_SIGNATURES = _parse_header()
 
 
 def lib_path() -> Path:

@@ -17,14 +17,22 @@ int creamfl_abi_version(void) { return 1; }
 int creamfl_gemm_bf16(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn, int M, int N,
                       int K, void* out, int64_t ldo, int out_bf16, void* out_preact_bf16, const float* bias,
                       int act, float alpha, const void* add, int64_t ld_add, int add_bf16, const void* aux_bf16,
-                      int64_t ld_aux, int split_k, void* stream) {
+                      int64_t ld_aux, int split_k, int accumulate, void* stream) {
   if (!a || !b || !out) {
     set_error("gemm_bf16: null pointer");
     return CFL_EINVAL;
   }
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
+  if (split_k == 0) {
+    const long long tiles = ((M + 127LL) / 128) * ((N + 127LL) / 128);
+    long long split = (2LL * sm_count() + tiles - 1) / tiles;
+    const long long nkb = (K + 63LL) / 64;
+    if (split > nkb / 4) split = nkb / 4;
+    split_k = (accumulate && split > 1) ? (int)split : 1;
+  }
   p.split_k = split_k;
+  p.atomic_out = accumulate ? 1 : 0;
   p.out = out; p.ldo = ldo; p.out_bf16 = out_bf16;
   p.out2 = out_preact_bf16;
   p.bias = bias; p.act = act; p.alpha = alpha;
@@ -195,6 +203,14 @@ int creamfl_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, i
     return CFL_EINVAL;
   }
   return l2norm_bwd(dy, y, inv_norm, R, D, dx, S(stream));
+}
+
+int creamfl_act_bwd_f32(const float* dy, const float* y, int64_t n, int kind, void* out, void* stream) {
+  if (!dy || !y || !out || n <= 0 || (kind != CREAMFL_ACT_SIGMOID && kind != CREAMFL_ACT_TANH)) {
+    set_error("act_bwd_f32: bad argument");
+    return CFL_EINVAL;
+  }
+  return act_bwd_f32(dy, y, n, kind, out, S(stream));
 }
 
 int creamfl_cast_f32_bf16(const float* x, int64_t n, void* y, void* stream) {

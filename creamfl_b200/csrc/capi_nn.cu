@@ -1,0 +1,302 @@
+// extern "C" surface of the encoder-tower operations (declared in include/creamfl_b200.h): argument checking and
+// the choice between the three convolution strategies; no kernel code lives here.
+#include "../../include/creamfl_b200.h"
+#include "kernels.cuh"
+
+using namespace cfl;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+namespace {
+struct ConvShape {
+  int N, H, W, Cin, Cout, R, S, stride, pad, Ho, Wo;
+  long long P_out;
+  int kcols;   // R*S*Cin
+  int ldc;     // patch-matrix pitch
+  bool is_1x1, is_same;
+};
+ConvShape shape_of(int N, int H, int W, int Cin, int Cout, int R, int S_, int stride, int pad) {
+  ConvShape c{N, H, W, Cin, Cout, R, S_, stride, pad, 0, 0, 0, 0, 0, false, false};
+  c.Ho = (H + 2 * pad - R) / stride + 1;
+  c.Wo = (W + 2 * pad - S_) / stride + 1;
+  c.P_out = (long long)N * c.Ho * c.Wo;
+  c.kcols = R * S_ * Cin;
+  c.ldc = (int)round_up(c.kcols, 8);
+  c.is_1x1 = (R == 1 && S_ == 1 && stride == 1 && pad == 0);
+  c.is_same = (!c.is_1x1 && stride == 1 && (R & 1) && (S_ & 1) && pad == R / 2 && pad == S_ / 2 && Cin % 64 == 0 &&
+               Cout % 64 == 0);
+  return c;
+}
+int check_shape(const char* who, const ConvShape& c) {
+  if (c.N <= 0 || c.H <= 0 || c.W <= 0 || c.Cin <= 0 || c.Cout <= 0 || c.R <= 0 || c.S <= 0 || c.stride <= 0 ||
+      c.pad < 0 || c.Ho <= 0 || c.Wo <= 0) {
+    set_error("%s: bad convolution shape", who);
+    return CFL_EINVAL;
+  }
+  if (c.Cin % 8 || c.Cout % 8) {
+    set_error("%s: channel counts must be multiples of 8 (Cin=%d Cout=%d)", who, c.Cin, c.Cout);
+    return CFL_EINVAL;
+  }
+  return CFL_OK;
+}
+int split_for(long long M, long long N, long long K) {
+  const long long tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  long long split = (2LL * sm_count() + tiles - 1) / tiles;
+  const long long nkb = (K + 63) / 64;
+  if (split > nkb / 4) split = nkb / 4;
+  if (split < 1) split = 1;
+  return (int)split;
+}
+}  // namespace
+
+extern "C" {
+
+size_t creamfl_conv2d_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S_, int stride, int pad) {
+  const ConvShape c = shape_of(N, H, W, Cin, Cout, R, S_, stride, pad);
+  if (c.is_1x1 || c.is_same || c.P_out <= 0) return 0;
+  return (size_t)c.P_out * c.ldc * 2;
+}
+
+int creamfl_conv2d_fprop(const void* x, const void* w, int N, int H, int W, int Cin, int Cout, int R, int S_,
+                         int stride, int pad, int64_t w_pitch, void* y, void* ws, size_t ws_bytes, void* stream) {
+  const ConvShape c = shape_of(N, H, W, Cin, Cout, R, S_, stride, pad);
+  int rc = check_shape("conv2d_fprop", c);
+  if (rc) return rc;
+  if (!x || !w || !y) {
+    set_error("conv2d_fprop: null pointer");
+    return CFL_EINVAL;
+  }
+  if (c.is_same && w_pitch == c.kcols) return conv_same_fprop(x, w, N, H, W, Cin, Cout, R, S_, y, S(stream));
+  GemmParams p{};
+  p.M = (int)c.P_out; p.N = Cout; p.split_k = 1;
+  p.out = y; p.ldo = Cout; p.out_bf16 = 1; p.alpha = 1.0f;
+  if (c.is_1x1) {
+    p.K = Cin;
+    return gemm_bf16(x, Cin, 0, w, w_pitch, 0, p, S(stream));
+  }
+  const size_t need = (size_t)c.P_out * c.ldc * 2;
+  if (!ws || ws_bytes < need) {
+    set_error("conv2d_fprop: workspace %zu B < %zu B", ws_bytes, need);
+    return CFL_EWORKSPACE;
+  }
+  if (w_pitch < c.ldc) {
+    set_error("conv2d_fprop: filter pitch %lld < padded patch width %d", (long long)w_pitch, c.ldc);
+    return CFL_EINVAL;
+  }
+  if ((rc = im2col_nhwc(x, N, H, W, Cin, R, S_, stride, pad, c.ldc, ws, S(stream)))) return rc;
+  p.K = c.ldc;
+  return gemm_bf16(ws, c.ldc, 0, w, w_pitch, 0, p, S(stream));
+}
+
+int creamfl_conv2d_dgrad(const void* dy, const void* w, int N, int H, int W, int Cin, int Cout, int R, int S_,
+                         int stride, int pad, int64_t w_pitch, const void* add, void* dx, void* ws, size_t ws_bytes,
+                         void* stream) {
+  const ConvShape c = shape_of(N, H, W, Cin, Cout, R, S_, stride, pad);
+  int rc = check_shape("conv2d_dgrad", c);
+  if (rc) return rc;
+  if (!dy || !w || !dx) {
+    set_error("conv2d_dgrad: null pointer");
+    return CFL_EINVAL;
+  }
+  if (c.is_same && w_pitch == c.kcols) return conv_same_dgrad(dy, w, N, H, W, Cin, Cout, R, S_, dx, add, S(stream));
+  GemmParams p{};
+  p.M = (int)c.P_out; p.K = Cout; p.split_k = 1; p.alpha = 1.0f; p.out_bf16 = 1;
+  if (c.is_1x1) {
+    p.N = Cin; p.out = dx; p.ldo = Cin;
+    p.add = add; p.ld_add = Cin; p.add_bf16 = 1;
+    return gemm_bf16(dy, Cout, 0, w, w_pitch, 1, p, S(stream));
+  }
+  const size_t need = (size_t)c.P_out * c.ldc * 2;
+  if (!ws || ws_bytes < need) {
+    set_error("conv2d_dgrad: workspace %zu B < %zu B", ws_bytes, need);
+    return CFL_EWORKSPACE;
+  }
+  p.N = c.kcols; p.out = ws; p.ldo = c.ldc;
+  if ((rc = gemm_bf16(dy, Cout, 0, w, w_pitch, 1, p, S(stream)))) return rc;
+  return col2im_nhwc(ws, N, H, W, Cin, R, S_, stride, pad, c.ldc, add, dx, S(stream));
+}
+
+int creamfl_conv2d_wgrad(const void* dy, const void* x, const void* col, int N, int H, int W, int Cin, int Cout, int R,
+                         int S_, int stride, int pad, float* dw, void* ws, size_t ws_bytes, void* stream) {
+  const ConvShape c = shape_of(N, H, W, Cin, Cout, R, S_, stride, pad);
+  int rc = check_shape("conv2d_wgrad", c);
+  if (rc) return rc;
+  if (!dy || !dw || (!x && !col)) {
+    set_error("conv2d_wgrad: null pointer");
+    return CFL_EINVAL;
+  }
+  if (c.is_same && !col) return conv_same_wgrad(dy, x, N, H, W, Cin, Cout, R, S_, dw, S(stream));
+  GemmParams p{};
+  p.M = Cout; p.K = (int)c.P_out; p.alpha = 1.0f; p.out = dw; p.ldo = c.kcols; p.out_bf16 = 0; p.atomic_out = 1;
+  if (c.is_1x1 && !col) {
+    p.N = Cin;
+    p.split_k = split_for(p.M, p.N, p.K);
+    return gemm_bf16(dy, Cout, 1, x, Cin, 1, p, S(stream));
+  }
+  const void* patches = col;
+  if (!patches) {
+    const size_t need = (size_t)c.P_out * c.ldc * 2;
+    if (!ws || ws_bytes < need) {
+      set_error("conv2d_wgrad: workspace %zu B < %zu B", ws_bytes, need);
+      return CFL_EWORKSPACE;
+    }
+    if ((rc = im2col_nhwc(x, N, H, W, Cin, R, S_, stride, pad, c.ldc, ws, S(stream)))) return rc;
+    patches = ws;
+  }
+  p.N = c.kcols;
+  p.split_k = split_for(p.M, p.N, p.K);
+  return gemm_bf16(dy, Cout, 1, patches, c.ldc, 1, p, S(stream));
+}
+
+int creamfl_im2col_nchw_f32(const float* images, int N, int C, int H, int W, int R, int S_, int stride, int pad,
+                            int col_pitch, void* col, void* stream) {
+  if (!images || !col || N <= 0 || C <= 0 || (col_pitch & 7)) {
+    set_error("im2col_nchw_f32: bad argument (pitch must be a multiple of 8)");
+    return CFL_EINVAL;
+  }
+  return im2col_nchw_f32(images, N, C, H, W, R, S_, stride, pad, col_pitch, col, S(stream));
+}
+
+int creamfl_bn_train_fwd(const void* x, int64_t P, int C, const float* gamma, const float* beta, float eps,
+                         float momentum, float* running_mean, float* running_var, double* sums, float* mean,
+                         float* rstd, float* scale, float* shift, const void* res, int relu, void* y, void* stream) {
+  if (!x || !gamma || !beta || !sums || !mean || !rstd || !scale || !shift || !y) {
+    set_error("bn_train_fwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return bn_train_fwd(x, P, C, gamma, beta, eps, momentum, running_mean, running_var, sums, mean, rstd, scale, shift,
+                      res, relu, y, S(stream));
+}
+
+int creamfl_bn_eval_fwd(const void* x, int64_t P, int C, const float* gamma, const float* beta, float eps,
+                        const float* running_mean, const float* running_var, float* scale, float* shift,
+                        const void* res, int relu, void* y, void* stream) {
+  if (!x || !gamma || !beta || !running_mean || !running_var || !scale || !shift || !y) {
+    set_error("bn_eval_fwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return bn_eval_fwd(x, P, C, gamma, beta, eps, running_mean, running_var, scale, shift, res, relu, y, S(stream));
+}
+
+int creamfl_bn_train_bwd(const void* dy, const void* y, const void* x, int64_t P, int C, const float* gamma,
+                         const float* mean, const float* rstd, double* sums, float* coef, float* dgamma, float* dbeta,
+                         void* dx, void* g_out, void* stream) {
+  if (!dy || !x || !gamma || !mean || !rstd || !sums || !coef || !dx) {
+    set_error("bn_train_bwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return bn_train_bwd(dy, y, x, P, C, gamma, mean, rstd, sums, coef, dgamma, dbeta, dx, g_out, S(stream));
+}
+
+int creamfl_maxpool_fwd(const void* x, int N, int H, int W, int C, void* y, void* idx, void* stream) {
+  if (!x || !y) {
+    set_error("maxpool_fwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return maxpool_fwd(x, N, H, W, C, y, idx, S(stream));
+}
+
+int creamfl_maxpool_bwd(const void* dy, const void* idx, int N, int H, int W, int C, void* dx, void* stream) {
+  if (!dy || !idx || !dx) {
+    set_error("maxpool_bwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return maxpool_bwd(dy, idx, N, H, W, C, dx, S(stream));
+}
+
+size_t creamfl_layernorm_bwd_workspace_bytes(int D) { return D > 0 ? layernorm_bwd_workspace_bytes(D) : 0; }
+
+int creamfl_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, float eps, int R,
+                          int D, int is_bf16, void* y, float* mean, float* rstd, void* stream) {
+  if (!x || !gamma || !beta || !y) {
+    set_error("layernorm_fwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return layernorm_fwd(x, res, gamma, beta, eps, R, D, is_bf16, y, mean, rstd, S(stream));
+}
+
+int creamfl_layernorm_bwd(const void* dy, const void* x, const void* res, const float* gamma, const float* mean,
+                          const float* rstd, int R, int D, int is_bf16, void* dx, float* dgamma, float* dbeta,
+                          void* ws, size_t ws_bytes, void* stream) {
+  if (!dy || !x || !gamma || !mean || !rstd || !dx || !ws) {
+    set_error("layernorm_bwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return layernorm_bwd(dy, x, res, gamma, mean, rstd, R, D, is_bf16, dx, dgamma, dbeta, ws, ws_bytes, S(stream));
+}
+
+int creamfl_colsum_bf16(const void* x, int M, int N, int64_t ld, float* out, void* stream) {
+  if (!x || !out) {
+    set_error("colsum_bf16: null pointer");
+    return CFL_EINVAL;
+  }
+  return colsum_bf16(x, M, N, ld, out, S(stream));
+}
+
+int creamfl_add_bf16(const void* a, const void* b, int64_t n, void* y, void* stream) {
+  if (!a || !b || !y) {
+    set_error("add_bf16: null pointer");
+    return CFL_EINVAL;
+  }
+  return add_bf16(a, b, n, y, S(stream));
+}
+
+int creamfl_embed_fwd(const int64_t* ids, const int64_t* tt, const float* word, const float* pos, const float* type,
+                      int T, int L, int D, void* out, void* stream) {
+  if (!ids || !word || !pos || !type || !out) {
+    set_error("embed_fwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return embed_fwd(reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(tt), word, pos, type, T,
+                   L, D, out, S(stream));
+}
+
+int creamfl_embed_bwd(const int64_t* ids, const int64_t* tt, const void* dh, int T, int L, int D, float* dword,
+                      float* dpos, float* dtype, void* stream) {
+  if (!ids || !dh || !dword || !dpos || !dtype) {
+    set_error("embed_bwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return embed_bwd(reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(tt), dh, T, L, D, dword,
+                   dpos, dtype, S(stream));
+}
+
+int creamfl_attn_fwd(const void* qkv, const float* mask, int B, int L, int H, int head_dim, void* ctx, void* probs,
+                     void* stream) {
+  if (!qkv || !mask || !ctx || !probs) {
+    set_error("attn_fwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return attn_fwd(qkv, mask, B, L, H, head_dim, ctx, probs, S(stream));
+}
+
+int creamfl_attn_bwd(const void* qkv, const void* probs, const void* dctx, int B, int L, int H, int head_dim,
+                     void* dqkv, void* stream) {
+  if (!qkv || !probs || !dctx || !dqkv) {
+    set_error("attn_bwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return attn_bwd(qkv, probs, dctx, B, L, H, head_dim, dqkv, S(stream));
+}
+
+int creamfl_pie_pool_fwd(const void* x, const void* h, const float* w2, int B, int P, int C, int Hd, float* attn,
+                         void* r, void* pooled, void* stream) {
+  if (!x || !h || !w2 || !attn || !r || !pooled) {
+    set_error("pie_pool_fwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return pie_pool_fwd(x, h, w2, B, P, C, Hd, attn, r, pooled, S(stream));
+}
+
+int creamfl_pie_pool_bwd(const void* x, const void* h, const float* w2, const float* attn, const void* d_r,
+                         const void* d_pooled, int B, int P, int C, int Hd, void* dx, void* dpre, float* dw2,
+                         void* stream) {
+  if (!x || !h || !w2 || !attn || !d_r || !d_pooled || !dx || !dpre || !dw2) {
+    set_error("pie_pool_bwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return pie_pool_bwd(x, h, w2, attn, d_r, d_pooled, B, P, C, Hd, dx, dpre, dw2, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,421 @@
+// Convolution as implicit GEMM on tcgen05 (NHWC bf16 activations, [Cout, R, S, Cin] bf16 filters, fp32 accumulate).
+//
+// Replaces the cuDNN fprop / dgrad / wgrad calls reached from the reference through torchvision ResNet101
+// (src/networks/models/image_encoder.py:24,55) and the client ResNet18 (src/networks/resnet_client.py:164-172).
+//
+// Stride-1 "same" convolutions (every 3x3 of ResNet except three) never materialise an im2col matrix: the A
+// operand of the GEMM is fetched by TMA as a 4-D box (64 channels x bw x bh x bn pixels) of the activation
+// tensor, shifted by the filter tap; out-of-image pixels are zero-filled by the TMA unit, which is exactly the
+// zero padding of the convolution.
+//
+//   MODE 0  fprop : Y[p, co]  = sum_{tap, ci} X[p + tap, ci] * Wt[co, tap, ci]      M = pixels, N = Cout, K = taps*Cin
+//   MODE 1  dgrad : dX[p, ci] = sum_{tap, co} dY[p - tap, co] * Wt[co, tap, ci]     M = pixels, N = Cin,  K = taps*Cout
+//   MODE 2  wgrad : dW[co, tap, ci] += sum_p dY[p, co] * X[p + tap, ci]             M = Cout,   N = Cin,  K = pixels
+//
+// Same warp-specialised pipeline as gemm_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 epilogue, double-buffered accumulators in TMEM, persistent over output tiles.  Strided convolutions and
+// the 7x7 stem go through an explicit im2col buffer + gemm_tc (they are 4 % of the FLOPs).
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace cfl {
+
+struct ConvParams {
+  int N, H, W;           // activation extent (input == output: stride 1, same padding)
+  int Cin, Cout;
+  int R, S, pad_h, pad_w;
+  int bw, bh, bn;        // pixel box of one tile (product 128 for fprop/dgrad, 64 for wgrad)
+  int tiles_w, tiles_h, tiles_n;
+  int split_k;           // wgrad only
+  void* out;             // bf16 [N,H,W,Cout|Cin] (fprop/dgrad) or fp32 [Cout, R*S*Cin] accumulated (wgrad)
+  const __nv_bfloat16* add;  // optional bf16 tensor added to the fprop/dgrad output (same layout as out)
+};
+
+constexpr int kCBM = 128;
+constexpr int kCBK = 64;
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int kABytes = kCBM * kCBK * 2;
+  static constexpr int kBBytes = BN * kCBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 128) ? 6 : 8;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr uint32_t kTmemCols = (BN == 128) ? 256 : 128;
+};
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tfull = bars + 2 * Cfg::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int taps = p.R * p.S;
+  const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+
+  // GEMM view of this mode
+  const int n_extent = (MODE == 0) ? p.Cout : p.Cin;                 // N of the GEMM
+  const int num_n = (n_extent + BN - 1) / BN;
+  int num_m, nkb, kb_per, units;
+  if (MODE == 2) {
+    num_m = (p.Cout + kCBM - 1) / kCBM;
+    nkb = pix_tiles;
+    kb_per = (nkb + p.split_k - 1) / p.split_k;
+    units = num_m * num_n * taps * p.split_k;
+  } else {
+    num_m = pix_tiles;
+    const int cred = (MODE == 0) ? p.Cin : p.Cout;
+    nkb = taps * (cred / kCBK);
+    kb_per = nkb;
+    units = num_m * num_n;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        if (MODE != 2) {
+          const int m_blk = u % num_m;
+          const int n_blk = u / num_m;
+          const int w0 = (m_blk % p.tiles_w) * p.bw;
+          const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * p.bh;
+          const int n0 = (m_blk / (p.tiles_w * p.tiles_h)) * p.bn;
+          const int cred = (MODE == 0) ? p.Cin : p.Cout;
+          const int cchunks = cred / kCBK;
+          for (int kb = 0; kb < nkb; ++kb) {
+            const int tap = kb / cchunks;
+            const int c0 = (kb % cchunks) * kCBK;
+            const int r = tap / p.S, s = tap % p.S;
+            const int dh = (MODE == 0) ? (r - p.pad_h) : (p.pad_h - r);
+            const int dw = (MODE == 0) ? (s - p.pad_w) : (p.pad_w - s);
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + Cfg::kABytes;
+            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+            tma_load_4d(&tmA, &full[stage], sa, c0, w0 + dw, h0 + dh, n0);
+            if (MODE == 0) {
+              tma_load_2d(&tmB, &full[stage], sb, tap * p.Cin + c0, n_blk * BN);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(&tmB, &full[stage], sb + j * 8192, tap * p.Cin + n_blk * BN + j * 64, c0);
+            }
+            if (++stage == Cfg::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        } else {
+          int t = u;
+          const int m_blk = t % num_m; t /= num_m;
+          const int n_blk = t % num_n; t /= num_n;
+          const int tap = t % taps;
+          const int ks = t / taps;
+          const int r = tap / p.S, s = tap % p.S;
+          const int dh = r - p.pad_h, dw = s - p.pad_w;
+          const int kb0 = ks * kb_per;
+          const int kb1 = min(nkb, kb0 + kb_per);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            const int w0 = (kb % p.tiles_w) * p.bw;
+            const int h0 = ((kb / p.tiles_w) % p.tiles_h) * p.bh;
+            const int n0 = (kb / (p.tiles_w * p.tiles_h)) * p.bn;
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + Cfg::kABytes;
+            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+#pragma unroll
+            for (int j = 0; j < kCBM / 64; ++j)
+              tma_load_4d(&tmA, &full[stage], sa + j * 8192, m_blk * kCBM + j * 64, w0, h0, n0);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(&tmB, &full[stage], sb + j * 8192, n_blk * BN + j * 64, w0 + dw, h0 + dh, n0);
+            if (++stage == Cfg::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr bool A_MN = (MODE == 2);
+      constexpr bool B_MN = (MODE != 0);
+      constexpr uint32_t idesc = make_idesc(1, kCBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        int kb0 = 0, kb1 = nkb;
+        if (MODE == 2) {
+          const int ks = u / (num_m * num_n * taps);
+          kb0 = ks * kb_per;
+          kb1 = min(nkb, kb0 + kb_per);
+        }
+        const int buf = it & 1;
+        const uint32_t bphase = (it >> 1) & 1;
+        mbar_wait(&tempty[buf], bphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kCBK / 16; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+            umma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    int it = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t bphase = (it >> 1) & 1;
+      const int rloc = q * 32 + lane;
+      bool row_ok;
+      long long row_off;   // element offset of this thread's output row
+      int n_blk;
+      bool has_k = true;
+      if (MODE != 2) {
+        const int m_blk = u % num_m;
+        n_blk = u / num_m;
+        const int w = (m_blk % p.tiles_w) * p.bw + rloc % p.bw;
+        const int h = ((m_blk / p.tiles_w) % p.tiles_h) * p.bh + (rloc / p.bw) % p.bh;
+        const int n = (m_blk / (p.tiles_w * p.tiles_h)) * p.bn + rloc / (p.bw * p.bh);
+        row_ok = (w < p.W) && (h < p.H) && (n < p.N);
+        row_off = (((long long)n * p.H + h) * p.W + w) * n_extent;
+      } else {
+        int t = u;
+        const int m_blk = t % num_m; t /= num_m;
+        n_blk = t % num_n; t /= num_n;
+        const int tap = t % taps;
+        const int ks = t / taps;
+        has_k = ks * kb_per < nkb;
+        const int row = m_blk * kCBM + rloc;
+        row_ok = row < p.Cout;
+        row_off = (long long)row * taps * p.Cin + (long long)tap * p.Cin;
+      }
+      mbar_wait(&tfull[buf], bphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (row_ok && has_k && col0 < n_extent) {
+          if (MODE == 2) {
+            float* o = reinterpret_cast<float*>(p.out) + row_off + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < n_extent) atomicAdd(o + j, __uint_as_float(v[j]));
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + col0;
+            if (p.add != nullptr) {
+              const __nv_bfloat16* ar = p.add + row_off + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < n_extent) v[j] = __float_as_uint(__uint_as_float(v[j]) + __bfloat162float(ar[j]));
+            }
+            if (col0 + 32 <= n_extent) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(o + j) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < n_extent) o[j] = __float2bfloat16(__uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN, int MODE>
+static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, int units,
+                       cudaStream_t stream) {
+  using Cfg = ConvCfg<BN>;
+  auto kern = conv_tc_kernel<BN, MODE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("conv_tc: cudaFuncSetAttribute(%d B smem): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return CFL_ECUDA;
+    }
+    attr_set = true;
+  }
+  const int grid = units < sm_count() ? units : sm_count();
+  kern<<<grid, 256, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  return check_launch("conv_tc_kernel");
+}
+
+// Largest power of two dividing x, capped.
+static int pow2_divisor(int x, int cap) {
+  int d = 1;
+  while (d * 2 <= cap && x % (d * 2) == 0) d *= 2;
+  return d;
+}
+
+// Pixel box (bw x bh x bn) with `rows` pixels that tiles an H x W map without remainder in h and w.
+static void plan_box(int H, int W, int rows, int* bw, int* bh, int* bn) {
+  *bw = pow2_divisor(W, rows < 16 ? rows : 16);
+  *bh = pow2_divisor(H, rows / *bw);
+  *bn = rows / (*bw * *bh);
+}
+
+static int check_conv(const char* who, int N, int H, int W, int Cin, int Cout, int R, int S) {
+  if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) {
+    set_error("%s: empty problem", who);
+    return CFL_EINVAL;
+  }
+  if ((R & 1) == 0 || (S & 1) == 0) {
+    set_error("%s: implicit path needs odd filter sizes (got %dx%d)", who, R, S);
+    return CFL_EINVAL;
+  }
+  if (Cin % 64 || Cout % 64) {
+    set_error("%s: implicit path needs Cin, Cout multiples of 64 (got %d, %d)", who, Cin, Cout);
+    return CFL_EINVAL;
+  }
+  return CFL_OK;
+}
+
+// Y = conv(X, Wt), stride 1, padding (R/2, S/2).  X [N,H,W,Cin], Wt [Cout,R,S,Cin], Y [N,H,W,Cout], all bf16.
+int conv_same_fprop(const void* x, const void* wt, int N, int H, int W, int Cin, int Cout, int R, int S, void* y,
+                    cudaStream_t stream) {
+  int rc = check_conv("conv_fprop", N, H, W, Cin, Cout, R, S);
+  if (rc) return rc;
+  ConvParams p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad_h = R / 2; p.pad_w = S / 2;
+  plan_box(H, W, kCBM, &p.bw, &p.bh, &p.bn);
+  p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.split_k = 1;
+  p.out = y;
+  const int BN = (Cout <= 64) ? 64 : 128;
+  CUtensorMap ta, tb;
+  if ((rc = make_tmap_nhwc(&ta, x, N, H, W, Cin, 64, p.bw, p.bh, p.bn, 1))) return rc;
+  if ((rc = make_tmap_2d(&tb, wt, 2, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, 64, BN))) return rc;
+  const int units = p.tiles_w * p.tiles_h * p.tiles_n * ((Cout + BN - 1) / BN);
+  return BN == 64 ? launch_conv<64, 0>(ta, tb, p, units, stream) : launch_conv<128, 0>(ta, tb, p, units, stream);
+}
+
+// dX = conv_transpose(dY, Wt).  dY [N,H,W,Cout], Wt [Cout,R,S,Cin], dX [N,H,W,Cin], all bf16.
+int conv_same_dgrad(const void* dy, const void* wt, int N, int H, int W, int Cin, int Cout, int R, int S, void* dx,
+                    const void* add, cudaStream_t stream) {
+  int rc = check_conv("conv_dgrad", N, H, W, Cin, Cout, R, S);
+  if (rc) return rc;
+  ConvParams p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad_h = R / 2; p.pad_w = S / 2;
+  plan_box(H, W, kCBM, &p.bw, &p.bh, &p.bn);
+  p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.split_k = 1;
+  p.out = dx;
+  p.add = reinterpret_cast<const __nv_bfloat16*>(add);
+  const int BN = (Cin <= 64) ? 64 : 128;
+  CUtensorMap ta, tb;
+  if ((rc = make_tmap_nhwc(&ta, dy, N, H, W, Cout, 64, p.bw, p.bh, p.bn, 1))) return rc;
+  if ((rc = make_tmap_2d(&tb, wt, 2, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, 64, 64))) return rc;
+  const int units = p.tiles_w * p.tiles_h * p.tiles_n * ((Cin + BN - 1) / BN);
+  return BN == 64 ? launch_conv<64, 1>(ta, tb, p, units, stream) : launch_conv<128, 1>(ta, tb, p, units, stream);
+}
+
+// dW[Cout,R,S,Cin] (fp32) += dY^T * shifted X.
+int conv_same_wgrad(const void* dy, const void* x, int N, int H, int W, int Cin, int Cout, int R, int S, float* dw,
+                    cudaStream_t stream) {
+  int rc = check_conv("conv_wgrad", N, H, W, Cin, Cout, R, S);
+  if (rc) return rc;
+  ConvParams p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad_h = R / 2; p.pad_w = S / 2;
+  plan_box(H, W, 64, &p.bw, &p.bh, &p.bn);
+  p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.out = dw;
+  const int BN = (Cin <= 64) ? 64 : 128;
+  const int num_m = (Cout + kCBM - 1) / kCBM, num_n = (Cin + BN - 1) / BN;
+  const int base_units = num_m * num_n * R * S;
+  const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  // two waves of units when the reduction is long enough to split (>= 8 pixel tiles per split)
+  int split = (2 * sm_count() + base_units - 1) / base_units;
+  if (split > pix_tiles / 8) split = pix_tiles / 8;
+  if (split < 1) split = 1;
+  {
+    const int per = (pix_tiles + split - 1) / split;
+    split = (pix_tiles + per - 1) / per;
+  }
+  p.split_k = split;
+  CUtensorMap ta, tb;
+  if ((rc = make_tmap_nhwc(&ta, dy, N, H, W, Cout, 64, p.bw, p.bh, p.bn, 1))) return rc;
+  if ((rc = make_tmap_nhwc(&tb, x, N, H, W, Cin, 64, p.bw, p.bh, p.bn, 1))) return rc;
+  const int units = base_units * split;
+  return BN == 64 ? launch_conv<64, 2>(ta, tb, p, units, stream) : launch_conv<128, 2>(ta, tb, p, units, stream);
+}
+
+}  // namespace cfl

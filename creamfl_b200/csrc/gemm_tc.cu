@@ -231,7 +231,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
-          if (p.split_k > 1) {
+          if (p.split_k > 1 || p.atomic_out) {
             float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -321,7 +321,7 @@ int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long l
     const int per = (nkb + p.split_k - 1) / p.split_k;
     p.split_k = (nkb + per - 1) / per;
   }
-  if (p.split_k > 1 && (p.out_bf16 || p.act != 0 || p.out2 != nullptr)) {
+  if ((p.split_k > 1 || p.atomic_out) && (p.out_bf16 || p.act != 0 || p.out2 != nullptr)) {
     set_error("gemm_bf16: split-K requires fp32 output without activation");
     return CFL_EINVAL;
   }

@@ -19,6 +19,7 @@ struct GemmParams {
   int add_bf16;
   const __nv_bfloat16* aux;
   long long ld_aux;
+  int atomic_out;  // accumulate into the fp32 output with atomics even when split_k == 1
 };
 int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, GemmParams p,
               cudaStream_t stream);
@@ -43,9 +44,44 @@ int l2norm_fwd(const float*, int, int, float*, void*, float*, cudaStream_t);
 int l2norm_bwd(const float*, const float*, const float*, int, int, float*, cudaStream_t);
 int cast_f32_bf16(const float*, long long, void*, cudaStream_t);
 int scale_by_scalar(float*, long long, const float*, float, cudaStream_t);
+int act_bwd_f32(const float*, const float*, long long, int, void*, cudaStream_t);
 __global__ void sum_finish_kernel(const float* in, int n, float scale, float* out);
 // agg_ops.cu
 int conw_reduce(const float* const*, const float*, int, int, int, float*, float*, cudaStream_t);
 int recall_ranks(const float*, const float*, const long long*, const long long*, int, int, int, int*, void*,
                  size_t, cudaStream_t);
+}  // namespace cfl
+
+namespace cfl {
+// conv_tc.cu
+int conv_same_fprop(const void*, const void*, int, int, int, int, int, int, int, void*, cudaStream_t);
+int conv_same_dgrad(const void*, const void*, int, int, int, int, int, int, int, void*, const void*, cudaStream_t);
+int conv_same_wgrad(const void*, const void*, int, int, int, int, int, int, int, float*, cudaStream_t);
+// nn_ops.cu
+int bn_train_fwd(const void*, long long, int, const float*, const float*, float, float, float*, float*, double*,
+                 float*, float*, float*, float*, const void*, int, void*, cudaStream_t);
+int bn_eval_fwd(const void*, long long, int, const float*, const float*, float, const float*, const float*, float*,
+                float*, const void*, int, void*, cudaStream_t);
+int bn_train_bwd(const void*, const void*, const void*, long long, int, const float*, const float*, const float*,
+                 double*, float*, float*, float*, void*, void*, cudaStream_t);
+int maxpool_fwd(const void*, int, int, int, int, void*, void*, cudaStream_t);
+int maxpool_bwd(const void*, const void*, int, int, int, int, void*, cudaStream_t);
+int im2col_nhwc(const void*, int, int, int, int, int, int, int, int, int, void*, cudaStream_t);
+int im2col_nchw_f32(const float*, int, int, int, int, int, int, int, int, int, void*, cudaStream_t);
+int col2im_nhwc(const void*, int, int, int, int, int, int, int, int, int, const void*, void*, cudaStream_t);
+size_t layernorm_bwd_workspace_bytes(int);
+int layernorm_fwd(const void*, const void*, const float*, const float*, float, int, int, int, void*, float*, float*,
+                  cudaStream_t);
+int layernorm_bwd(const void*, const void*, const void*, const float*, const float*, const float*, int, int, int,
+                  void*, float*, float*, void*, size_t, cudaStream_t);
+int colsum_bf16(const void*, int, int, long long, float*, cudaStream_t);
+int add_bf16(const void*, const void*, long long, void*, cudaStream_t);
+int embed_fwd(const long long*, const long long*, const float*, const float*, const float*, int, int, int, void*,
+              cudaStream_t);
+int embed_bwd(const long long*, const long long*, const void*, int, int, int, float*, float*, float*, cudaStream_t);
+int attn_fwd(const void*, const float*, int, int, int, int, void*, void*, cudaStream_t);
+int attn_bwd(const void*, const void*, const void*, int, int, int, int, void*, cudaStream_t);
+int pie_pool_fwd(const void*, const void*, const float*, int, int, int, int, float*, void*, void*, cudaStream_t);
+int pie_pool_bwd(const void*, const void*, const float*, const float*, const void*, const void*, int, int, int, int,
+                 void*, void*, float*, cudaStream_t);
 }  // namespace cfl

@@ -280,6 +280,15 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, long long n, _
   }
 }
 
+// out = dy * f'(y) from the activation OUTPUT: kind 6 sigmoid, 3 tanh
+__global__ void act_bwd_f32_kernel(const float* __restrict__ dy, const float* __restrict__ y, long long n, int kind,
+                                   __nv_bfloat16* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = y[i];
+  out[i] = __float2bfloat16(dy[i] * (kind == 6 ? v * (1.0f - v) : 1.0f - v * v));
+}
+
 // dQ init for the InfoNCE backward is implicit (P already holds softmax - onehot); this scales fp32 rows.
 __global__ void scale_by_scalar_kernel(float* __restrict__ x, long long n, const float* __restrict__ s,
                                        float c) {
@@ -397,6 +406,11 @@ int cast_f32_bf16(const float* x, long long n, void* y, cudaStream_t st) {
   const long long thr = (n + 3) / 4;
   cast_f32_bf16_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(x, n, reinterpret_cast<__nv_bfloat16*>(y));
   return check_launch("cast_f32_bf16");
+}
+
+int act_bwd_f32(const float* dy, const float* y, long long n, int kind, void* out, cudaStream_t st) {
+  act_bwd_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dy, y, n, kind, reinterpret_cast<__nv_bfloat16*>(out));
+  return check_launch("act_bwd_f32");
 }
 
 int scale_by_scalar(float* x, long long n, const float* s, float c, cudaStream_t st) {

@@ -1,0 +1,1275 @@
+// HBM-bound kernels of the encoder towers: everything between the tensor-core contractions.
+//
+//   bn_*        BatchNorm2d over NHWC bf16 (train: batch statistics in fp64 accumulators; eval: running stats),
+//               fused with ReLU and the residual add of the ResNet blocks
+//               (torchvision ResNet reached from src/networks/models/image_encoder.py:24,55; resnet_client.py:163-201)
+//   maxpool_*   3x3 stride-2 pad-1 max pooling of the ResNet stem
+//   im2col_*    explicit patch matrix for the strided convolutions and the 7x7 stem (feeds gemm_tc)
+//   layernorm_* LayerNorm over the last dimension, bf16 activations, fp32 statistics (HF BertModel, pie_model.py:66)
+//   embed_*     BERT embedding gather (+ position + token type) and its scatter-add backward
+//   attn_*      BERT self-attention for short sequences (L <= 64, head dim 64): one CTA per (sequence, head)
+//   pie_*       PIENet attention pooling over the 7x7 map (pie_model.py:28-40,61-67) and global average pooling
+//
+// All kernels read/write 16 bytes per thread where the layout allows it; reductions use warp shuffles and a fixed
+// per-block order, with fp64 atomics across blocks for the BatchNorm statistics (1.6 M values per channel at B = 128).
+#include "kernels.cuh"
+
+namespace cfl {
+
+// ------------------------------------------------------------------------------------------------ helpers
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ BatchNorm
+// Thread layout of the reduction kernels: C/8 channel groups along x (16-byte loads), pixel rows along y; every
+// thread accumulates fp32 partials over its pixel stride, rows are combined through shared memory, one fp64 atomic
+// per channel per block.
+constexpr int kBnThreads = 256;
+
+// sums[0..C) += sum_p x[p,c] ; sums[C..2C) += sum_p x[p,c]^2
+__global__ void __launch_bounds__(kBnThreads)
+bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, double* __restrict__ sums) {
+  extern __shared__ float sh[];  // [rows][2][C] reduced in place
+  const int groups = C >> 3;
+  const int rows = kBnThreads / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.0f;
+  if (r < rows) {
+    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + p * C + g * 8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        q[i] = fmaf(f[i], f[i], q[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sh[(r * 2 + 0) * C + g * 8 + i] = s[i];
+      sh[(r * 2 + 1) * C + g * 8 + i] = q[i];
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * C; e += kBnThreads) {
+    const int which = e / C, c = e % C;
+    double acc = 0.0;
+    for (int rr = 0; rr < rows; ++rr) acc += (double)sh[(rr * 2 + which) * C + c];
+    atomicAdd(sums + e, acc);
+  }
+}
+
+// Per-channel affine of the normalisation and running-statistics update (torch semantics: biased variance for the
+// normalisation, unbiased for running_var, momentum 0.1).  Zeroes `sums` for the next use.
+__global__ void bn_finalize_kernel(double* __restrict__ sums, long long P, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                   float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sums[c] / (double)P;
+  double var = sums[C + c] / (double)P - m * m;
+  if (var < 0.0) var = 0.0;
+  sums[c] = 0.0;
+  sums[C + c] = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  mean_out[c] = (float)m;
+  rstd_out[c] = rstd;
+  const float sc = gamma[c] * rstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)m * sc;
+  if (running_mean) {
+    const double unbiased = P > 1 ? var * (double)P / (double)(P - 1) : var;
+    running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// eval mode: scale/shift from the running statistics
+__global__ void bn_eval_affine_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      float eps, const float* __restrict__ running_mean,
+                                      const float* __restrict__ running_var, float* __restrict__ scale,
+                                      float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] * rsqrtf(running_var[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] - running_mean[c] * sc;
+}
+
+// y = [relu]( x * scale[c] + shift[c] [+ res] )
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                const __nv_bfloat16* __restrict__ res, int relu, long long total8, int C,
+                __nv_bfloat16* __restrict__ y) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total8) return;
+  const int c0 = (int)((t * 8) % C);
+  float f[8], r[8];
+  unpack8(reinterpret_cast<const bf16x8*>(x)[t], f);
+  const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
+  const float4 h0 = *reinterpret_cast<const float4*>(shift + c0), h1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
+  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const float sf[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sf[i]);
+  if (res) {
+    unpack8(reinterpret_cast<const bf16x8*>(res)[t], r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] += r[i];
+  }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
+  }
+  reinterpret_cast<bf16x8*>(y)[t] = pack8(f);
+}
+
+// sums[0..C) += sum_p g ; sums[C..2C) += sum_p g * xhat    with g = dy * (y > 0 if relu)
+__global__ void __launch_bounds__(kBnThreads)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y /* null: no relu */,
+                     const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, long long P, int C, double* __restrict__ sums) {
+  extern __shared__ float sh[];
+  const int groups = C >> 3;
+  const int rows = kBnThreads / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.0f;
+  if (r < rows) {
+    float mu[8], rs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mu[i] = mean[g * 8 + i];
+      rs[i] = rstd[g * 8 + i];
+    }
+    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
+      float d[8], xv[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dy + p * C + g * 8), d);
+      unpack8(*reinterpret_cast<const bf16x8*>(x + p * C + g * 8), xv);
+      if (y) {
+        float yv[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(y + p * C + g * 8), yv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = yv[i] > 0.0f ? d[i] : 0.0f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += d[i];
+        q[i] = fmaf(d[i], (xv[i] - mu[i]) * rs[i], q[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sh[(r * 2 + 0) * C + g * 8 + i] = s[i];
+      sh[(r * 2 + 1) * C + g * 8 + i] = q[i];
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * C; e += kBnThreads) {
+    const int which = e / C, c = e % C;
+    double acc = 0.0;
+    for (int rr = 0; rr < rows; ++rr) acc += (double)sh[(rr * 2 + which) * C + c];
+    atomicAdd(sums + e, acc);
+  }
+}
+
+// dbeta += S1, dgamma += S2;  coefficients of dx = a*g + b*x + c0 with
+//   a = gamma*rstd, b = -gamma*rstd^2*S2/P, c0 = -a*S1/P - b*mean     (train mode)
+__global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, long long P, int C, const float* __restrict__ gamma,
+                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ coef /* [3, C] */) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s1 = sums[c], s2 = sums[C + c];
+  sums[c] = 0.0;
+  sums[C + c] = 0.0;
+  if (dbeta) dbeta[c] += (float)s1;
+  if (dgamma) dgamma[c] += (float)s2;
+  const double a = (double)gamma[c] * rstd[c];
+  const double b = -a * rstd[c] * s2 / (double)P;
+  coef[c] = (float)a;
+  coef[C + c] = (float)b;
+  coef[2 * C + c] = (float)(-a * s1 / (double)P - b * mean[c]);
+}
+
+// dx = a*g + b*x + c0 ; optionally g itself is written out (gradient of the residual branch)
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                    const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef, long long total8, int C,
+                    __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ g_out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total8) return;
+  const int c0 = (int)((t * 8) % C);
+  float d[8], xv[8];
+  unpack8(reinterpret_cast<const bf16x8*>(dy)[t], d);
+  unpack8(reinterpret_cast<const bf16x8*>(x)[t], xv);
+  if (y) {
+    float yv[8];
+    unpack8(reinterpret_cast<const bf16x8*>(y)[t], yv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = yv[i] > 0.0f ? d[i] : 0.0f;
+  }
+  if (g_out) reinterpret_cast<bf16x8*>(g_out)[t] = pack8(d);
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = fmaf(coef[c0 + i], d[i], fmaf(coef[C + c0 + i], xv[i], coef[2 * C + c0 + i]));
+  reinterpret_cast<bf16x8*>(dx)[t] = pack8(o);
+}
+
+static int bn_check(const char* who, long long P, int C) {
+  if (P <= 0 || C <= 0 || (C & 7) || C > 2048) {
+    set_error("%s: bad shape P=%lld C=%d (C %% 8 == 0, C <= 2048 required)", who, P, C);
+    return CFL_EINVAL;
+  }
+  return CFL_OK;
+}
+
+static int bn_reduce_grid(long long P, int C) {
+  const int rows = kBnThreads / (C >> 3) > 0 ? kBnThreads / (C >> 3) : 1;
+  long long want = (P + (long long)rows * 16 - 1) / ((long long)rows * 16);  // >= 16 pixels per thread
+  const long long cap = (long long)sm_count() * 8;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+int bn_train_fwd(const void* x, long long P, int C, const float* gamma, const float* beta, float eps, float momentum,
+                 float* running_mean, float* running_var, double* sums, float* mean, float* rstd, float* scale,
+                 float* shift, const void* res, int relu, void* y, cudaStream_t st) {
+  int rc = bn_check("bn_train_fwd", P, C);
+  if (rc) return rc;
+  if (C > 8 * kBnThreads) {
+    set_error("bn: C=%d too large", C);
+    return CFL_EINVAL;
+  }
+  const int rows = kBnThreads / (C >> 3);
+  const size_t smem = (size_t)(rows > 0 ? rows : 1) * 2 * C * sizeof(float);
+  bn_stats_kernel<<<bn_reduce_grid(P, C), kBnThreads, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), P, C, sums);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, beta, eps, momentum, running_mean,
+                                                       running_var, mean, rstd, scale, shift);
+  const long long total8 = P * C / 8;
+  bn_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(res), relu,
+      total8, C, reinterpret_cast<__nv_bfloat16*>(y));
+  return check_launch("bn_train_fwd");
+}
+
+int bn_eval_fwd(const void* x, long long P, int C, const float* gamma, const float* beta, float eps,
+                const float* running_mean, const float* running_var, float* scale, float* shift, const void* res,
+                int relu, void* y, cudaStream_t st) {
+  int rc = bn_check("bn_eval_fwd", P, C);
+  if (rc) return rc;
+  bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, eps, running_mean, running_var, scale, shift);
+  const long long total8 = P * C / 8;
+  bn_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(res), relu,
+      total8, C, reinterpret_cast<__nv_bfloat16*>(y));
+  return check_launch("bn_eval_fwd");
+}
+
+int bn_train_bwd(const void* dy, const void* y_or_null, const void* x, long long P, int C, const float* gamma,
+                 const float* mean, const float* rstd, double* sums, float* coef, float* dgamma, float* dbeta,
+                 void* dx, void* g_out, cudaStream_t st) {
+  int rc = bn_check("bn_train_bwd", P, C);
+  if (rc) return rc;
+  const int rows = kBnThreads / (C >> 3);
+  const size_t smem = (size_t)(rows > 0 ? rows : 1) * 2 * C * sizeof(float);
+  bn_bwd_reduce_kernel<<<bn_reduce_grid(P, C), kBnThreads, smem, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_or_null),
+      reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, P, C, sums);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, mean, rstd, dgamma, dbeta, coef);
+  const long long total8 = P * C / 8;
+  bn_bwd_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_or_null),
+      reinterpret_cast<const __nv_bfloat16*>(x), coef, total8, C, reinterpret_cast<__nv_bfloat16*>(dx),
+      reinterpret_cast<__nv_bfloat16*>(g_out));
+  return check_launch("bn_train_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------ max pooling
+// 3x3, stride 2, pad 1 (torchvision ResNet stem).  idx stores the winning tap (0..8) per output element.
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int Ho, int Wo,
+                   __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx) {
+  const int groups = C >> 3;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * Ho * Wo * groups;
+  if (t >= total) return;
+  const int g = (int)(t % groups);
+  long long pix = t / groups;
+  const int wo = (int)(pix % Wo); pix /= Wo;
+  const int ho = (int)(pix % Ho);
+  const int n = (int)(pix / Ho);
+  float best[8];
+  int bi[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; bi[i] = 0; }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int h = ho * 2 + r - 1;
+    if (h < 0 || h >= H) continue;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int w = wo * 2 + s - 1;
+      if (w < 0 || w >= W) continue;
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + (((long long)n * H + h) * W + w) * C + g * 8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (f[i] > best[i]) { best[i] = f[i]; bi[i] = r * 3 + s; }
+    }
+  }
+  const long long o = (((long long)n * Ho + ho) * Wo + wo) * C + g * 8;
+  *reinterpret_cast<bf16x8*>(y + o) = pack8(best);
+  if (idx) {
+    uint2 pk;
+    pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    *reinterpret_cast<uint2*>(idx + o) = pk;
+  }
+}
+
+// gather form: every input element collects from the (<= 4) windows that contain it
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx, int N, int H, int W, int C,
+                   int Ho, int Wo, __nv_bfloat16* __restrict__ dx) {
+  const int groups = C >> 3;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * H * W * groups;
+  if (t >= total) return;
+  const int g = (int)(t % groups);
+  long long pix = t / groups;
+  const int w = (int)(pix % W); pix /= W;
+  const int h = (int)(pix % H);
+  const int n = (int)(pix / H);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  for (int r = 0; r < 3; ++r) {
+    const int hn = h + 1 - r;
+    if (hn < 0 || (hn & 1)) continue;
+    const int ho = hn >> 1;
+    if (ho >= Ho) continue;
+    for (int s = 0; s < 3; ++s) {
+      const int wn = w + 1 - s;
+      if (wn < 0 || (wn & 1)) continue;
+      const int wo = wn >> 1;
+      if (wo >= Wo) continue;
+      const long long o = (((long long)n * Ho + ho) * Wo + wo) * C + g * 8;
+      const uint2 pk = *reinterpret_cast<const uint2*>(idx + o);
+      float d[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dy + o), d);
+      const int tap = r * 3 + s;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int who = ((i < 4 ? pk.x : pk.y) >> (8 * (i & 3))) & 0xff;
+        if (who == tap) acc[i] += d[i];
+      }
+    }
+  }
+  *reinterpret_cast<bf16x8*>(dx + ((((long long)n * H + h) * W + w) * C + g * 8)) = pack8(acc);
+}
+
+int maxpool_fwd(const void* x, int N, int H, int W, int C, void* y, void* idx, cudaStream_t st) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7)) {
+    set_error("maxpool_fwd: bad shape");
+    return CFL_EINVAL;
+  }
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)N * Ho * Wo * (C >> 3);
+  maxpool_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, Ho, Wo, reinterpret_cast<__nv_bfloat16*>(y),
+      reinterpret_cast<uint8_t*>(idx));
+  return check_launch("maxpool_fwd");
+}
+
+int maxpool_bwd(const void* dy, const void* idx, int N, int H, int W, int C, void* dx, cudaStream_t st) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7)) {
+    set_error("maxpool_bwd: bad shape");
+    return CFL_EINVAL;
+  }
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)N * H * W * (C >> 3);
+  maxpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const uint8_t*>(idx), N, H, W, C, Ho, Wo,
+      reinterpret_cast<__nv_bfloat16*>(dx));
+  return check_launch("maxpool_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------ im2col
+// col[p, (r, s, c)] for NHWC bf16 input; rows have pitch ldc >= R*S*C (tail columns are zero-filled).
+__global__ void __launch_bounds__(256)
+im2col_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int R, int S, int stride, int pad,
+                   int Ho, int Wo, int ldc, __nv_bfloat16* __restrict__ col) {
+  const int groups = C >> 3;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * Ho * Wo * R * S * groups;
+  if (t >= total) return;
+  const int g = (int)(t % groups);
+  long long q = t / groups;
+  const int tap = (int)(q % (R * S)); q /= (R * S);
+  const long long pix = q;
+  const int wo = (int)(q % Wo); q /= Wo;
+  const int ho = (int)(q % Ho);
+  const int n = (int)(q / Ho);
+  const int h = ho * stride + tap / S - pad, w = wo * stride + tap % S - pad;
+  bf16x8 v;
+  if (h >= 0 && h < H && w >= 0 && w < W)
+    v = *reinterpret_cast<const bf16x8*>(x + (((long long)n * H + h) * W + w) * C + g * 8);
+  else
+    for (int i = 0; i < 4; ++i) v.v[i] = __floats2bfloat162_rn(0.f, 0.f);
+  *reinterpret_cast<bf16x8*>(col + pix * ldc + (long long)tap * C + g * 8) = v;
+}
+
+// Stem: fp32 NCHW images straight to the bf16 patch matrix (fuses the layout change and the cast).
+// Column order (r, s, c) to match [Cout, R, S, Cin] filters; one thread per (pixel, tap).
+__global__ void __launch_bounds__(256)
+im2col_nchw_f32_kernel(const float* __restrict__ x, int N, int C, int H, int W, int R, int S, int stride, int pad,
+                       int Ho, int Wo, int ldc, __nv_bfloat16* __restrict__ col) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int taps = R * S;
+  const int slots = ldc / C;  // taps plus zero-padding slots (tail handled below)
+  const long long total = (long long)N * Ho * Wo * slots;
+  if (t >= total) return;
+  const int tap = (int)(t % slots);
+  long long q = t / slots;
+  const long long pix = q;
+  const int wo = (int)(q % Wo); q /= Wo;
+  const int ho = (int)(q % Ho);
+  const int n = (int)(q / Ho);
+  __nv_bfloat16* dst = col + pix * ldc + (long long)tap * C;
+  if (tap >= taps) {
+    for (int c = 0; c < C; ++c) dst[c] = __float2bfloat16(0.f);
+    if (tap == slots - 1)
+      for (int c = slots * C; c < ldc; ++c) col[pix * ldc + c] = __float2bfloat16(0.f);
+    return;
+  }
+  const int h = ho * stride + tap / S - pad, w = wo * stride + tap % S - pad;
+  const bool ok = h >= 0 && h < H && w >= 0 && w < W;
+  for (int c = 0; c < C; ++c)
+    dst[c] = __float2bfloat16(ok ? x[(((long long)n * C + c) * H + h) * W + w] : 0.f);
+  if (tap == slots - 1)
+    for (int c = slots * C; c < ldc; ++c) col[pix * ldc + c] = __float2bfloat16(0.f);
+}
+
+// dX (NHWC bf16) from dcol: gather over the taps that touch each input pixel.
+__global__ void __launch_bounds__(256)
+col2im_nhwc_kernel(const __nv_bfloat16* __restrict__ dcol, int N, int H, int W, int C, int R, int S, int stride,
+                   int pad, int Ho, int Wo, int ldc, const __nv_bfloat16* __restrict__ add,
+                   __nv_bfloat16* __restrict__ dx) {
+  const int groups = C >> 3;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * H * W * groups;
+  if (t >= total) return;
+  const int g = (int)(t % groups);
+  long long q = t / groups;
+  const int w = (int)(q % W); q /= W;
+  const int h = (int)(q % H);
+  const int n = (int)(q / H);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  for (int r = 0; r < R; ++r) {
+    const int hn = h + pad - r;
+    if (hn < 0 || hn % stride) continue;
+    const int ho = hn / stride;
+    if (ho >= Ho) continue;
+    for (int s = 0; s < S; ++s) {
+      const int wn = w + pad - s;
+      if (wn < 0 || wn % stride) continue;
+      const int wo = wn / stride;
+      if (wo >= Wo) continue;
+      float d[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dcol + (((long long)n * Ho + ho) * Wo + wo) * ldc +
+                                               (long long)(r * S + s) * C + g * 8), d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += d[i];
+    }
+  }
+  if (add) {
+    float a[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(add + ((((long long)n * H + h) * W + w) * C + g * 8)), a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += a[i];
+  }
+  *reinterpret_cast<bf16x8*>(dx + ((((long long)n * H + h) * W + w) * C + g * 8)) = pack8(acc);
+}
+
+int im2col_nhwc(const void* x, int N, int H, int W, int C, int R, int S, int stride, int pad, int ldc, void* col,
+                cudaStream_t st) {
+  if ((C & 7) || ldc < R * S * C || (ldc & 7)) {
+    set_error("im2col_nhwc: C %% 8 and pitch constraints violated (C=%d ldc=%d)", C, ldc);
+    return CFL_EINVAL;
+  }
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  const long long total = (long long)N * Ho * Wo * R * S * (C >> 3);
+  if (ldc > R * S * C) cudaMemsetAsync(col, 0, (size_t)N * Ho * Wo * ldc * 2, st);
+  im2col_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, R, S, stride, pad, Ho, Wo, ldc,
+      reinterpret_cast<__nv_bfloat16*>(col));
+  return check_launch("im2col_nhwc");
+}
+
+int im2col_nchw_f32(const float* x, int N, int C, int H, int W, int R, int S, int stride, int pad, int ldc, void* col,
+                    cudaStream_t st) {
+  if (ldc < R * S * C) {
+    set_error("im2col_nchw_f32: pitch %d < %d", ldc, R * S * C);
+    return CFL_EINVAL;
+  }
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  const int slots = ldc / C;
+  const long long total = (long long)N * Ho * Wo * slots;
+  im2col_nchw_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      x, N, C, H, W, R, S, stride, pad, Ho, Wo, ldc, reinterpret_cast<__nv_bfloat16*>(col));
+  return check_launch("im2col_nchw_f32");
+}
+
+int col2im_nhwc(const void* dcol, int N, int H, int W, int C, int R, int S, int stride, int pad, int ldc,
+                const void* add, void* dx, cudaStream_t st) {
+  if ((C & 7) || (ldc & 7)) {
+    set_error("col2im_nhwc: C %% 8 required");
+    return CFL_EINVAL;
+  }
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  const long long total = (long long)N * H * W * (C >> 3);
+  col2im_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dcol), N, H, W, C, R, S, stride, pad, Ho, Wo, ldc,
+      reinterpret_cast<const __nv_bfloat16*>(add), reinterpret_cast<__nv_bfloat16*>(dx));
+  return check_launch("col2im_nhwc");
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// One warp per row; D <= 1024, D % 8 == 0.  x (+ optional residual) in bf16 or fp32; statistics in fp32.
+template <typename TIn>
+__device__ __forceinline__ void load8(const TIn* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  unpack8(*reinterpret_cast<const bf16x8*>(p), f);
+}
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <typename TOut>
+__device__ __forceinline__ void store8(TOut* p, const float (&f)[8]);
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[8]) {
+  *reinterpret_cast<bf16x8*>(p) = pack8(f);
+}
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+constexpr int kLnMaxChunks = 4;  // 32 lanes * 8 values * 4 = D up to 1024
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, int R, int D, T* __restrict__ y,
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  float v[kLnMaxChunks][8];
+  float s = 0.0f;
+#pragma unroll
+  for (int c = 0; c < kLnMaxChunks; ++c) {
+    const int k = (c * 32 + lane) * 8;
+    if (k < D) {
+      load8<T>(x + (long long)row * D + k, v[c]);
+      if (res) {
+        float r[8];
+        load8<T>(res + (long long)row * D + k, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[c][i] += r[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[c][i];
+    }
+  }
+  const float mean = warp_sum_f(s) / (float)D;
+  float q = 0.0f;
+#pragma unroll
+  for (int c = 0; c < kLnMaxChunks; ++c) {
+    const int k = (c * 32 + lane) * 8;
+    if (k < D) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[c][i] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum_f(q) / (float)D + eps);
+#pragma unroll
+  for (int c = 0; c < kLnMaxChunks; ++c) {
+    const int k = (c * 32 + lane) * 8;
+    if (k < D) {
+      float g[8], b[8], o[8];
+      load8<float>(gamma + k, g);
+      load8<float>(beta + k, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf((v[c][i] - mean) * rstd, g[i], b[i]);
+      store8<T>(y + (long long)row * D + k, o);
+    }
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+// Backward from the OUTPUT y (xhat = (y - beta) / gamma would lose precision; instead the caller keeps the LN input
+// sum `xin` = x + res).  dx = rstd * (gy*gamma - mean(gy*gamma) - xhat * mean(gy*gamma*xhat)).
+// dgamma/dbeta partials: one row of [2, D] per block, reduced by ln_param_reduce_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ xin, const T* __restrict__ res_in,
+                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     int R, int D, T* __restrict__ dx, float* __restrict__ part /* [gridDim.x, 2, D] */) {
+  extern __shared__ float sh[];  // [warps][2][D]
+  const int warps = blockDim.x >> 5;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float ag[kLnMaxChunks][8], ab[kLnMaxChunks][8];
+#pragma unroll
+  for (int c = 0; c < kLnMaxChunks; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ag[c][i] = ab[c][i] = 0.0f;
+  for (int row = blockIdx.x * warps + w; row < R; row += gridDim.x * warps) {
+    const float mu = mean[row], rs = rstd[row];
+    float g[kLnMaxChunks][8], xh[kLnMaxChunks][8];
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kLnMaxChunks; ++c) {
+      const int k = (c * 32 + lane) * 8;
+      if (k < D) {
+        float d[8], xv[8], gm[8];
+        load8<T>(dy + (long long)row * D + k, d);
+        load8<T>(xin + (long long)row * D + k, xv);
+        if (res_in) {
+          float r[8];
+          load8<T>(res_in + (long long)row * D + k, r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xv[i] += r[i];
+        }
+        load8<float>(gamma + k, gm);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[c][i] = (xv[i] - mu) * rs;
+          ag[c][i] = fmaf(d[i], xh[c][i], ag[c][i]);
+          ab[c][i] += d[i];
+          g[c][i] = d[i] * gm[i];
+          s1 += g[c][i];
+          s2 = fmaf(g[c][i], xh[c][i], s2);
+        }
+      }
+    }
+    s1 = warp_sum_f(s1) / (float)D;
+    s2 = warp_sum_f(s2) / (float)D;
+#pragma unroll
+    for (int c = 0; c < kLnMaxChunks; ++c) {
+      const int k = (c * 32 + lane) * 8;
+      if (k < D) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rs * (g[c][i] - s1 - xh[c][i] * s2);
+        store8<T>(dx + (long long)row * D + k, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kLnMaxChunks; ++c) {
+    const int k = (c * 32 + lane) * 8;
+    if (k < D) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sh[(w * 2 + 0) * D + k + i] = ag[c][i];
+        sh[(w * 2 + 1) * D + k + i] = ab[c][i];
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * D; e += blockDim.x) {
+    const int which = e / D, k = e % D;
+    float acc = 0.0f;
+    for (int ww = 0; ww < warps; ++ww) acc += sh[(ww * 2 + which) * D + k];
+    part[((long long)blockIdx.x * 2 + which) * D + k] = acc;
+  }
+}
+
+// dgamma[k] += sum_b part[b,0,k]; dbeta[k] += sum_b part[b,1,k]   (fixed order)
+__global__ void ln_param_reduce_kernel(const float* __restrict__ part, int blocks, int D, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 2 * D) return;
+  const int which = e / D, k = e % D;
+  float acc = 0.0f;
+  for (int b = 0; b < blocks; ++b) acc += part[((long long)b * 2 + which) * D + k];
+  if (which == 0) {
+    if (dgamma) dgamma[k] += acc;
+  } else {
+    if (dbeta) dbeta[k] += acc;
+  }
+}
+
+constexpr int kLnBwdBlocks = 148;
+
+size_t layernorm_bwd_workspace_bytes(int D) { return (size_t)kLnBwdBlocks * 2 * D * sizeof(float); }
+
+int layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, float eps, int R, int D,
+                  int is_bf16, void* y, float* mean, float* rstd, cudaStream_t st) {
+  if (R <= 0 || D <= 0 || (D & 7) || D > kLnMaxChunks * 256) {
+    set_error("layernorm_fwd: bad shape R=%d D=%d (D %% 8 == 0, D <= %d)", R, D, kLnMaxChunks * 256);
+    return CFL_EINVAL;
+  }
+  const int grid = (R + 7) / 8;
+  if (is_bf16)
+    layernorm_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(res), gamma, beta, eps, R, D,
+        reinterpret_cast<__nv_bfloat16*>(y), mean, rstd);
+  else
+    layernorm_fwd_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x),
+                                                      reinterpret_cast<const float*>(res), gamma, beta, eps, R, D,
+                                                      reinterpret_cast<float*>(y), mean, rstd);
+  return check_launch("layernorm_fwd");
+}
+
+int layernorm_bwd(const void* dy, const void* xin, const void* res_in, const float* gamma, const float* mean,
+                  const float* rstd, int R, int D, int is_bf16, void* dx, float* dgamma, float* dbeta, void* ws,
+                  size_t ws_bytes, cudaStream_t st) {
+  if (R <= 0 || D <= 0 || (D & 7) || D > kLnMaxChunks * 256) {
+    set_error("layernorm_bwd: bad shape R=%d D=%d", R, D);
+    return CFL_EINVAL;
+  }
+  if (ws_bytes < layernorm_bwd_workspace_bytes(D)) {
+    set_error("layernorm_bwd: workspace too small");
+    return CFL_EWORKSPACE;
+  }
+  int blocks = (R + 7) / 8;
+  if (blocks > kLnBwdBlocks) blocks = kLnBwdBlocks;
+  const size_t smem = (size_t)8 * 2 * D * sizeof(float);
+  float* part = reinterpret_cast<float*>(ws);
+  if (is_bf16) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(layernorm_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    layernorm_bwd_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(xin),
+        reinterpret_cast<const __nv_bfloat16*>(res_in), gamma, mean, rstd, R, D, reinterpret_cast<__nv_bfloat16*>(dx),
+        part);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    layernorm_bwd_kernel<float><<<blocks, 256, smem, st>>>(
+        reinterpret_cast<const float*>(dy), reinterpret_cast<const float*>(xin), reinterpret_cast<const float*>(res_in),
+        gamma, mean, rstd, R, D, reinterpret_cast<float*>(dx), part);
+  }
+  ln_param_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, st>>>(part, blocks, D, dgamma, dbeta);
+  return check_launch("layernorm_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+// out[n] += sum_m x[m, n]  (bias gradients).  x bf16 [M, N], N % 8 == 0.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, long long ld, float* __restrict__ out) {
+  // block = 32 column groups (256 columns) x 8 row lanes
+  __shared__ float sh[8][256 + 8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + cg * 8;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  if (col < N) {
+    for (int m = blockIdx.y * 8 + rl; m < M; m += gridDim.y * 8) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + (long long)m * ld + col), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sh[rl][cg * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < N) {
+    float s = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += sh[r][c];
+    atomicAdd(out + blockIdx.x * 256 + c, s);
+  }
+}
+
+int colsum_bf16(const void* x, int M, int N, long long ld, float* out, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || (N & 7) || (ld & 7)) {
+    set_error("colsum: bad shape M=%d N=%d", M, N);
+    return CFL_EINVAL;
+  }
+  int gy = (M + 255) / 256;
+  if (gy > 64) gy = 64;
+  colsum_kernel<<<dim3((N + 255) / 256, gy), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, N, ld, out);
+  return check_launch("colsum");
+}
+
+// ------------------------------------------------------------------------------------------------ BERT embeddings
+// h[t, :] = word[ids[t]] + pos[t % L] + type[tt[t]]   (fp32 tables, bf16 out); LayerNorm follows as its own kernel.
+__global__ void __launch_bounds__(256)
+embed_fwd_kernel(const long long* __restrict__ ids, const long long* __restrict__ tt, const float* __restrict__ word,
+                 const float* __restrict__ pos, const float* __restrict__ type, int T, int L, int D,
+                 __nv_bfloat16* __restrict__ out) {
+  const int groups = D >> 3;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)T * groups) return;
+  const int tok = (int)(t / groups), k = (int)(t % groups) * 8;
+  float a[8], b[8], c[8];
+  load8<float>(word + ids[tok] * D + k, a);
+  load8<float>(pos + (long long)(tok % L) * D + k, b);
+  load8<float>(type + (tt ? tt[tok] : 0) * D + k, c);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] += b[i] + c[i];
+  *reinterpret_cast<bf16x8*>(out + (long long)tok * D + k) = pack8(a);
+}
+
+__global__ void __launch_bounds__(256)
+embed_bwd_kernel(const long long* __restrict__ ids, const long long* __restrict__ tt, const __nv_bfloat16* __restrict__ dh,
+                 int T, int L, int D, float* __restrict__ dword, float* __restrict__ dpos, float* __restrict__ dtype) {
+  const int groups = D >> 3;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)T * groups) return;
+  const int tok = (int)(t / groups), k = (int)(t % groups) * 8;
+  float d[8];
+  unpack8(*reinterpret_cast<const bf16x8*>(dh + (long long)tok * D + k), d);
+  float* w = dword + ids[tok] * D + k;
+  float* p = dpos + (long long)(tok % L) * D + k;
+  float* y = dtype + (tt ? tt[tok] : 0) * D + k;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(w + i, d[i]);
+    atomicAdd(p + i, d[i]);
+    atomicAdd(y + i, d[i]);
+  }
+}
+
+int embed_fwd(const long long* ids, const long long* tt, const float* word, const float* pos, const float* type, int T,
+              int L, int D, void* out, cudaStream_t st) {
+  if (T <= 0 || L <= 0 || (D & 7)) {
+    set_error("embed_fwd: bad shape");
+    return CFL_EINVAL;
+  }
+  const long long n = (long long)T * (D >> 3);
+  embed_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ids, tt, word, pos, type, T, L, D,
+                                                                reinterpret_cast<__nv_bfloat16*>(out));
+  return check_launch("embed_fwd");
+}
+
+int embed_bwd(const long long* ids, const long long* tt, const void* dh, int T, int L, int D, float* dword, float* dpos,
+              float* dtype, cudaStream_t st) {
+  if (T <= 0 || L <= 0 || (D & 7)) {
+    set_error("embed_bwd: bad shape");
+    return CFL_EINVAL;
+  }
+  const long long n = (long long)T * (D >> 3);
+  embed_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ids, tt, reinterpret_cast<const __nv_bfloat16*>(dh), T,
+                                                                L, D, dword, dpos, dtype);
+  return check_launch("embed_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------ BERT attention
+// qkv [B*L, 3*H*64] bf16 (Q | K | V blocks of H*64 columns), mask [B, L] (1 = attend), ctx [B*L, H*64] bf16,
+// probs [B, H, L, L] bf16 kept for the backward.  One CTA of 128 threads per (sequence, head); L <= 64.
+constexpr int kAttD = 64;
+constexpr int kAttMaxL = 64;
+
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ mask, int L, int H, float scale,
+                __nv_bfloat16* __restrict__ ctx, __nv_bfloat16* __restrict__ probs) {
+  extern __shared__ float att_sm[];
+  typedef float (*RowD)[kAttD + 1];
+  typedef float (*RowL)[kAttMaxL + 1];
+  RowD sq = reinterpret_cast<RowD>(att_sm);
+  RowD sk = sq + L;
+  RowD sv = sk + L;
+  RowL sp = reinterpret_cast<RowL>(sv + L);
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int ld = 3 * H * kAttD;
+  const __nv_bfloat16* base = qkv + (long long)b * L * ld + h * kAttD;
+  for (int e = threadIdx.x; e < L * (kAttD / 8); e += blockDim.x) {
+    const int r = e / (kAttD / 8), k = (e % (kAttD / 8)) * 8;
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)r * ld + k), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sq[r][k + i] = f[i];
+    unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)r * ld + H * kAttD + k), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sk[r][k + i] = f[i];
+    unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)r * ld + 2 * H * kAttD + k), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sv[r][k + i] = f[i];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
+    const int i = e / L, j = e % L;
+    float acc = 0.0f;
+#pragma unroll 16
+    for (int k = 0; k < kAttD; ++k) acc = fmaf(sq[i][k], sk[j][k], acc);
+    // HF extended attention mask: (1 - mask) * finfo.min added to the scores
+    sp[i][j] = acc * scale + (mask[b * L + j] > 0.5f ? 0.0f : -3.0e38f);
+  }
+  __syncthreads();
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = w; i < L; i += 4) {
+    float m = -INFINITY;
+    for (int j = lane; j < L; j += 32) m = fmaxf(m, sp[i][j]);
+    m = warp_max_f(m);
+    float s = 0.0f;
+    for (int j = lane; j < L; j += 32) {
+      const float e = __expf(sp[i][j] - m);
+      sp[i][j] = e;
+      s += e;
+    }
+    s = warp_sum_f(s);
+    const float inv = 1.0f / s;
+    for (int j = lane; j < L; j += 32) {
+      // round to bf16 once: forward PV product and the backward use the very same probabilities
+      const __nv_bfloat16 pb = __float2bfloat16(sp[i][j] * inv);
+      sp[i][j] = __bfloat162float(pb);
+      probs[(((long long)b * H + h) * L + i) * L + j] = pb;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < L * (kAttD / 2); e += blockDim.x) {
+    const int i = e / (kAttD / 2), k = (e % (kAttD / 2)) * 2;
+    float a0 = 0.0f, a1 = 0.0f;
+    for (int j = 0; j < L; ++j) {
+      a0 = fmaf(sp[i][j], sv[j][k], a0);
+      a1 = fmaf(sp[i][j], sv[j][k + 1], a1);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(ctx + ((long long)b * L + i) * (H * kAttD) + h * kAttD + k) =
+        __floats2bfloat162_rn(a0, a1);
+  }
+}
+
+// dqkv [B*L, 3*H*64] bf16 from dctx [B*L, H*64], the saved probabilities and qkv.
+__global__ void __launch_bounds__(128)
+attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ probs,
+                const __nv_bfloat16* __restrict__ dctx, int L, int H, float scale, __nv_bfloat16* __restrict__ dqkv) {
+  extern __shared__ float att_sm[];
+  typedef float (*RowD)[kAttD + 1];
+  typedef float (*RowL)[kAttMaxL + 1];
+  RowD sq = reinterpret_cast<RowD>(att_sm);
+  RowD sk = sq + L;
+  RowD sv = sk + L;
+  RowD sdo = sv + L;
+  RowL sp = reinterpret_cast<RowL>(sdo + L);
+  RowL sds = sp + L;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int ld = 3 * H * kAttD;
+  const __nv_bfloat16* base = qkv + (long long)b * L * ld + h * kAttD;
+  for (int e = threadIdx.x; e < L * (kAttD / 8); e += blockDim.x) {
+    const int r = e / (kAttD / 8), k = (e % (kAttD / 8)) * 8;
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)r * ld + k), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sq[r][k + i] = f[i];
+    unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)r * ld + H * kAttD + k), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sk[r][k + i] = f[i];
+    unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)r * ld + 2 * H * kAttD + k), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sv[r][k + i] = f[i];
+    unpack8(*reinterpret_cast<const bf16x8*>(dctx + ((long long)b * L + r) * (H * kAttD) + h * kAttD + k), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sdo[r][k + i] = f[i];
+  }
+  for (int e = threadIdx.x; e < L * L; e += blockDim.x)
+    sp[e / L][e % L] = __bfloat162float(probs[((long long)b * H + h) * L * L + e]);
+  __syncthreads();
+  // dP = dO V^T
+  for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
+    const int i = e / L, j = e % L;
+    float acc = 0.0f;
+#pragma unroll 16
+    for (int k = 0; k < kAttD; ++k) acc = fmaf(sdo[i][k], sv[j][k], acc);
+    sds[i][j] = acc;
+  }
+  __syncthreads();
+  // dS = P * (dP - rowsum(dP * P)) * scale
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = w; i < L; i += 4) {
+    float s = 0.0f;
+    for (int j = lane; j < L; j += 32) s = fmaf(sds[i][j], sp[i][j], s);
+    s = warp_sum_f(s);
+    for (int j = lane; j < L; j += 32) sds[i][j] = sp[i][j] * (sds[i][j] - s) * scale;
+  }
+  __syncthreads();
+  __nv_bfloat16* obase = dqkv + (long long)b * L * ld + h * kAttD;
+  for (int e = threadIdx.x; e < L * (kAttD / 2); e += blockDim.x) {
+    const int i = e / (kAttD / 2), k = (e % (kAttD / 2)) * 2;
+    float q0 = 0.f, q1 = 0.f, k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+    for (int j = 0; j < L; ++j) {
+      q0 = fmaf(sds[i][j], sk[j][k], q0);
+      q1 = fmaf(sds[i][j], sk[j][k + 1], q1);
+      k0 = fmaf(sds[j][i], sq[j][k], k0);
+      k1 = fmaf(sds[j][i], sq[j][k + 1], k1);
+      v0 = fmaf(sp[j][i], sdo[j][k], v0);
+      v1 = fmaf(sp[j][i], sdo[j][k + 1], v1);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(obase + (long long)i * ld + k) = __floats2bfloat162_rn(q0, q1);
+    *reinterpret_cast<__nv_bfloat162*>(obase + (long long)i * ld + H * kAttD + k) = __floats2bfloat162_rn(k0, k1);
+    *reinterpret_cast<__nv_bfloat162*>(obase + (long long)i * ld + 2 * H * kAttD + k) = __floats2bfloat162_rn(v0, v1);
+  }
+}
+
+int attn_fwd(const void* qkv, const float* mask, int B, int L, int H, int dh, void* ctx, void* probs, cudaStream_t st) {
+  if (B <= 0 || L <= 0 || L > kAttMaxL || dh != kAttD || H <= 0) {
+    set_error("attn_fwd: unsupported shape B=%d L=%d H=%d dh=%d (L <= %d, head dim %d)", B, L, H, dh, kAttMaxL, kAttD);
+    return CFL_EINVAL;
+  }
+  static bool set = false;
+  if (!set) {
+    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)((3 * kAttMaxL * (kAttD + 1) + kAttMaxL * (kAttMaxL + 1)) * sizeof(float)));
+    set = true;
+  }
+  const size_t smem = (size_t)(3 * L * (kAttD + 1) + L * (kAttMaxL + 1)) * sizeof(float);
+  attn_fwd_kernel<<<B * H, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), mask, L, H, 0.125f,
+                                         reinterpret_cast<__nv_bfloat16*>(ctx), reinterpret_cast<__nv_bfloat16*>(probs));
+  return check_launch("attn_fwd");
+}
+
+int attn_bwd(const void* qkv, const void* probs, const void* dctx, int B, int L, int H, int dh, void* dqkv,
+             cudaStream_t st) {
+  if (B <= 0 || L <= 0 || L > kAttMaxL || dh != kAttD || H <= 0) {
+    set_error("attn_bwd: unsupported shape");
+    return CFL_EINVAL;
+  }
+  static bool set = false;
+  if (!set) {
+    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)((4 * kAttMaxL * (kAttD + 1) + 2 * kAttMaxL * (kAttMaxL + 1)) * sizeof(float)));
+    set = true;
+  }
+  const size_t smem = (size_t)(4 * L * (kAttD + 1) + 2 * L * (kAttMaxL + 1)) * sizeof(float);
+  attn_bwd_kernel<<<B * H, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                         reinterpret_cast<const __nv_bfloat16*>(probs),
+                                         reinterpret_cast<const __nv_bfloat16*>(dctx), L, H, 0.125f,
+                                         reinterpret_cast<__nv_bfloat16*>(dqkv));
+  return check_launch("attn_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------ PIE pooling
+// Per image: a[p] = <h[p,:], w2>, attn = softmax_p(a), r = sum_p attn[p] x[p,:], pooled = mean_p x[p,:].
+// x [B, P, C] bf16 (the NHWC 7x7 map), h [B, P, Hd] bf16 = tanh(x W1^T).  One CTA per image.
+__global__ void __launch_bounds__(256)
+pie_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ h,
+                    const float* __restrict__ w2, int P, int C, int Hd, float* __restrict__ attn /* [B, P] */,
+                    __nv_bfloat16* __restrict__ r_out /* [B, C] */, __nv_bfloat16* __restrict__ pooled /* [B, C] */) {
+  __shared__ float sa[64];
+  const int b = blockIdx.x;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int p = w; p < P; p += 8) {
+    float acc = 0.0f;
+    const __nv_bfloat16* hr = h + ((long long)b * P + p) * Hd;
+    for (int k = lane * 8; k < Hd; k += 256) {
+      float f[8], g[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(hr + k), f);
+      load8<float>(w2 + k, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc = fmaf(f[i], g[i], acc);
+    }
+    acc = warp_sum_f(acc);
+    if (lane == 0) sa[p] = acc;
+  }
+  __syncthreads();
+  if (w == 0) {
+    float m = -INFINITY;
+    for (int p = lane; p < P; p += 32) m = fmaxf(m, sa[p]);
+    m = warp_max_f(m);
+    float s = 0.0f;
+    for (int p = lane; p < P; p += 32) s += __expf(sa[p] - m);
+    s = warp_sum_f(s);
+    for (int p = lane; p < P; p += 32) {
+      const float a = __expf(sa[p] - m) / s;
+      sa[p] = a;
+      attn[(long long)b * P + p] = a;
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x * 8; k < C; k += 256 * 8) {
+    float r[8], m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = m[i] = 0.0f;
+    for (int p = 0; p < P; ++p) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + ((long long)b * P + p) * C + k), f);
+      const float a = sa[p];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        r[i] = fmaf(a, f[i], r[i]);
+        m[i] += f[i];
+      }
+    }
+    const float invp = 1.0f / (float)P;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] *= invp;
+    *reinterpret_cast<bf16x8*>(r_out + (long long)b * C + k) = pack8(r);
+    *reinterpret_cast<bf16x8*>(pooled + (long long)b * C + k) = pack8(m);
+  }
+}
+
+// Backward of the pooling: given d_r, d_pooled [B, C] (bf16):
+//   dx[p,:]   = attn[p] * d_r + d_pooled / P                    (bf16; the W1 path is added by the dgrad GEMM)
+//   dattn[p]  = <d_r, x[p,:]> ;  da = attn * (dattn - sum attn*dattn)
+//   dpre[p,:] = da[p] * w2 * (1 - h[p,:]^2)                     (bf16, gradient at the tanh pre-activation)
+//   dw2      += sum_p da[p] * h[p,:]
+__global__ void __launch_bounds__(256)
+pie_pool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ h,
+                    const float* __restrict__ w2, const float* __restrict__ attn, const __nv_bfloat16* __restrict__ d_r,
+                    const __nv_bfloat16* __restrict__ d_pooled, int P, int C, int Hd, __nv_bfloat16* __restrict__ dx,
+                    __nv_bfloat16* __restrict__ dpre, float* __restrict__ dw2) {
+  __shared__ float sda[64];
+  __shared__ float sat[64];
+  const int b = blockIdx.x;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int p = threadIdx.x; p < P; p += 256) sat[p] = attn[(long long)b * P + p];
+  for (int p = w; p < P; p += 8) {
+    float acc = 0.0f;
+    for (int k = lane * 8; k < C; k += 256) {
+      float f[8], g[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + ((long long)b * P + p) * C + k), f);
+      unpack8(*reinterpret_cast<const bf16x8*>(d_r + (long long)b * C + k), g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc = fmaf(f[i], g[i], acc);
+    }
+    acc = warp_sum_f(acc);
+    if (lane == 0) sda[p] = acc;
+  }
+  __syncthreads();
+  if (w == 0) {
+    float s = 0.0f;
+    for (int p = lane; p < P; p += 32) s = fmaf(sat[p], sda[p], s);
+    s = warp_sum_f(s);
+    for (int p = lane; p < P; p += 32) sda[p] = sat[p] * (sda[p] - s);
+  }
+  __syncthreads();
+  const float invp = 1.0f / (float)P;
+  for (int k = threadIdx.x * 8; k < C; k += 256 * 8) {
+    float g[8], m[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(d_r + (long long)b * C + k), g);
+    unpack8(*reinterpret_cast<const bf16x8*>(d_pooled + (long long)b * C + k), m);
+    for (int p = 0; p < P; ++p) {
+      float o[8];
+      const float a = sat[p];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(a, g[i], m[i] * invp);
+      *reinterpret_cast<bf16x8*>(dx + ((long long)b * P + p) * C + k) = pack8(o);
+    }
+  }
+  for (int k = threadIdx.x * 8; k < Hd; k += 256 * 8) {
+    float wv[8], acc[8];
+    load8<float>(w2 + k, wv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+    for (int p = 0; p < P; ++p) {
+      float f[8], o[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(h + ((long long)b * P + p) * Hd + k), f);
+      const float da = sda[p];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        o[i] = da * wv[i] * (1.0f - f[i] * f[i]);
+        acc[i] = fmaf(da, f[i], acc[i]);
+      }
+      *reinterpret_cast<bf16x8*>(dpre + ((long long)b * P + p) * Hd + k) = pack8(o);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(dw2 + k + i, acc[i]);
+  }
+}
+
+int pie_pool_fwd(const void* x, const void* h, const float* w2, int B, int P, int C, int Hd, float* attn, void* r,
+                 void* pooled, cudaStream_t st) {
+  if (B <= 0 || P <= 0 || P > 64 || (C & 7) || (Hd & 7)) {
+    set_error("pie_pool_fwd: bad shape B=%d P=%d C=%d Hd=%d (P <= 64)", B, P, C, Hd);
+    return CFL_EINVAL;
+  }
+  pie_pool_fwd_kernel<<<B, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                         reinterpret_cast<const __nv_bfloat16*>(h), w2, P, C, Hd, attn,
+                                         reinterpret_cast<__nv_bfloat16*>(r), reinterpret_cast<__nv_bfloat16*>(pooled));
+  return check_launch("pie_pool_fwd");
+}
+
+int pie_pool_bwd(const void* x, const void* h, const float* w2, const float* attn, const void* d_r, const void* d_pooled,
+                 int B, int P, int C, int Hd, void* dx, void* dpre, float* dw2, cudaStream_t st) {
+  if (B <= 0 || P <= 0 || P > 64 || (C & 7) || (Hd & 7)) {
+    set_error("pie_pool_bwd: bad shape");
+    return CFL_EINVAL;
+  }
+  pie_pool_bwd_kernel<<<B, 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(h), w2, attn,
+      reinterpret_cast<const __nv_bfloat16*>(d_r), reinterpret_cast<const __nv_bfloat16*>(d_pooled), P, C, Hd,
+      reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(dpre), dw2);
+  return check_launch("pie_pool_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------ misc elementwise
+// y_bf16 = a_bf16 + b_bf16
+__global__ void __launch_bounds__(256)
+add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, long long n8,
+                __nv_bfloat16* __restrict__ y) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n8) return;
+  float f[8], g[8];
+  unpack8(reinterpret_cast<const bf16x8*>(a)[t], f);
+  unpack8(reinterpret_cast<const bf16x8*>(b)[t], g);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] += g[i];
+  reinterpret_cast<bf16x8*>(y)[t] = pack8(f);
+}
+
+int add_bf16(const void* a, const void* b, long long n, void* y, cudaStream_t st) {
+  if (n <= 0 || (n & 7)) {
+    set_error("add_bf16: n %% 8 == 0 required");
+    return CFL_EINVAL;
+  }
+  add_bf16_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a),
+                                                                    reinterpret_cast<const __nv_bfloat16*>(b), n / 8,
+                                                                    reinterpret_cast<__nv_bfloat16*>(y));
+  return check_launch("add_bf16");
+}
+
+// fp32 -> bf16 with a permutation-free layout (used to refresh the bf16 shadow of the parameters after an
+// optimizer step): plain cast, reuse cast_f32_bf16 from loss_ops.cu.
+
+}  // namespace cfl

@@ -76,7 +76,7 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: boo
               bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, alpha: float = 1.0,
               add: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
               out_dtype: torch.dtype = torch.bfloat16, want_preact: bool = False, split_k: int = 1,
-              out: Optional[torch.Tensor] = None):
+              out: Optional[torch.Tensor] = None, accumulate: bool = False):
     """out[M,N] = act(alpha * A B^T + bias + add) on tcgen05.
 
     a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn); both bf16, 2-D, unit inner stride.
@@ -109,7 +109,7 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: boo
         _p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), M, N, K, _p(out), out.stride(0),
         1 if out.dtype == torch.bfloat16 else 0, _p(pre), _p(bias), act, float(alpha), _p(add),
         add.stride(0) if add is not None else 0, add_bf16, _p(aux), aux.stride(0) if aux is not None else 0,
-        int(split_k), _stream())
+        int(split_k), int(accumulate), _stream())
     _lib.check(rc, "gemm_bf16")
     _count("gemm")
     return (out, pre) if want_preact else out

@@ -1,0 +1,246 @@
+"""Thin tensor-level wrappers of the encoder-tower entry points of the C ABI (include/creamfl_b200.h).
+
+No autograd here: these are the forward / backward primitives the block-level autograd Functions in
+creamfl_b200/towers.py are composed of.  Activations are NHWC bf16 (4-D tensors [N, H, W, C], contiguous) or
+[rows, features] bf16; every function raises if handed a CPU tensor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from . import ops as _ops
+from .ops import _p, _stream, _need_cuda
+
+BF16 = torch.bfloat16
+
+_ws_cache: dict = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only scratch buffer per device (stream-ordered reuse; contents are dead once the consuming kernel has
+    been enqueued)."""
+    key = (device.type, device.index)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _chk(rc: int, what: str, launches: int = 1) -> None:
+    _lib.check(rc, what)
+    _ops._launches += launches
+
+
+# --------------------------------------------------------------------------------------------------- convolution
+def conv_out_hw(h: int, w: int, r: int, s: int, stride: int, pad: int):
+    return (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
+
+
+def conv_fprop(x: torch.Tensor, w2d: torch.Tensor, r: int, s: int, stride: int, pad: int) -> torch.Tensor:
+    """x [N,H,W,Cin] bf16, w2d [Cout, >= R*S*Cin] bf16 (row = one filter in (r, s, cin) order)."""
+    _need_cuda(x, w2d)
+    n, h, w, cin = x.shape
+    cout = w2d.shape[0]
+    ho, wo = conv_out_hw(h, w, r, s, stride, pad)
+    y = torch.empty((n, ho, wo, cout), dtype=BF16, device=x.device)
+    lib = _lib.load()
+    nb = lib.creamfl_conv2d_workspace_bytes(n, h, w, cin, cout, r, s, stride, pad)
+    ws = workspace(nb, x.device) if nb else None
+    _chk(lib.creamfl_conv2d_fprop(_p(x), _p(w2d), n, h, w, cin, cout, r, s, stride, pad, w2d.stride(0), _p(y), _p(ws),
+                                  nb, _stream()), "conv2d_fprop", 2 if nb else 1)
+    return y
+
+
+def conv_dgrad(dy: torch.Tensor, w2d: torch.Tensor, x_shape, r: int, s: int, stride: int, pad: int,
+               add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(dy, w2d, add)
+    n, h, w, cin = x_shape
+    cout = w2d.shape[0]
+    dx = torch.empty((n, h, w, cin), dtype=BF16, device=dy.device)
+    lib = _lib.load()
+    nb = lib.creamfl_conv2d_workspace_bytes(n, h, w, cin, cout, r, s, stride, pad)
+    ws = workspace(nb, dy.device) if nb else None
+    _chk(lib.creamfl_conv2d_dgrad(_p(dy), _p(w2d), n, h, w, cin, cout, r, s, stride, pad, w2d.stride(0), _p(add),
+                                  _p(dx), _p(ws), nb, _stream()), "conv2d_dgrad", 2 if nb else 1)
+    return dx
+
+
+def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, r: int, s: int, stride: int, pad: int) -> None:
+    """dw (fp32, [Cout, R*S*Cin] contiguous memory) += dy^T patches(x)."""
+    _need_cuda(dy, x, dw)
+    n, h, w, cin = x.shape
+    cout = dy.shape[-1]
+    lib = _lib.load()
+    nb = lib.creamfl_conv2d_workspace_bytes(n, h, w, cin, cout, r, s, stride, pad)
+    ws = workspace(nb, dy.device) if nb else None
+    _chk(lib.creamfl_conv2d_wgrad(_p(dy), _p(x), None, n, h, w, cin, cout, r, s, stride, pad, _p(dw), _p(ws), nb,
+                                  _stream()), "conv2d_wgrad", 2 if nb else 1)
+
+
+def im2col_images(images: torch.Tensor, r: int, s: int, stride: int, pad: int, pitch: int) -> torch.Tensor:
+    """fp32 NCHW images -> bf16 patch matrix [N*Ho*Wo, pitch] in the shared workspace (valid until the next
+    workspace user is enqueued... callers consume it immediately)."""
+    _need_cuda(images)
+    n, c, h, w = images.shape
+    ho, wo = conv_out_hw(h, w, r, s, stride, pad)
+    col = torch.empty((n * ho * wo, pitch), dtype=BF16, device=images.device)
+    _chk(_lib.load().creamfl_im2col_nchw_f32(_p(images), n, c, h, w, r, s, stride, pad, pitch, _p(col), _stream()),
+         "im2col_nchw_f32")
+    return col
+
+
+# --------------------------------------------------------------------------------------------------- BatchNorm
+class BNScratch:
+    """Per-layer scratch of the BatchNorm kernels (fp64 sums, per-channel affine / backward coefficients)."""
+
+    def __init__(self, c: int, device):
+        self.sums = torch.zeros(2 * c, dtype=torch.float64, device=device)
+        self.scale = torch.empty(c, dtype=torch.float32, device=device)
+        self.shift = torch.empty(c, dtype=torch.float32, device=device)
+        self.coef = torch.empty(3 * c, dtype=torch.float32, device=device)
+
+
+def bn_train_fwd(x, gamma, beta, running_mean, running_var, sc: BNScratch, eps, momentum, res=None, relu=True):
+    c = x.shape[-1]
+    p = x.numel() // c
+    mean = torch.empty(c, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(c, dtype=torch.float32, device=x.device)
+    y = torch.empty_like(x)
+    _chk(_lib.load().creamfl_bn_train_fwd(_p(x), p, c, _p(gamma), _p(beta), eps, momentum, _p(running_mean),
+                                          _p(running_var), _p(sc.sums), _p(mean), _p(rstd), _p(sc.scale), _p(sc.shift),
+                                          _p(res), int(relu), _p(y), _stream()), "bn_train_fwd", 3)
+    return y, mean, rstd
+
+
+def bn_eval_fwd(x, gamma, beta, running_mean, running_var, sc: BNScratch, eps, res=None, relu=True):
+    c = x.shape[-1]
+    p = x.numel() // c
+    y = torch.empty_like(x)
+    _chk(_lib.load().creamfl_bn_eval_fwd(_p(x), p, c, _p(gamma), _p(beta), eps, _p(running_mean), _p(running_var),
+                                         _p(sc.scale), _p(sc.shift), _p(res), int(relu), _p(y), _stream()),
+         "bn_eval_fwd", 2)
+    return y
+
+
+def bn_train_bwd(dy, y_mask, x, gamma, mean, rstd, sc: BNScratch, dgamma, dbeta, want_g=False):
+    """Returns (dx, g) where g = dy * (y_mask > 0) (only if want_g)."""
+    c = x.shape[-1]
+    p = x.numel() // c
+    dx = torch.empty_like(x)
+    g = torch.empty_like(x) if want_g else None
+    _chk(_lib.load().creamfl_bn_train_bwd(_p(dy), _p(y_mask), _p(x), p, c, _p(gamma), _p(mean), _p(rstd), _p(sc.sums),
+                                          _p(sc.coef), _p(dgamma), _p(dbeta), _p(dx), _p(g), _stream()),
+         "bn_train_bwd", 3)
+    return dx, g
+
+
+# --------------------------------------------------------------------------------------------------- pooling
+def maxpool_fwd(x, want_idx=True):
+    n, h, w, c = x.shape
+    ho, wo = conv_out_hw(h, w, 3, 3, 2, 1)
+    y = torch.empty((n, ho, wo, c), dtype=BF16, device=x.device)
+    idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device) if want_idx else None
+    _chk(_lib.load().creamfl_maxpool_fwd(_p(x), n, h, w, c, _p(y), _p(idx), _stream()), "maxpool_fwd")
+    return y, idx
+
+
+def maxpool_bwd(dy, idx, x_shape):
+    n, h, w, c = x_shape
+    dx = torch.empty((n, h, w, c), dtype=BF16, device=dy.device)
+    _chk(_lib.load().creamfl_maxpool_bwd(_p(dy), _p(idx), n, h, w, c, _p(dx), _stream()), "maxpool_bwd")
+    return dx
+
+
+# --------------------------------------------------------------------------------------------------- LayerNorm
+def layernorm_fwd(x, gamma, beta, eps, res=None):
+    r, d = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(r, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(r, dtype=torch.float32, device=x.device)
+    _chk(_lib.load().creamfl_layernorm_fwd(_p(x), _p(res), _p(gamma), _p(beta), eps, r, d, int(x.dtype == BF16), _p(y),
+                                           _p(mean), _p(rstd), _stream()), "layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, res=None):
+    r, d = x.shape
+    lib = _lib.load()
+    dx = torch.empty_like(x)
+    nb = lib.creamfl_layernorm_bwd_workspace_bytes(d)
+    ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+    _chk(lib.creamfl_layernorm_bwd(_p(dy), _p(x), _p(res), _p(gamma), _p(mean), _p(rstd), r, d, int(x.dtype == BF16),
+                                   _p(dx), _p(dgamma), _p(dbeta), _p(ws), nb, _stream()), "layernorm_bwd", 2)
+    return dx
+
+
+def colsum_into(x, out):
+    m, n = x.shape
+    _chk(_lib.load().creamfl_colsum_bf16(_p(x), m, n, x.stride(0), _p(out), _stream()), "colsum_bf16")
+
+
+def add_bf16(a, b):
+    y = torch.empty_like(a)
+    _chk(_lib.load().creamfl_add_bf16(_p(a), _p(b), a.numel(), _p(y), _stream()), "add_bf16")
+    return y
+
+
+def act_bwd(dy, y, kind):
+    out = torch.empty(dy.shape, dtype=BF16, device=dy.device)
+    _chk(_lib.load().creamfl_act_bwd_f32(_p(dy), _p(y), dy.numel(), kind, _p(out), _stream()), "act_bwd_f32")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------- BERT pieces
+def embed_fwd(ids, token_type, word, pos, typ, seq_len):
+    t = ids.numel()
+    d = word.shape[1]
+    out = torch.empty((t, d), dtype=BF16, device=ids.device)
+    _chk(_lib.load().creamfl_embed_fwd(_p(ids), _p(token_type), _p(word), _p(pos), _p(typ), t, seq_len, d, _p(out),
+                                       _stream()), "embed_fwd")
+    return out
+
+
+def embed_bwd(ids, token_type, dh, seq_len, dword, dpos, dtyp):
+    t, d = dh.shape
+    _chk(_lib.load().creamfl_embed_bwd(_p(ids), _p(token_type), _p(dh), t, seq_len, d, _p(dword), _p(dpos), _p(dtyp),
+                                       _stream()), "embed_bwd")
+
+
+def attn_fwd(qkv, mask, b, l, heads):
+    ctx = torch.empty((b * l, heads * 64), dtype=BF16, device=qkv.device)
+    probs = torch.empty((b, heads, l, l), dtype=BF16, device=qkv.device)
+    _chk(_lib.load().creamfl_attn_fwd(_p(qkv), _p(mask), b, l, heads, 64, _p(ctx), _p(probs), _stream()), "attn_fwd")
+    return ctx, probs
+
+
+def attn_bwd(qkv, probs, dctx, b, l, heads):
+    dqkv = torch.empty_like(qkv)
+    _chk(_lib.load().creamfl_attn_bwd(_p(qkv), _p(probs), _p(dctx), b, l, heads, 64, _p(dqkv), _stream()), "attn_bwd")
+    return dqkv
+
+
+# --------------------------------------------------------------------------------------------------- PIE pooling
+def pie_pool_fwd(x, h, w2):
+    b, p, c = x.shape
+    hd = h.shape[-1]
+    attn = torch.empty((b, p), dtype=torch.float32, device=x.device)
+    r = torch.empty((b, c), dtype=BF16, device=x.device)
+    pooled = torch.empty((b, c), dtype=BF16, device=x.device)
+    _chk(_lib.load().creamfl_pie_pool_fwd(_p(x), _p(h), _p(w2), b, p, c, hd, _p(attn), _p(r), _p(pooled), _stream()),
+         "pie_pool_fwd")
+    return attn, r, pooled
+
+
+def pie_pool_bwd(x, h, w2, attn, d_r, d_pooled, dw2):
+    b, p, c = x.shape
+    hd = h.shape[-1]
+    dx = torch.empty_like(x)
+    dpre = torch.empty_like(h)
+    _chk(_lib.load().creamfl_pie_pool_bwd(_p(x), _p(h), _p(w2), _p(attn), _p(d_r), _p(d_pooled), b, p, c, hd, _p(dx),
+                                          _p(dpre), _p(dw2), _stream()), "pie_pool_bwd")
+    return dx, dpre

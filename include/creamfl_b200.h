@@ -44,11 +44,15 @@ int creamfl_abi_version(void);
  * a_mn/b_mn = 0: operand stored [rows, K] (K contiguous); = 1: stored [K, rows].
  * Replaces cuBLAS behind nn.Linear / HF BertModel (src/networks/models/pcme.py:31-44,
  * pie_model.py:18-19,51, image_encoder.py:30,57) and 1x1 convolutions of torchvision ResNet
- * (image_encoder.py:24) in NHWC.  split_k > 1 accumulates with fp32 atomics into a pre-zeroed fp32 `out`. */
+ * (image_encoder.py:24) in NHWC.  split_k > 1 or accumulate != 0 adds into the existing fp32 `out` with atomics
+ * (weight gradients accumulate into the parameter's grad buffer); split_k == 0 lets the library choose. */
 int creamfl_gemm_bf16(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn, int M, int N,
                       int K, void* out, int64_t ldo, int out_bf16, void* out_preact_bf16, const float* bias,
                       int act, float alpha, const void* add, int64_t ld_add, int add_bf16, const void* aux_bf16,
-                      int64_t ld_aux, int split_k, void* stream);
+                      int64_t ld_aux, int split_k, int accumulate, void* stream);
+/* elementwise derivative of an activation from its OUTPUT y: kind CREAMFL_ACT_SIGMOID -> dy*y*(1-y),
+ * CREAMFL_ACT_TANH -> dy*(1-y^2); fp32 in, bf16 out (the result feeds a dgrad/wgrad GEMM) */
+int creamfl_act_bwd_f32(const float* dy, const float* y, int64_t n, int kind, void* out_bf16, void* stream);
 
 /* ---- inter-modal InfoNCE (MMClientTrainer.py:193-201,301-308; ClientTrainer.py:388-401,493-502) ------
  * logits = inv_tau * Q G^T  (never materialised in fp32), CE against column labels[i], mean over rows.
@@ -109,6 +113,88 @@ int creamfl_cast_f32_bf16(const float* x, int64_t n, void* y_bf16, void* stream)
 size_t creamfl_recall_workspace_bytes(int Nq);
 int creamfl_recall_ranks(const float* q, const float* g, const int64_t* q_lab, const int64_t* g_lab, int Nq,
                          int Ng, int D, int32_t* ranks, void* workspace, size_t workspace_bytes, void* stream);
+
+
+/* ======================================================================================================
+ * Encoder towers.  Activations are NHWC bf16 (images) / [tokens, hidden] bf16 (text); parameters are fp32
+ * masters with bf16 shadows for the tensor-core operands; filters are [Cout, R, S, Cin] (the memory order of
+ * a torch channels_last OIHW tensor).  Replaces cuDNN / cuBLAS behind torchvision ResNet
+ * (src/networks/models/image_encoder.py:24,55; src/networks/resnet_client.py:163-201) and HF BertModel
+ * (src/networks/models/pcme.py:31-44).
+ * ====================================================================================================== */
+
+/* ---- convolution: implicit GEMM on tcgen05 for stride-1 "same" filters, plain GEMM for 1x1, im2col + GEMM
+ * for strided filters (workspace = patch matrix).  w_pitch = elements between filter rows (>= R*S*Cin). */
+size_t creamfl_conv2d_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad);
+int creamfl_conv2d_fprop(const void* x_bf16, const void* w_bf16, int N, int H, int W, int Cin, int Cout, int R, int S,
+                         int stride, int pad, int64_t w_pitch, void* y_bf16, void* workspace, size_t workspace_bytes,
+                         void* stream);
+/* dx = conv_transpose(dy, w) [+ add] ; add (optional) is a bf16 tensor shaped like dx (residual-branch gradient) */
+int creamfl_conv2d_dgrad(const void* dy_bf16, const void* w_bf16, int N, int H, int W, int Cin, int Cout, int R, int S,
+                         int stride, int pad, int64_t w_pitch, const void* add_bf16, void* dx_bf16, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* dw[Cout, R*S*Cin] (fp32, pitch R*S*Cin) += dy^T * patches(x).  If col_bf16 is non-null it is the patch matrix
+ * kept from the forward pass (strided path) and x is not read. */
+int creamfl_conv2d_wgrad(const void* dy_bf16, const void* x_bf16, const void* col_bf16, int N, int H, int W, int Cin,
+                         int Cout, int R, int S, int stride, int pad, float* dw, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* 7x7/2 stem: fp32 NCHW images -> bf16 patch matrix [N*Ho*Wo, col_pitch] (column order r, s, c; zero tail) */
+int creamfl_im2col_nchw_f32(const float* images, int N, int C, int H, int W, int R, int S, int stride, int pad,
+                            int col_pitch, void* col_bf16, void* stream);
+
+/* ---- BatchNorm2d over NHWC bf16 (P = N*H*W pixels), fused with the residual add and ReLU of the ResNet blocks.
+ * train: batch statistics (fp64 accumulation in `sums`, 2*C doubles, zero on entry and on exit), running stats
+ * updated with `momentum`; keeps mean/rstd for the backward.  scale/shift: C-float scratch each. */
+int creamfl_bn_train_fwd(const void* x_bf16, int64_t P, int C, const float* gamma, const float* beta, float eps,
+                         float momentum, float* running_mean, float* running_var, double* sums, float* mean,
+                         float* rstd, float* scale, float* shift, const void* res_bf16, int relu, void* y_bf16,
+                         void* stream);
+int creamfl_bn_eval_fwd(const void* x_bf16, int64_t P, int C, const float* gamma, const float* beta, float eps,
+                        const float* running_mean, const float* running_var, float* scale, float* shift,
+                        const void* res_bf16, int relu, void* y_bf16, void* stream);
+/* g = dy * (y > 0) if y_bf16 != null else dy;  dgamma += sum g*xhat, dbeta += sum g;  dx = BN'(g);
+ * g_out (optional) receives g (gradient of the residual branch).  coef: 3*C floats scratch. */
+int creamfl_bn_train_bwd(const void* dy_bf16, const void* y_bf16, const void* x_bf16, int64_t P, int C,
+                         const float* gamma, const float* mean, const float* rstd, double* sums, float* coef,
+                         float* dgamma, float* dbeta, void* dx_bf16, void* g_out_bf16, void* stream);
+
+/* ---- 3x3 / stride 2 / pad 1 max pooling (ResNet stem); idx: one byte per output element */
+int creamfl_maxpool_fwd(const void* x_bf16, int N, int H, int W, int C, void* y_bf16, void* idx_u8, void* stream);
+int creamfl_maxpool_bwd(const void* dy_bf16, const void* idx_u8, int N, int H, int W, int C, void* dx_bf16,
+                        void* stream);
+
+/* ---- LayerNorm over the last dimension of [R, D] (+ optional residual input), bf16 or fp32 activations */
+size_t creamfl_layernorm_bwd_workspace_bytes(int D);
+int creamfl_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, float eps, int R,
+                          int D, int is_bf16, void* y, float* mean, float* rstd, void* stream);
+int creamfl_layernorm_bwd(const void* dy, const void* x, const void* res, const float* gamma, const float* mean,
+                          const float* rstd, int R, int D, int is_bf16, void* dx, float* dgamma, float* dbeta,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- out[n] += sum_m x[m, n]  (bias gradients) */
+int creamfl_colsum_bf16(const void* x_bf16, int M, int N, int64_t ld, float* out, void* stream);
+int creamfl_add_bf16(const void* a_bf16, const void* b_bf16, int64_t n, void* y_bf16, void* stream);
+
+/* ---- BERT embeddings (word + position + token type; LayerNorm is a separate call) */
+int creamfl_embed_fwd(const int64_t* ids, const int64_t* token_type, const float* word, const float* pos,
+                      const float* type, int T, int L, int D, void* out_bf16, void* stream);
+int creamfl_embed_bwd(const int64_t* ids, const int64_t* token_type, const void* dh_bf16, int T, int L, int D,
+                      float* dword, float* dpos, float* dtype, void* stream);
+
+/* ---- BERT self-attention, L <= 64, head dim 64: qkv [B*L, 3*H*64] bf16, mask [B, L] fp32 (1 = attend),
+ * ctx [B*L, H*64] bf16, probs [B, H, L, L] bf16 */
+int creamfl_attn_fwd(const void* qkv_bf16, const float* mask, int B, int L, int H, int head_dim, void* ctx_bf16,
+                     void* probs_bf16, void* stream);
+int creamfl_attn_bwd(const void* qkv_bf16, const void* probs_bf16, const void* dctx_bf16, int B, int L, int H,
+                     int head_dim, void* dqkv_bf16, void* stream);
+
+/* ---- PIENet attention pooling over the P (= 49) positions of the final feature map (pie_model.py:28-40,61-67)
+ * and global average pooling (image_encoder.py:56): x [B, P, C] bf16, h = tanh(x W1^T) [B, P, Hd] bf16 */
+int creamfl_pie_pool_fwd(const void* x_bf16, const void* h_bf16, const float* w2, int B, int P, int C, int Hd,
+                         float* attn, void* r_bf16, void* pooled_bf16, void* stream);
+int creamfl_pie_pool_bwd(const void* x_bf16, const void* h_bf16, const float* w2, const float* attn,
+                         const void* d_r_bf16, const void* d_pooled_bf16, int B, int P, int C, int Hd, void* dx_bf16,
+                         void* dpre_bf16, float* dw2, void* stream);
 
 #ifdef __cplusplus
 }
