@@ -71,12 +71,40 @@ def to_bf16(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def cast_into(src_f32: torch.Tensor, dst_bf16: torch.Tensor) -> None:
+    """dst (bf16, same numel) <- src (fp32), both contiguous 1-D views; used to refresh parameter shadows."""
+    _need_cuda(src_f32, dst_bf16)
+    if src_f32.numel() != dst_bf16.numel() or src_f32.dtype != torch.float32 or dst_bf16.dtype != torch.bfloat16:
+        raise ValueError("cast_into: shape / dtype mismatch")
+    _lib.check(_lib.load().creamfl_cast_f32_bf16(_p(src_f32), src_f32.numel(), _p(dst_bf16), _stream()),
+               "cast_f32_bf16")
+    _count("cast")
+
+
+def l2norm_raw(x32: torch.Tensor):
+    """(y, inv_norm) of F.normalize over the last dim of an fp32 [R, D] tensor; no autograd."""
+    R, D = x32.shape
+    y = torch.empty_like(x32)
+    inv = torch.empty(R, dtype=torch.float32, device=x32.device)
+    _lib.check(_lib.load().creamfl_l2norm_fwd(_p(x32), R, D, _p(y), None, _p(inv), _stream()), "l2norm_fwd")
+    _count("l2norm_fwd")
+    return y, inv
+
+
+def l2norm_bwd_raw(gy: torch.Tensor, y: torch.Tensor, inv: torch.Tensor) -> torch.Tensor:
+    R, D = y.shape
+    dx = torch.empty_like(y)
+    _lib.check(_lib.load().creamfl_l2norm_bwd(_p(gy), _p(y), _p(inv), R, D, _p(dx), _stream()), "l2norm_bwd")
+    _count("l2norm_bwd")
+    return dx
+
+
 # --------------------------------------------------------------------------------------------------- GEMM
 def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
               bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, alpha: float = 1.0,
               add: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
               out_dtype: torch.dtype = torch.bfloat16, want_preact: bool = False, split_k: int = 1,
-              out: Optional[torch.Tensor] = None, accumulate: bool = False):
+              out: Optional[torch.Tensor] = None, accumulate: bool = False, n_cols: Optional[int] = None):
     """out[M,N] = act(alpha * A B^T + bias + add) on tcgen05.
 
     a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn); both bf16, 2-D, unit inner stride.
@@ -90,6 +118,10 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: boo
     N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
     if K != Kb:
         raise ValueError(f"gemm_bf16: K mismatch {K} vs {Kb}")
+    if n_cols is not None:
+        if n_cols > N:
+            raise ValueError("gemm_bf16: n_cols exceeds the operand")
+        N = n_cols
     if out is None:
         if split_k > 1:
             out = torch.zeros((M, N), dtype=torch.float32, device=a.device)

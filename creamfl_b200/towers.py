@@ -1,0 +1,800 @@
+"""Encoder towers of the CreamFL hot path on the creamfl_b200 kernels.
+
+Mirrors the modules the reference reaches through `get_model` (src/networks/models/__init__.py:6):
+  * ResNet           - torchvision ResNet-{18,101} feature extractor as used by EncoderImage
+                       (src/networks/models/image_encoder.py:24-32,55): NHWC bf16, convolutions as implicit GEMM on
+                       tcgen05, BatchNorm with batch statistics, one autograd node per residual block
+  * EncoderImage     - ResNet -> avgpool -> fc -> PIENet -> LayerNorm -> l2_normalize (image_encoder.py:54-71,
+                       pie_model.py:28-40,61-67)
+  * BertEncoder      - HF BertModel (bert-base) forward/backward restricted to what pcme.py:43-44 consumes
+                       (last_hidden_state[:, 0]); state_dict keys equal HF's
+Parameter names / shapes equal the reference's so `{'net': state_dict}` checkpoints (MMFL.py:281) load unchanged.
+
+Numerics: fp32 master parameters, bf16 shadows as tensor-core operands, bf16 activations, fp32 accumulation and
+statistics (the policy replacing apex O2).  Weight gradients are accumulated by the kernels
+directly into a flat fp32 gradient buffer that `param.grad` views.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops, tower_ops as T
+
+BF16 = torch.bfloat16
+
+
+# ===================================================================================================== parameters
+class ParamStore:
+    """All parameters of a model in one flat fp32 buffer, with a flat fp32 gradient buffer and a flat bf16 shadow.
+
+    4-D (convolution) parameters keep their logical OIHW shape but live in memory as [O, H, W, I] (torch
+    channels_last), the order the implicit-GEMM kernels read.  `adjacent` lists parameter groups that must be
+    contiguous (BERT query/key/value -> one [2304, 768] operand)."""
+
+    def __init__(self, module: nn.Module, adjacent: Sequence[Sequence[nn.Parameter]] = ()):
+        params: List[nn.Parameter] = []
+        seen = set()
+        for grp in adjacent:
+            for p in grp:
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    params.append(p)
+        for p in module.parameters():
+            if id(p) not in seen:
+                seen.add(id(p))
+                params.append(p)
+        if not params:
+            raise ValueError('ParamStore: module has no parameters')
+        dev = params[0].device
+        if dev.type != 'cuda':
+            raise RuntimeError('creamfl_b200 towers run on CUDA only (no CPU fallback exists); call .cuda() first')
+        in_group = {id(p) for grp in adjacent for p in grp}
+        offs, total = [], 0
+        for p in params:
+            if id(p) not in in_group:
+                total = (total + 63) // 64 * 64
+            offs.append(total)
+            total += p.numel()
+        total = (total + 63) // 64 * 64
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.shadow = torch.zeros(total, dtype=BF16, device=dev)
+        self.params = params
+        self.offsets = {}
+        for p, off in zip(params, offs):
+            n = p.numel()
+            self.offsets[id(p)] = off
+            if p.dim() == 4:
+                o, i, r, s = p.shape
+                view = self.flat[off:off + n].view(o, r, s, i).permute(0, 3, 1, 2)
+                gview = self.grad[off:off + n].view(o, r, s, i).permute(0, 3, 1, 2)
+                p._w16 = self.shadow[off:off + n].view(o, r * s * i)
+                p._g2d = self.grad[off:off + n].view(o, r * s * i)
+            else:
+                view = self.flat[off:off + n].view(p.shape)
+                gview = self.grad[off:off + n].view(p.shape)
+                p._w16 = self.shadow[off:off + n].view(p.shape)
+                p._g2d = gview
+            view.copy_(p.data)
+            p.data = view
+            p._gview = gview
+            p.grad = gview if p.requires_grad else None
+        self.first_ptr = params[0].data_ptr()
+        self.sync_shadow()
+
+    def fused(self, group: Sequence[nn.Parameter], rows: int, cols: Optional[int] = None):
+        """bf16 shadow and fp32 grad of an adjacent group viewed as one tensor."""
+        off = self.offsets[id(group[0])]
+        n = sum(p.numel() for p in group)
+        shape = (rows,) if cols is None else (rows, cols)
+        return self.shadow[off:off + n].view(shape), self.grad[off:off + n].view(shape)
+
+    def sync_shadow(self) -> None:
+        """Refresh the bf16 shadow after the fp32 masters changed (optimizer step, load_state_dict)."""
+        ops.cast_into(self.flat, self.shadow)
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+        for p in self.params:
+            if p.requires_grad:
+                p.grad = p._gview
+
+    def intact(self) -> bool:
+        return self.params[0].data_ptr() == self.first_ptr
+
+
+def grad_target(p: nn.Parameter) -> torch.Tensor:
+    """The fp32 buffer a kernel accumulates d(loss)/dp into.  Handles `optimizer.zero_grad(set_to_none=True)`."""
+    if p.grad is None:
+        p._g2d.zero_()
+        p.grad = p._gview
+    elif p.grad.data_ptr() != p._gview.data_ptr():
+        raise RuntimeError('parameter .grad was replaced; creamfl_b200 accumulates into its flat gradient buffer')
+    return p._g2d
+
+
+class StoreMixin:
+    """Modules that own a ParamStore: (re)build lazily - deepcopy / .to() / .cpu() re-home the parameters."""
+    _store: Optional[ParamStore] = None
+
+    def _adjacent_groups(self):
+        return []
+
+    def store(self) -> ParamStore:
+        st = self.__dict__.get('_store')
+        if st is None or not st.intact() or st.params[0] is not next(iter(self._ordered_first())):
+            st = ParamStore(self, self._adjacent_groups())
+            self.__dict__['_store'] = st
+            self._after_store_build(st)
+        return st
+
+    def _ordered_first(self):
+        groups = self._adjacent_groups()
+        if groups:
+            yield groups[0][0]
+        else:
+            yield next(self.parameters())
+
+    def _after_store_build(self, st: ParamStore) -> None:
+        pass
+
+    def sync_shadow(self) -> None:
+        self.store().sync_shadow()
+
+    def zero_grad(self, set_to_none: bool = False) -> None:  # noqa: D401 - nn.Module signature
+        self.store().zero_grad()
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k == '_store':
+                continue
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        new.__dict__['_store'] = None
+        return new
+
+
+# ===================================================================================================== ResNet
+class Conv(nn.Module):
+    def __init__(self, cin, cout, k, stride, pad):
+        super().__init__()
+        self.k, self.stride, self.pad = k, stride, pad
+        self.weight = nn.Parameter(torch.empty(cout, cin, k, k))
+        nn.init.kaiming_normal_(self.weight, mode='fan_out', nonlinearity='relu')
+
+
+class BN(nn.Module):
+    def __init__(self, c, eps=1e-5, momentum=0.1):
+        super().__init__()
+        self.eps, self.momentum = eps, momentum
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer('running_mean', torch.zeros(c))
+        self.register_buffer('running_var', torch.ones(c))
+        self.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
+        self._scratch = None
+
+    def scratch(self) -> T.BNScratch:
+        sc = self._scratch
+        if sc is None or sc.sums.device != self.weight.device:
+            sc = self._scratch = T.BNScratch(self.weight.numel(), self.weight.device)
+        return sc
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == '_scratch' else copy.deepcopy(v, memo)
+        return new
+
+    def fwd(self, x, res=None, relu=True):
+        """Returns (y, saved) - saved is (mean, rstd) in training mode, None in eval mode."""
+        if self.training:
+            y, mean, rstd = T.bn_train_fwd(x, self.weight, self.bias, self.running_mean, self.running_var,
+                                           self.scratch(), self.eps, self.momentum, res=res, relu=relu)
+            self.num_batches_tracked += 1
+            return y, (mean, rstd)
+        return T.bn_eval_fwd(x, self.weight, self.bias, self.running_mean, self.running_var, self.scratch(), self.eps,
+                             res=res, relu=relu), None
+
+    def bwd(self, dy, y_mask, x, saved, want_g=False):
+        if saved is None:
+            raise RuntimeError('BatchNorm backward needs a training-mode forward (batch statistics)')
+        mean, rstd = saved
+        return T.bn_train_bwd(dy, y_mask, x, self.weight, mean, rstd, self.scratch(), grad_target(self.weight),
+                              grad_target(self.bias), want_g=want_g)
+
+
+def _conv_f(c: Conv, x):
+    return T.conv_fprop(x, c.weight._w16, c.k, c.k, c.stride, c.pad)
+
+
+def _conv_b(c: Conv, dy, x, need_dx=True, add=None):
+    T.conv_wgrad(dy, x, grad_target(c.weight), c.k, c.k, c.stride, c.pad)
+    if not need_dx:
+        return None
+    return T.conv_dgrad(dy, c.weight._w16, x.shape, c.k, c.k, c.stride, c.pad, add=add)
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1, self.bn1 = Conv(inplanes, planes, 1, 1, 0), BN(planes)
+        self.conv2, self.bn2 = Conv(planes, planes, 3, stride, 1), BN(planes)       # torchvision v1.5: stride on 3x3
+        self.conv3, self.bn3 = Conv(planes, planes * 4, 1, 1, 0), BN(planes * 4)
+        self.downsample = downsample
+
+    def block_params(self):
+        return [p for p in self.parameters()]
+
+    def forward(self, x):
+        return _BlockFn.apply(x, self, *self.block_params())
+
+    def run_fwd(self, x, save):
+        o1 = _conv_f(self.conv1, x)
+        a1, s1 = self.bn1.fwd(o1)
+        o2 = _conv_f(self.conv2, a1)
+        a2, s2 = self.bn2.fwd(o2)
+        o3 = _conv_f(self.conv3, a2)
+        if self.downsample is not None:
+            od = _conv_f(self.downsample[0], x)
+            idn, sd = self.downsample[1].fwd(od, relu=False)
+        else:
+            od, idn, sd = None, x, None
+        y, s3 = self.bn3.fwd(o3, res=idn, relu=True)
+        if save:
+            return y, (x, o1, a1, s1, o2, a2, s2, o3, s3, od, sd, y)
+        return y, None
+
+    def run_bwd(self, saved, dy):
+        x, o1, a1, s1, o2, a2, s2, o3, s3, od, sd, y = saved
+        do3, g = self.bn3.bwd(dy, y, o3, s3, want_g=True)
+        da2 = _conv_b(self.conv3, do3, a2)
+        do2, _ = self.bn2.bwd(da2, a2, o2, s2)
+        da1 = _conv_b(self.conv2, do2, a1)
+        do1, _ = self.bn1.bwd(da1, a1, o1, s1)
+        if self.downsample is not None:
+            dod, _ = self.downsample[1].bwd(g, None, od, sd)
+            dxd = _conv_b(self.downsample[0], dod, x)
+            return _conv_b(self.conv1, do1, x, add=dxd)
+        return _conv_b(self.conv1, do1, x, add=g)
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1, self.bn1 = Conv(inplanes, planes, 3, stride, 1), BN(planes)
+        self.conv2, self.bn2 = Conv(planes, planes, 3, 1, 1), BN(planes)
+        self.downsample = downsample
+
+    def block_params(self):
+        return [p for p in self.parameters()]
+
+    def forward(self, x):
+        return _BlockFn.apply(x, self, *self.block_params())
+
+    def run_fwd(self, x, save):
+        o1 = _conv_f(self.conv1, x)
+        a1, s1 = self.bn1.fwd(o1)
+        o2 = _conv_f(self.conv2, a1)
+        if self.downsample is not None:
+            od = _conv_f(self.downsample[0], x)
+            idn, sd = self.downsample[1].fwd(od, relu=False)
+        else:
+            od, idn, sd = None, x, None
+        y, s2 = self.bn2.fwd(o2, res=idn, relu=True)
+        if save:
+            return y, (x, o1, a1, s1, o2, s2, od, sd, y)
+        return y, None
+
+    def run_bwd(self, saved, dy):
+        x, o1, a1, s1, o2, s2, od, sd, y = saved
+        do2, g = self.bn2.bwd(dy, y, o2, s2, want_g=True)
+        da1 = _conv_b(self.conv2, do2, a1)
+        do1, _ = self.bn1.bwd(da1, a1, o1, s1)
+        if self.downsample is not None:
+            dod, _ = self.downsample[1].bwd(g, None, od, sd)
+            dxd = _conv_b(self.downsample[0], dod, x)
+            return _conv_b(self.conv1, do1, x, add=dxd)
+        return _conv_b(self.conv1, do1, x, add=g)
+
+
+class _BlockFn(torch.autograd.Function):
+    """One residual block = one autograd node; the block's own run_fwd/run_bwd sequence the kernels."""
+
+    @staticmethod
+    def forward(ctx, x, block, *params):
+        need = any(ctx.needs_input_grad)
+        y, saved = block.run_fwd(x, need)
+        ctx.block, ctx.saved = block, saved
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        if ctx.saved is None:
+            raise RuntimeError('block was run without saving activations')
+        dx = ctx.block.run_bwd(ctx.saved, dy.contiguous())
+        ctx.saved = None
+        return (dx, None) + (None,) * (len(ctx.needs_input_grad) - 2)
+
+
+class _StemFn(torch.autograd.Function):
+    """conv 7x7/2 (im2col from fp32 NCHW images + tcgen05 GEMM) -> BN -> ReLU -> maxpool 3x3/2."""
+
+    @staticmethod
+    def forward(ctx, images, net, *params):
+        n, c, h, w = images.shape
+        need = any(ctx.needs_input_grad)
+        w16 = net.stem_shadow()
+        col = T.im2col_images(images, 7, 7, 2, 3, w16.shape[1])
+        ho, wo = T.conv_out_hw(h, w, 7, 7, 2, 3)
+        o = ops.gemm_bf16(col, w16).view(n, ho, wo, 64)
+        del col
+        a, s = net.bn1.fwd(o)
+        y, idx = T.maxpool_fwd(a, want_idx=need)
+        ctx.net = net
+        ctx.saved = (images, o, a, s, idx) if need else None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        net = ctx.net
+        images, o, a, s, idx = ctx.saved
+        ctx.saved = None
+        da = T.maxpool_bwd(dy.contiguous(), idx, a.shape)
+        do, _ = net.bn1.bwd(da, a, o, s)
+        w16 = net.stem_shadow()
+        col = T.im2col_images(images, 7, 7, 2, 3, w16.shape[1])
+        g = grad_target(net.conv1.weight)                         # [64, 147] fp32
+        ops.gemm_bf16(do.view(-1, 64), col, a_mn=True, b_mn=True, out=g, split_k=0, accumulate=True, n_cols=g.shape[1])
+        return (None, None) + (None,) * (len(ctx.needs_input_grad) - 2)
+
+
+class ResNet(nn.Module):
+    """torchvision.models.resnet{18,101} without avgpool/fc (image_encoder.py:24-32): images fp32 NCHW in,
+    final feature map NHWC bf16 out."""
+
+    CFG = {'resnet18': (BasicBlock, [2, 2, 2, 2]), 'resnet34': (BasicBlock, [3, 4, 6, 3]),
+           'resnet50': (Bottleneck, [3, 4, 6, 3]), 'resnet101': (Bottleneck, [3, 4, 23, 3]),
+           'resnet152': (Bottleneck, [3, 8, 36, 3])}
+
+    def __init__(self, arch='resnet101'):
+        super().__init__()
+        block, layers = self.CFG[arch]
+        self.inplanes = 64
+        self.conv1, self.bn1 = Conv(3, 64, 7, 2, 3), BN(64)
+        self.layer1 = self._make_layer(block, 64, layers[0], 1)
+        self.layer2 = self._make_layer(block, 128, layers[1], 2)
+        self.layer3 = self._make_layer(block, 256, layers[2], 2)
+        self.layer4 = self._make_layer(block, 512, layers[3], 2)
+        self.out_dim = 512 * block.expansion
+        self._stem16 = None
+
+    def _make_layer(self, block, planes, blocks, stride):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            downsample = nn.Sequential(Conv(self.inplanes, planes * block.expansion, 1, stride, 0),
+                                       BN(planes * block.expansion))
+        layers = [block(self.inplanes, planes, stride, downsample)]
+        self.inplanes = planes * block.expansion
+        for _ in range(1, blocks):
+            layers.append(block(self.inplanes, planes))
+        return nn.Sequential(*layers)
+
+    def stem_shadow(self):
+        """[64, 152] bf16 filter matrix of the stem (147 columns padded to a 16-byte pitch), refreshed lazily."""
+        w = self.conv1.weight
+        ver = (w.data_ptr(), w._version, getattr(self, '_stem_epoch', 0))
+        if self._stem16 is None or self._stem16[0] != ver or self._stem16[1].device != w.device:
+            s = torch.zeros(64, 152, dtype=BF16, device=w.device)
+            s[:, :147] = w._w16
+            self._stem16 = (ver, s)
+        return self._stem16[1]
+
+    def invalidate_stem(self):
+        self._stem_epoch = getattr(self, '_stem_epoch', 0) + 1
+
+    def forward(self, images):
+        x = _StemFn.apply(images, self, self.conv1.weight, self.bn1.weight, self.bn1.bias)
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for blk in layer:
+                x = blk(x)
+        return x
+
+
+# ===================================================================================================== image head
+class _Linear(nn.Module):
+    def __init__(self, din, dout, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(dout, din))
+        self.bias = nn.Parameter(torch.zeros(dout)) if bias else None
+        nn.init.xavier_uniform_(self.weight)
+
+
+class _LayerNormP(nn.Module):
+    def __init__(self, d, eps):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(d))
+        self.bias = nn.Parameter(torch.zeros(d))
+
+
+class _SelfAttnPool(nn.Module):
+    def __init__(self, n_head, d_in, d_hidden):
+        super().__init__()
+        self.w_1 = _Linear(d_in, d_hidden, bias=False)
+        self.w_2 = _Linear(d_hidden, n_head, bias=False)
+
+
+class PIENet(nn.Module):
+    """Parameter container of pie_model.PIENet (n_embeds = 1)."""
+
+    def __init__(self, n_embeds, d_in, d_out, d_h):
+        super().__init__()
+        if n_embeds != 1:
+            raise NotImplementedError('the reference instantiates PIENet with n_embeds = 1 only')
+        self.attention = _SelfAttnPool(n_embeds, d_in, d_h)
+        self.fc = _Linear(d_in, d_out)
+        self.layer_norm = _LayerNormP(d_out, 1e-5)
+
+
+class _ImageHeadFn(torch.autograd.Function):
+    """x7 [B,7,7,C] -> l2_normalize(LayerNorm(fc(avgpool) + sigmoid(pie.fc(attention-pool)))) (image_encoder.py:55-67)."""
+
+    @staticmethod
+    def forward(ctx, x7, enc, *params):
+        b, h, w, c = x7.shape
+        p = h * w
+        pie = enc.pie_net
+        x2 = x7.reshape(b * p, c)
+        hid = ops.gemm_bf16(x2, pie.attention.w_1.weight._w16, act=ops.ACT_TANH)
+        attn, r, pooled = T.pie_pool_fwd(x7.view(b, p, c), hid.view(b, p, -1), pie.attention.w_2.weight.view(-1))
+        out = ops.gemm_bf16(pooled, enc.fc.weight._w16, bias=enc.fc.bias, out_dtype=torch.float32)
+        res = ops.gemm_bf16(r, pie.fc.weight._w16, bias=pie.fc.bias, act=ops.ACT_SIGMOID, out_dtype=torch.float32)
+        z, mean, rstd = T.layernorm_fwd(out, pie.layer_norm.weight, pie.layer_norm.bias, pie.layer_norm.eps, res=res)
+        emb, inv = ops.l2norm_raw(z)
+        ctx.enc = enc
+        ctx.saved = (x7, hid, attn, r, pooled, out, res, mean, rstd, emb, inv) if any(ctx.needs_input_grad) else None
+        return emb
+
+    @staticmethod
+    def backward(ctx, demb):
+        enc = ctx.enc
+        pie = enc.pie_net
+        x7, hid, attn, r, pooled, out, res, mean, rstd, emb, inv = ctx.saved
+        ctx.saved = None
+        b, h, w, c = x7.shape
+        p = h * w
+        dz = ops.l2norm_bwd_raw(demb.contiguous().float(), emb, inv)
+        dsum = T.layernorm_bwd(dz, out, pie.layer_norm.weight, mean, rstd, grad_target(pie.layer_norm.weight),
+                               grad_target(pie.layer_norm.bias), res=res)
+        d_out16 = ops.to_bf16(dsum)
+        d_respre = T.act_bwd(dsum, res, ops.ACT_SIGMOID)
+        # fc: out = pooled Wfc^T + b
+        ops.gemm_bf16(d_out16, pooled, a_mn=True, b_mn=True, out=grad_target(enc.fc.weight), split_k=0, accumulate=True)
+        T.colsum_into(d_out16, grad_target(enc.fc.bias))
+        d_pooled = ops.gemm_bf16(d_out16, enc.fc.weight._w16, b_mn=True)
+        # pie.fc: res = sigmoid(r Wp^T + b)
+        ops.gemm_bf16(d_respre, r, a_mn=True, b_mn=True, out=grad_target(pie.fc.weight), split_k=0, accumulate=True)
+        T.colsum_into(d_respre, grad_target(pie.fc.bias))
+        d_r = ops.gemm_bf16(d_respre, pie.fc.weight._w16, b_mn=True)
+        dx_part, dpre = T.pie_pool_bwd(x7.view(b, p, c), hid.view(b, p, -1), pie.attention.w_2.weight.view(-1), attn,
+                                       d_r, d_pooled, grad_target(pie.attention.w_2.weight).view(-1))
+        x2 = x7.reshape(b * p, c)
+        dpre2 = dpre.view(b * p, -1)
+        ops.gemm_bf16(dpre2, x2, a_mn=True, b_mn=True, out=grad_target(pie.attention.w_1.weight), split_k=0,
+                      accumulate=True)
+        dx = ops.gemm_bf16(dpre2, pie.attention.w_1.weight._w16, b_mn=True, add=dx_part.view(b * p, c))
+        return (dx.view(b, h, w, c), None) + (None,) * (len(ctx.needs_input_grad) - 2)
+
+
+class EncoderImage(nn.Module):
+    """Mirror of src/networks/models/image_encoder.py:17-71 (mlp_local=False)."""
+
+    def __init__(self, config, mlp_local=False):
+        super().__init__()
+        if mlp_local:
+            raise NotImplementedError('mlp_local heads are hard-wired to 512-d in the reference (SURVEY appendix B); '
+                                      'not part of the accelerated path')
+        embed_dim = config['embed_dim'] if isinstance(config, dict) else config.embed_dim
+        cnn_type = config['cnn_type'] if isinstance(config, dict) else config.cnn_type
+        self.cnn = ResNet(cnn_type)
+        self.cnn_dim = self.cnn.out_dim
+        self.fc = _Linear(self.cnn_dim, embed_dim)
+        self.pie_net = PIENet(1, self.cnn_dim, embed_dim, self.cnn_dim // 2)
+        self.mlp_local = mlp_local
+
+    def head_params(self):
+        return [self.fc.weight, self.fc.bias, self.pie_net.attention.w_1.weight, self.pie_net.attention.w_2.weight,
+                self.pie_net.fc.weight, self.pie_net.fc.bias, self.pie_net.layer_norm.weight,
+                self.pie_net.layer_norm.bias]
+
+    def forward(self, images):
+        x7 = self.cnn(images)
+        # the reference returns only 'embedding' from EncoderImage.forward (image_encoder.py:69-71)
+        return {'embedding': _ImageHeadFn.apply(x7, self, *self.head_params())}
+
+
+# ===================================================================================================== BERT
+class _BertSelfAttention(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.query, self.key, self.value = _Linear(d, d), _Linear(d, d), _Linear(d, d)
+
+
+class _BertSelfOutput(nn.Module):
+    def __init__(self, din, d, eps):
+        super().__init__()
+        self.dense = _Linear(din, d)
+        self.LayerNorm = _LayerNormP(d, eps)
+
+
+class _BertAttention(nn.Module):
+    def __init__(self, d, eps):
+        super().__init__()
+        self.self = _BertSelfAttention(d)
+        self.output = _BertSelfOutput(d, d, eps)
+
+
+class _BertIntermediate(nn.Module):
+    def __init__(self, d, dff):
+        super().__init__()
+        self.dense = _Linear(d, dff)
+
+
+class _BertLayer(nn.Module):
+    def __init__(self, d, dff, eps):
+        super().__init__()
+        self.attention = _BertAttention(d, eps)
+        self.intermediate = _BertIntermediate(d, dff)
+        self.output = _BertSelfOutput(dff, d, eps)
+
+
+class _BertEmbeddings(nn.Module):
+    def __init__(self, vocab, d, max_pos, types, eps):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(vocab, d, padding_idx=0)
+        self.position_embeddings = nn.Embedding(max_pos, d)
+        self.token_type_embeddings = nn.Embedding(types, d)
+        self.LayerNorm = _LayerNormP(d, eps)
+
+
+class _BertEncoderStack(nn.Module):
+    def __init__(self, n, d, dff, eps):
+        super().__init__()
+        self.layer = nn.ModuleList([_BertLayer(d, dff, eps) for _ in range(n)])
+
+
+class _BertPooler(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.dense = _Linear(d, d)       # dead on this path (pcme.py:44 reads last_hidden_state), kept for checkpoints
+
+
+class BertEncoder(nn.Module):
+    """bert-base-uncased geometry (HF BertConfig defaults); dropout is not applied (the parity
+    protocol runs the reference with dropout frozen)."""
+
+    def __init__(self, vocab=30522, hidden=768, layers=12, heads=12, ffn=3072, max_pos=512, types=2, eps=1e-12):
+        super().__init__()
+        self.hidden, self.heads = hidden, heads
+        self.embeddings = _BertEmbeddings(vocab, hidden, max_pos, types, eps)
+        self.encoder = _BertEncoderStack(layers, hidden, ffn, eps)
+        self.pooler = _BertPooler(hidden)
+        for m in self.modules():
+            if isinstance(m, _Linear):
+                nn.init.normal_(m.weight, std=0.02)
+            elif isinstance(m, nn.Embedding):
+                nn.init.normal_(m.weight, std=0.02)
+        with torch.no_grad():
+            self.embeddings.word_embeddings.weight[0].zero_()
+
+    def qkv_groups(self):
+        groups = []
+        for lyr in self.encoder.layer:
+            s = lyr.attention.self
+            groups.append([s.query.weight, s.key.weight, s.value.weight])
+            groups.append([s.query.bias, s.key.bias, s.value.bias])
+        return groups
+
+
+class _BertFn(torch.autograd.Function):
+    """ids, mask -> Linear(768, D)(last_hidden_state[:, 0]) fp32 [B, D]  (pcme.py:43-44 before l2_normalize)."""
+
+    @staticmethod
+    def forward(ctx, ids, token_type, mask, model, *params):
+        bert, lin, store = model.txt_enc, model.linear, model.store()
+        b, l = ids.shape
+        t = b * l
+        d, heads = bert.hidden, bert.heads
+        need = any(ctx.needs_input_grad)
+        emb = bert.embeddings
+        e = T.embed_fwd(ids, token_type, emb.word_embeddings.weight, emb.position_embeddings.weight,
+                        emb.token_type_embeddings.weight, l)
+        h, m0, r0 = T.layernorm_fwd(e, emb.LayerNorm.weight, emb.LayerNorm.bias, emb.LayerNorm.eps)
+        saved_layers = []
+        maskf = mask.to(torch.float32).contiguous()
+        for lyr in bert.encoder.layer:
+            s = lyr.attention.self
+            wqkv, _ = store.fused([s.query.weight, s.key.weight, s.value.weight], 3 * d, d)
+            bqkv_view = store.flat[store.offsets[id(s.query.bias)]:store.offsets[id(s.query.bias)] + 3 * d]
+            qkv = ops.gemm_bf16(h, wqkv, bias=bqkv_view)
+            ctxv, probs = T.attn_fwd(qkv, maskf, b, l, heads)
+            ao = ops.gemm_bf16(ctxv, lyr.attention.output.dense.weight._w16, bias=lyr.attention.output.dense.bias,
+                               add=h)
+            ln1 = lyr.attention.output.LayerNorm
+            h1, m1, r1 = T.layernorm_fwd(ao, ln1.weight, ln1.bias, ln1.eps)
+            ff, pre = ops.gemm_bf16(h1, lyr.intermediate.dense.weight._w16, bias=lyr.intermediate.dense.bias,
+                                    act=ops.ACT_GELU, want_preact=True)
+            fo = ops.gemm_bf16(ff, lyr.output.dense.weight._w16, bias=lyr.output.dense.bias, add=h1)
+            ln2 = lyr.output.LayerNorm
+            h2, m2, r2 = T.layernorm_fwd(fo, ln2.weight, ln2.bias, ln2.eps)
+            if need:
+                saved_layers.append((h, qkv, probs, ctxv, ao, m1, r1, h1, pre, ff, fo, m2, r2))
+            h = h2
+        cls = h.view(b, l * d)[:, :d]                       # rows b*L of the token matrix (pitch L*d)
+        out = ops.gemm_bf16(cls, lin.weight._w16, bias=lin.bias, out_dtype=torch.float32)
+        ctx.model = model
+        ctx.saved = (ids, token_type, e, m0, r0, saved_layers, h, b, l) if need else None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        model = ctx.model
+        bert, lin, store = model.txt_enc, model.linear, model.store()
+        ids, token_type, e, m0, r0, saved_layers, h_last, b, l = ctx.saved
+        ctx.saved = None
+        d, heads = bert.hidden, bert.heads
+        t = b * l
+        dout16 = ops.to_bf16(dout.contiguous().float())
+        cls = h_last.view(b, l * d)[:, :d]
+        ops.gemm_bf16(dout16, cls, a_mn=True, b_mn=True, out=grad_target(lin.weight), split_k=0, accumulate=True)
+        T.colsum_into(dout16, grad_target(lin.bias))
+        dh = torch.zeros((t, d), dtype=BF16, device=dout.device)
+        ops.gemm_bf16(dout16, lin.weight._w16, b_mn=True, out=dh.view(b, l * d)[:, :d])
+        for lyr, sv in zip(reversed(bert.encoder.layer), reversed(saved_layers)):
+            h_in, qkv, probs, ctxv, ao, m1, r1, h1, pre, ff, fo, m2, r2 = sv
+            ln2, ln1 = lyr.output.LayerNorm, lyr.attention.output.LayerNorm
+            d_fo = T.layernorm_bwd(dh, fo, ln2.weight, m2, r2, grad_target(ln2.weight), grad_target(ln2.bias))
+            ops.gemm_bf16(d_fo, ff, a_mn=True, b_mn=True, out=grad_target(lyr.output.dense.weight), split_k=0,
+                          accumulate=True)
+            T.colsum_into(d_fo, grad_target(lyr.output.dense.bias))
+            d_pre = ops.gemm_bf16(d_fo, lyr.output.dense.weight._w16, b_mn=True, act=ops.ACT_DGELU, aux=pre)
+            ops.gemm_bf16(d_pre, h1, a_mn=True, b_mn=True, out=grad_target(lyr.intermediate.dense.weight), split_k=0,
+                          accumulate=True)
+            T.colsum_into(d_pre, grad_target(lyr.intermediate.dense.bias))
+            d_h1 = ops.gemm_bf16(d_pre, lyr.intermediate.dense.weight._w16, b_mn=True, add=d_fo)
+            d_ao = T.layernorm_bwd(d_h1, ao, ln1.weight, m1, r1, grad_target(ln1.weight), grad_target(ln1.bias))
+            ops.gemm_bf16(d_ao, ctxv, a_mn=True, b_mn=True, out=grad_target(lyr.attention.output.dense.weight),
+                          split_k=0, accumulate=True)
+            T.colsum_into(d_ao, grad_target(lyr.attention.output.dense.bias))
+            d_ctx = ops.gemm_bf16(d_ao, lyr.attention.output.dense.weight._w16, b_mn=True)
+            d_qkv = T.attn_bwd(qkv, probs, d_ctx, b, l, heads)
+            s = lyr.attention.self
+            for p_ in (s.query.weight, s.key.weight, s.value.weight, s.query.bias, s.key.bias, s.value.bias):
+                grad_target(p_)
+            wqkv, gqkv = store.fused([s.query.weight, s.key.weight, s.value.weight], 3 * d, d)
+            _, gbqkv = store.fused([s.query.bias, s.key.bias, s.value.bias], 3 * d)
+            ops.gemm_bf16(d_qkv, h_in, a_mn=True, b_mn=True, out=gqkv, split_k=0, accumulate=True)
+            T.colsum_into(d_qkv, gbqkv)
+            dh = ops.gemm_bf16(d_qkv, wqkv, b_mn=True, add=d_ao)
+        emb = bert.embeddings
+        de = T.layernorm_bwd(dh, e, emb.LayerNorm.weight, m0, r0, grad_target(emb.LayerNorm.weight),
+                             grad_target(emb.LayerNorm.bias))
+        T.embed_bwd(ids, token_type, de, l, grad_target(emb.word_embeddings.weight),
+                    grad_target(emb.position_embeddings.weight), grad_target(emb.token_type_embeddings.weight))
+        return (None, None, None, None) + (None,) * (len(ctx.needs_input_grad) - 4)
+
+
+# ===================================================================================================== PCME
+class PCME(StoreMixin, nn.Module):
+    """Mirror of src/networks/models/pcme.py:15-57 with the BERT text tower (config.not_bert = False).
+
+    forward(images, sentences, captions_word, lengths) returns the reference's 10-key dict.  `captions_word` is
+    either the reference's tuple of strings (needs a BertTokenizer, only available when its vocabulary is on disk)
+    or a pre-tokenised dict / tuple (input_ids [B,L] int64, attention_mask [B,L], optional token_type_ids)."""
+
+    def __init__(self, word2idx, config, mlp_local=False):
+        super().__init__()
+        self.config = config
+        get = (lambda k, dflt=None: config.get(k, dflt))
+        self.embed_dim = get('embed_dim')
+        self.n_embeddings = get('n_samples_inference', 0) or 1
+        if get('not_bert', False):
+            raise NotImplementedError('GRU text tower is served by creamfl_b200.clients (cuDNN GRU, SURVEY 8f-f2)')
+        self.img_enc = EncoderImage(config, mlp_local)
+        self.txt_enc = BertEncoder()
+        self.linear = _Linear(768, self.embed_dim)
+        self.tokenizer = None
+
+    def _adjacent_groups(self):
+        return self.txt_enc.qkv_groups()
+
+    def _after_store_build(self, st):
+        self.img_enc.cnn.invalidate_stem()
+
+    def sync_shadow(self):
+        self.store().sync_shadow()
+        self.img_enc.cnn.invalidate_stem()
+
+    def _tokens(self, captions_word):
+        if isinstance(captions_word, dict):
+            ids, mask, tt = captions_word['input_ids'], captions_word['attention_mask'], captions_word.get(
+                'token_type_ids')
+        elif isinstance(captions_word, (tuple, list)) and len(captions_word) and torch.is_tensor(captions_word[0]):
+            ids, mask = captions_word[0], captions_word[1]
+            tt = captions_word[2] if len(captions_word) > 2 else None
+        else:
+            if self.tokenizer is None:
+                from transformers import BertTokenizer
+                self.tokenizer = BertTokenizer.from_pretrained('bert-base-uncased')
+            enc = self.tokenizer(list(captions_word), padding=True, return_tensors='pt')
+            ids, mask, tt = enc['input_ids'], enc['attention_mask'], enc['token_type_ids']
+        dev = self.linear.weight.device
+        ids = ids.to(dev, non_blocking=True).long().contiguous()
+        mask = mask.to(dev, non_blocking=True)
+        tt = torch.zeros_like(ids) if tt is None else tt.to(dev, non_blocking=True).long().contiguous()
+        return ids, tt, mask
+
+    def text_forward(self, captions_word):
+        ids, tt, mask = self._tokens(captions_word)
+        params = [p for p in self.txt_enc.parameters()] + [self.linear.weight, self.linear.bias]
+        out = _BertFn.apply(ids, tt, mask, self, *params)
+        return {'embedding': ops.l2_normalize(out)}
+
+    def image_forward(self, images):
+        self.store()
+        return self.img_enc(images)
+
+    def forward(self, images, sentences, captions_word, lengths):
+        self.store()
+        image_output = self.img_enc(images)
+        caption_output = self.text_forward(captions_word)
+        return {
+            'image_features': image_output['embedding'],
+            'image_attentions': image_output.get('attention'),
+            'image_residuals': image_output.get('residual'),
+            'image_logsigma': image_output.get('logsigma'),
+            'image_logsigma_att': image_output.get('uncertainty_attention'),
+            'caption_features': caption_output['embedding'],
+            'caption_attentions': caption_output.get('attention'),
+            'caption_residuals': caption_output.get('residual'),
+            'caption_logsigma': caption_output.get('logsigma'),
+            'caption_logsigma_att': caption_output.get('uncertainty_attention'),
+        }
+
+
+class ImageModel(StoreMixin, nn.Module):
+    """Stand-alone image tower (EncoderImage with its own parameter store)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.img_enc = EncoderImage(config)
+
+    def _after_store_build(self, st):
+        self.img_enc.cnn.invalidate_stem()
+
+    def sync_shadow(self):
+        self.store().sync_shadow()
+        self.img_enc.cnn.invalidate_stem()
+
+    def forward(self, images):
+        self.store()
+        return self.img_enc(images)['embedding']
+
+
+def get_model(word2idx, config, mlp_local=False):
+    """Mirror of src/networks/models/__init__.py:6-7."""
+    return PCME(word2idx, config, mlp_local)

@@ -1,0 +1,133 @@
+"""Torch restatement of the reference's encoder towers - TEST INFRASTRUCTURE ONLY (see oracle/creamfl_oracle.py).
+
+The reference builds its towers from third-party modules (torchvision ResNet, `torchvision==0.11.1` in its
+requirements.txt:15; HF `BertModel`, unpinned) plus ~60 lines of its own glue.  This file restates the glue on top of
+the torchvision / transformers versions present in the image, so that the CUDA towers (creamfl_b200/towers.py) can
+be compared with it on identical weights and inputs, in fp32/fp64 torch.
+
+Pinning: tests/golden/make_golden.py (case `towers`) runs the reference's own `PCME` (with import shims) on
+deterministic weights (`fill_deterministic`) and stores its outputs; tests/test_oracle_golden.py checks this
+restatement against them.
+"""
+from __future__ import annotations
+
+import zlib
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def l2_normalize(x, axis=-1):
+    """reference src/utils/tensor_utils.py:25-27."""
+    return F.normalize(x, p=2, dim=axis)
+
+
+class RefSelfAttnPool(nn.Module):
+    """reference src/networks/models/pie_model.py:11-40 (mask=None path)."""
+
+    def __init__(self, n_head, d_in, d_hidden):
+        super().__init__()
+        self.w_1 = nn.Linear(d_in, d_hidden, bias=False)
+        self.w_2 = nn.Linear(d_hidden, n_head, bias=False)
+
+    def forward(self, x):
+        attn = self.w_2(torch.tanh(self.w_1(x)))          # pie_model.py:30
+        attn = torch.softmax(attn, dim=1)                 # :35
+        output = torch.bmm(attn.transpose(1, 2), x)       # :37
+        if output.shape[1] == 1:
+            output = output.squeeze(1)
+        return output, attn
+
+
+class RefPIENet(nn.Module):
+    """reference pie_model.py:43-67 with dropout = 0."""
+
+    def __init__(self, n_embeds, d_in, d_out, d_h):
+        super().__init__()
+        self.attention = RefSelfAttnPool(n_embeds, d_in, d_h)
+        self.fc = nn.Linear(d_in, d_out)
+        self.layer_norm = nn.LayerNorm(d_out)
+
+    def forward(self, out, x):
+        residual, attn = self.attention(x)
+        residual = torch.sigmoid(self.fc(residual))       # :63
+        out = self.layer_norm(out + residual)             # :66
+        return out, attn, residual
+
+
+class RefEncoderImage(nn.Module):
+    """reference src/networks/models/image_encoder.py:17-71 (mlp_local False, random init instead of pretrained)."""
+
+    def __init__(self, cnn_type, embed_dim):
+        super().__init__()
+        import torchvision
+        self.cnn = getattr(torchvision.models, cnn_type)(weights=None)
+        cnn_dim = self.cnn_dim = self.cnn.fc.in_features
+        self.avgpool = self.cnn.avgpool
+        self.cnn.avgpool = nn.Sequential()
+        self.fc = nn.Linear(cnn_dim, embed_dim)
+        self.cnn.fc = nn.Sequential()
+        self.pie_net = RefPIENet(1, cnn_dim, embed_dim, cnn_dim // 2)
+
+    def forward(self, images):
+        out_7x7 = self.cnn(images).view(-1, self.cnn_dim, 7, 7)          # :55
+        pooled = self.avgpool(out_7x7).view(-1, self.cnn_dim)            # :56
+        out = self.fc(pooled)                                            # :57
+        out_7x7 = out_7x7.view(-1, self.cnn_dim, 7 * 7)                  # :60
+        out, attn, residual = self.pie_net(out, out_7x7.transpose(1, 2)) # :62
+        return {'embedding': l2_normalize(out)}                          # :67-71
+
+
+class RefPCME(nn.Module):
+    """reference src/networks/models/pcme.py:15-57 with the BERT tower and pre-tokenised inputs (the reference
+    tokenises strings on the host inside forward, pcme.py:40-42)."""
+
+    def __init__(self, cnn_type, embed_dim, bert_config=None):
+        super().__init__()
+        from transformers import BertConfig, BertModel
+        cfg = bert_config or BertConfig()
+        cfg.hidden_dropout_prob = 0.0             # parity protocol: dropout frozen
+        cfg.attention_probs_dropout_prob = 0.0
+        self.embed_dim = embed_dim
+        self.img_enc = RefEncoderImage(cnn_type, embed_dim)
+        self.txt_enc = BertModel(cfg)
+        self.linear = nn.Linear(cfg.hidden_size, embed_dim)
+
+    def forward(self, images, input_ids, attention_mask, token_type_ids=None):
+        image_output = self.img_enc(images)
+        caption_output = self.txt_enc(input_ids=input_ids, attention_mask=attention_mask,
+                                      token_type_ids=token_type_ids)
+        cap = l2_normalize(self.linear(caption_output['last_hidden_state'][:, 0, :]))     # pcme.py:44
+        return {'image_features': image_output['embedding'], 'caption_features': cap}
+
+
+def fill_deterministic(module: nn.Module, seed: int = 0) -> None:
+    """Overwrite every parameter / buffer with values that depend only on (name, shape, seed), so that two
+    independently constructed models (the reference's and a restatement) hold identical weights without shipping a
+    checkpoint.  Scales keep activations O(1) through deep stacks."""
+    with torch.no_grad():
+        for name, t in sorted(module.state_dict().items()):
+            if not t.is_floating_point():
+                t.zero_()
+                continue
+            g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + seed) & 0x7fffffff)
+            shape = tuple(t.shape)
+            if name.endswith('running_var'):
+                v = 0.5 + torch.rand(shape, generator=g)
+            elif name.endswith('running_mean'):
+                v = 0.1 * torch.randn(shape, generator=g)
+            elif t.dim() == 1:
+                if 'bn' in name or 'norm' in name.lower() or 'downsample.1' in name:
+                    v = (1.0 + 0.1 * torch.randn(shape, generator=g)) if name.endswith('weight') else \
+                        0.1 * torch.randn(shape, generator=g)
+                else:
+                    v = 0.05 * torch.randn(shape, generator=g)
+            elif t.dim() == 4:
+                fan_in = shape[1] * shape[2] * shape[3]
+                v = torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
+            elif 'embeddings' in name:
+                v = 0.05 * torch.randn(shape, generator=g)
+            else:
+                v = torch.randn(shape, generator=g) * (1.0 / shape[-1]) ** 0.5
+            t.copy_(v.to(t.dtype))
