@@ -299,4 +299,15 @@ int creamfl_pie_pool_bwd(const void* x, const void* h, const float* w2, const fl
   return pie_pool_bwd(x, h, w2, attn, d_r, d_pooled, B, P, C, Hd, dx, dpre, dw2, S(stream));
 }
 
+int creamfl_optimizer_step(const void* rows, int n_rows, const void* tensors, int n_tensors, const float* hyper,
+                           float* state, double* total_gg, float* stats, int32_t* flag, float* tnorm,
+                           float* layer_acc, void* stream) {
+  if (!rows || !tensors || !hyper || !state || !total_gg || !stats || !flag || !tnorm || !layer_acc) {
+    set_error("optimizer_step: null pointer");
+    return CFL_EINVAL;
+  }
+  return optimizer_step(rows, n_rows, tensors, n_tensors, hyper, state, total_gg, stats, flag, tnorm, layer_acc,
+                        S(stream));
+}
+
 }  // extern "C"

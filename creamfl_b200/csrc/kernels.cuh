@@ -84,4 +84,7 @@ int attn_bwd(const void*, const void*, const void*, int, int, int, int, void*, c
 int pie_pool_fwd(const void*, const void*, const float*, int, int, int, int, float*, void*, void*, cudaStream_t);
 int pie_pool_bwd(const void*, const void*, const float*, const float*, const void*, const void*, int, int, int, int,
                  void*, void*, float*, cudaStream_t);
+// optim.cu
+int optimizer_step(const void*, int, const void*, int, const float*, float*, double*, float*, int*, float*, float*,
+                   cudaStream_t);
 }  // namespace cfl

@@ -65,6 +65,7 @@ class ParamStore:
         self.shadow = torch.zeros(total, dtype=BF16, device=dev)
         self.params = params
         self.offsets = {}
+        self.padded = []
         for p, off in zip(params, offs):
             n = p.numel()
             self.offsets[id(p)] = off
@@ -72,8 +73,13 @@ class ParamStore:
                 o, i, r, s = p.shape
                 view = self.flat[off:off + n].view(o, r, s, i).permute(0, 3, 1, 2)
                 gview = self.grad[off:off + n].view(o, r, s, i).permute(0, 3, 1, 2)
-                p._w16 = self.shadow[off:off + n].view(o, r * s * i)
-                p._g2d = self.grad[off:off + n].view(o, r * s * i)
+                k = r * s * i
+                if k % 8 == 0:
+                    p._w16 = self.shadow[off:off + n].view(o, k)
+                else:  # 7x7x3 stem: rows padded to a 16-byte pitch (TMA), zero tail
+                    p._w16 = torch.zeros((o, (k + 7) // 8 * 8), dtype=BF16, device=dev)
+                    self.padded.append((p._w16, self.shadow[off:off + n].view(o, k)))
+                p._g2d = self.grad[off:off + n].view(o, k)
             else:
                 view = self.flat[off:off + n].view(p.shape)
                 gview = self.grad[off:off + n].view(p.shape)
@@ -96,6 +102,8 @@ class ParamStore:
     def sync_shadow(self) -> None:
         """Refresh the bf16 shadow after the fp32 masters changed (optimizer step, load_state_dict)."""
         ops.cast_into(self.flat, self.shadow)
+        for dst, src in self.padded:
+            dst[:, :src.shape[1]].copy_(src)
 
     def zero_grad(self) -> None:
         self.grad.zero_()
@@ -380,7 +388,6 @@ class ResNet(nn.Module):
         self.layer3 = self._make_layer(block, 256, layers[2], 2)
         self.layer4 = self._make_layer(block, 512, layers[3], 2)
         self.out_dim = 512 * block.expansion
-        self._stem16 = None
 
     def _make_layer(self, block, planes, blocks, stride):
         downsample = None
@@ -394,17 +401,8 @@ class ResNet(nn.Module):
         return nn.Sequential(*layers)
 
     def stem_shadow(self):
-        """[64, 152] bf16 filter matrix of the stem (147 columns padded to a 16-byte pitch), refreshed lazily."""
-        w = self.conv1.weight
-        ver = (w.data_ptr(), w._version, getattr(self, '_stem_epoch', 0))
-        if self._stem16 is None or self._stem16[0] != ver or self._stem16[1].device != w.device:
-            s = torch.zeros(64, 152, dtype=BF16, device=w.device)
-            s[:, :147] = w._w16
-            self._stem16 = (ver, s)
-        return self._stem16[1]
-
-    def invalidate_stem(self):
-        self._stem_epoch = getattr(self, '_stem_epoch', 0) + 1
+        """[64, 152] bf16 filter matrix of the stem (147 columns padded to a 16-byte pitch by the ParamStore)."""
+        return self.conv1.weight._w16
 
     def forward(self, images):
         x = _StemFn.apply(images, self, self.conv1.weight, self.bn1.weight, self.bn1.bias)
@@ -722,13 +720,6 @@ class PCME(StoreMixin, nn.Module):
     def _adjacent_groups(self):
         return self.txt_enc.qkv_groups()
 
-    def _after_store_build(self, st):
-        self.img_enc.cnn.invalidate_stem()
-
-    def sync_shadow(self):
-        self.store().sync_shadow()
-        self.img_enc.cnn.invalidate_stem()
-
     def _tokens(self, captions_word):
         if isinstance(captions_word, dict):
             ids, mask, tt = captions_word['input_ids'], captions_word['attention_mask'], captions_word.get(
@@ -782,13 +773,6 @@ class ImageModel(StoreMixin, nn.Module):
     def __init__(self, config):
         super().__init__()
         self.img_enc = EncoderImage(config)
-
-    def _after_store_build(self, st):
-        self.img_enc.cnn.invalidate_stem()
-
-    def sync_shadow(self):
-        self.store().sync_shadow()
-        self.img_enc.cnn.invalidate_stem()
 
     def forward(self, images):
         self.store()

@@ -196,6 +196,21 @@ int creamfl_pie_pool_bwd(const void* x_bf16, const void* h_bf16, const float* w2
                          const void* d_r_bf16, const void* d_pooled_bf16, int B, int P, int C, int Hd, void* dx_bf16,
                          void* dpre_bf16, float* dw2, void* stream);
 
+/* ---- fused optimizer step: global-norm clipping + AdamP / Adam / SGD-momentum + bf16 shadow refresh in four
+ * launches for any number of tensors.  Replaces adamp.AdamP.step (third-party adamp==0.3.0, call site
+ * src/algorithms/optimizers.py:24-28), clip_grad_norm_ (retrieval_trainer.py:211-214) and torch.optim.SGD
+ * (ClientTrainer.py:287-288).
+ *   rows    : device array of n_rows records {float* p, g, m, v; bf16* shadow; int32 len; int32 tensor} (48 bytes)
+ *   tensors : device array of n_tensors records {int32 row_begin, row_end, project, clip; int64 numel} (24 bytes)
+ *   hyper   : device float[9]  {lr, beta1|momentum, beta2, eps, weight_decay, delta, wd_ratio, max_norm, mode}
+ *             mode 0 AdamP, 1 Adam, 2 SGD with momentum
+ *   state   : device float[3]  {step, clip coefficient, gradient norm} (step advances by one per call)
+ *   total_gg: device double[1], zero on entry and on exit; stats float[3*n_rows]; flag int32[n_tensors];
+ *   tnorm, layer_acc float[n_tensors] - scratch */
+int creamfl_optimizer_step(const void* rows, int n_rows, const void* tensors, int n_tensors, const float* hyper,
+                           float* state, double* total_gg, float* stats, int32_t* flag, float* tnorm,
+                           float* layer_acc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

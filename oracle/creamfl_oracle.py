@@ -246,3 +246,61 @@ def shard_partition(n_items: int, num_users: int = 15, num_shards: int = 150,
             img_idx = list(set(img_idx) - set(idxs[rand * num_imgs:(rand + 1) * num_imgs]))
     dict_users[i] = np.concatenate([dict_users[i], img_idx])
     return dict_users
+
+
+# ------------------------------------------------------------------------------------------------- optimizer
+def clip_grad_norm(grads: Sequence[torch.Tensor], max_norm: float) -> float:
+    """torch.nn.utils.clip_grad_norm_ (retrieval_trainer.py:211-214): in-place, returns the total norm."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads))
+    coef = min(1.0, max_norm / (float(total) + 1e-6))
+    for g in grads:
+        g.mul_(coef)
+    return float(total)
+
+
+def adamp_step(params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor], exp_avgs: Sequence[torch.Tensor],
+               exp_avg_sqs: Sequence[torch.Tensor], step: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+               weight_decay: float = 0.0, delta: float = 0.1, wd_ratio: float = 0.1) -> List[int]:
+    """AdamP.step restated from the published algorithm (Heo et al., ICLR 2021, Algorithm 1/2 and the adamp==0.3.0
+    package the reference pins in requirements.txt:1 and calls at src/algorithms/optimizers.py:24-28; nesterov
+    False).  PARITY UNPINNED: the package source is not in the reference tree nor in this image.
+    `step` is the 1-based step count.  Returns, per tensor, which projection fired (0 none, 1 channel, 2 layer)."""
+    import math
+    beta1, beta2 = betas
+    fired = []
+    for p, grad, exp_avg, exp_avg_sq in zip(params, grads, exp_avgs, exp_avg_sqs):
+        bias_correction1 = 1 - beta1 ** step
+        bias_correction2 = 1 - beta2 ** step
+        exp_avg.mul_(beta1).add_(grad, alpha=1 - beta1)
+        exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+        denom = (exp_avg_sq.sqrt() / math.sqrt(bias_correction2)).add_(eps)
+        step_size = lr / bias_correction1
+        perturb = exp_avg / denom
+        ratio, which = 1.0, 0
+        if p.dim() > 1:
+            views = [lambda x: x.reshape(x.shape[0], -1), lambda x: x.reshape(1, -1)]
+            expand = [-1] + [1] * (p.dim() - 1)
+            for vi, view in enumerate(views):
+                gv, pv = view(grad), view(p)
+                cosine = (gv * pv).sum(1).abs() / (gv.norm(dim=1) + eps) / (pv.norm(dim=1) + eps)
+                if cosine.max() < delta / math.sqrt(pv.shape[1]):
+                    p_n = p / (pv.norm(dim=1).reshape(expand) + eps)
+                    perturb = perturb - p_n * view(p_n * perturb).sum(1).reshape(expand)
+                    ratio, which = wd_ratio, vi + 1
+                    break
+        if weight_decay > 0:
+            p.mul_(1 - lr * weight_decay * ratio)
+        p.add_(perturb, alpha=-step_size)
+        fired.append(which)
+    return fired
+
+
+def sgd_momentum_step(params, grads, bufs, step: int, lr: float, momentum: float = 0.9, weight_decay: float = 0.0):
+    """torch.optim.SGD semantics (ClientTrainer.py:287-288): g += wd*p; buf = g (first step) or mom*buf + g; p -= lr*buf."""
+    for p, g, buf in zip(params, grads, bufs):
+        d = g + weight_decay * p
+        if step == 1:
+            buf.copy_(d)
+        else:
+            buf.mul_(momentum).add_(d)
+        p.add_(buf, alpha=-lr)
