@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""Benchmark of the CreamFL hot path on B200 (contract: python bench.py --gpus N --steps K --warmup W).
+
+Workload (BASELINE.json configs[1]): ResNet101+BERT server, one multimodal client (ResNet18+GRU) per GPU, COCO-shape
+synthetic public batches of 128 pairs, inter+intra contrast against a 50 000-row public bank, con_w aggregation.
+
+One "step" is one mini-round over S = 4 public batches on every rank (what the reference's MMFL.train does per
+round, with the per-batch loops shortened from 391 batches to S; the public bank keeps its full size):
+  A  server train          S x (ResNet101+BERT fwd/bwd, PCME loss, clip, AdamP)        retrieval_trainer.py:192-214
+  B  server extraction     S x eval forward -> rows of the global banks                MMFL.py:194-221
+  C  client                deepcopy(old model); 1 private step; S x contrast step
+                           (client fwd/bwd + old-model fwd + inter/intra + AdamP)      MMClientTrainer.py:91-222
+  D  client generate       S x eval forward -> rows of the client representations      MMClientTrainer.py:326-359
+  E  con_w aggregation     score [50000 x 50000] per modality, all-gather, reduce      MMFL.py:298-335
+  F  server distillation   S x (fwd/bwd, kd MSE to aggregated rows, clip, AdamP)       MMFL.py:346-391
+value = public pairs per second (S*128 per rank per step, every pair counted once although it passes the encoders
+in phases A-D and F), whole job, inputs resident in HBM; e2e = the same with the step's inputs copied from pinned
+host memory inside the timed region and the step's losses read back.
+
+--impl reference times the reference's CPU implementation of the same mini-round (torch restatement in oracle/,
+fp32, all host threads) on a bounded sample; see cpu_baseline.sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+D = 256
+N_PUB = 50000
+BERT_L = 32
+CAP_L = 30
+VOCAB = 11755
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=4)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='creamfl_b200', choices=['creamfl_b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=128)
+    ap.add_argument('--sub-batches', type=int, default=4)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--phases', default='ABCDEF', help='debug: subset of phases to run')
+    return ap.parse_args()
+
+
+def unit(x):
+    return x / x.norm(dim=-1, keepdim=True)
+
+
+# ===================================================================================================== synthetic data
+def make_host_batches(S, B, seed):
+    """SURVEY.md 8d recipe: N(0,1) images, BERT ids U[1000, 30522) with CLS/SEP, lengths U{8..32} sorted descending,
+    vocab-id captions U[4, 11755) with lengths U{5..30} sorted descending, bank rows = a random subset."""
+    g = torch.Generator().manual_seed(seed)
+    pin = lambda t: t.pin_memory() if torch.cuda.is_available() else t
+    out = {}
+    out['images'] = pin(torch.randn(S, B, 3, 224, 224, generator=g))
+    lens = torch.sort(torch.randint(8, BERT_L + 1, (S, B), generator=g), dim=1, descending=True).values
+    lens[:, 0] = BERT_L
+    ids = torch.randint(1000, 30522, (S, B, BERT_L), generator=g)
+    mask = (torch.arange(BERT_L)[None, None, :] < lens[:, :, None]).long()
+    ids[:, :, 0] = 101
+    ids.scatter_(2, (lens - 1).unsqueeze(-1), 102)
+    out['ids'] = pin(ids * mask)
+    out['mask'] = pin(mask)
+    clen = torch.sort(torch.randint(5, CAP_L + 1, (B,), generator=g), descending=True).values
+    clen[0] = CAP_L
+    cmask = (torch.arange(CAP_L)[None, :] < clen[:, None]).long()
+    out['caps'] = pin(torch.randint(4, VOCAB, (S, B, CAP_L), generator=g) * cmask[None])
+    out['cap_lens'] = clen                      # identical profile for every batch (host tensor, like the loader's)
+    out['d_idx'] = pin(torch.stack([torch.randperm(N_PUB, generator=g)[:B] for _ in range(S)]))
+    out['priv_images'] = pin(torch.randn(B, 3, 224, 224, generator=g))
+    out['priv_caps'] = pin(torch.randint(4, VOCAB, (B, CAP_L), generator=g) * cmask)
+    return out
+
+
+def h2d_bytes(host):
+    return sum(v.numel() * v.element_size() for k, v in host.items() if k != 'cap_lens')
+
+
+def make_banks(device, seed):
+    g = torch.Generator().manual_seed(seed)
+    g_img = unit(torch.randn(N_PUB, D, generator=g))
+    g_txt = unit(0.7 * g_img + 0.5 * unit(torch.randn(N_PUB, D, generator=g)))
+    c_img = unit(g_img + 0.5 * unit(torch.randn(N_PUB, D, generator=g)))
+    c_txt = unit(g_txt + 0.5 * unit(torch.randn(N_PUB, D, generator=g)))
+    return [t.to(device) for t in (g_img, g_txt, c_img, c_txt)]
+
+
+# ===================================================================================================== clocks
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.index), '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        # median of the busy half (the sampler also sees the idle gaps around the timed region)
+        busy = sm[len(sm) // 2:] if sm else []
+        return {'sm_mhz': busy[len(busy) // 2] if busy else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ===================================================================================================== our arm
+class KernelTimer:
+    """CUDA-event timing of one (op, shape) inside the timed region: wraps tower_ops.conv_fprop for the dominant
+    convolution shape.  Events are recorded on the launching stream right around the C-ABI call."""
+
+    def __init__(self, T, shape_key):
+        self.T, self.key, self.events, self.orig, self.on = T, shape_key, [], T.conv_fprop, False
+
+    def install(self):
+        def wrapped(x, w2d, r, s, stride, pad):
+            if self.on and (tuple(x.shape), w2d.shape[0], r, stride) == self.key:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                y = self.orig(x, w2d, r, s, stride, pad)
+                b.record()
+                self.events.append((a, b))
+                return y
+            return self.orig(x, w2d, r, s, stride, pad)
+        self.T.conv_fprop = wrapped
+        import creamfl_b200.towers as tw
+        tw.T.conv_fprop = wrapped
+
+    def mean_ms(self):
+        if not self.events:
+            return None
+        ts = [a.elapsed_time(b) for a, b in self.events]
+        return sum(ts) / len(ts), len(ts)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from creamfl_b200 import engine, ops, tower_ops as T
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    S, B = args.sub_batches, args.batch
+    torch.manual_seed(1234 + rank)
+    server = engine.ServerEngine(D, 'resnet101', device=dev, data_parallel=world > 1)
+    client = engine.MMClient(D, device=dev)
+    if world > 1:   # identical server replicas
+        dist.broadcast(server.model.store().flat, 0)
+        server.model.sync_shadow()
+    host = make_host_batches(S, B, 1234 + rank)
+    g_img, g_txt, c_img, c_txt = make_banks(dev, 99)          # same banks on every rank (server features)
+    if world > 1:
+        c_img, c_txt = make_banks(dev, 100 + rank)[2:]        # every client has its own representations
+    resident = {k: (v.to(dev) if k != 'cap_lens' else v) for k, v in host.items()}
+    phases = args.phases
+
+    ktimer = KernelTimer(T, ((B, 14, 14, 256), 256, 3, 1))
+    ktimer.install()
+
+    def step(src, copy_in):
+        if copy_in:
+            cur = {k: (v.to(dev, non_blocking=True) if k != 'cap_lens' else v) for k, v in src.items()}
+        else:
+            cur = src
+        lens = cur['cap_lens']
+        losses = []
+        tok = lambda s: {'input_ids': cur['ids'][s], 'attention_mask': cur['mask'][s]}
+        if 'A' in phases:
+            for s in range(S):
+                losses.append(server.train_step(cur['images'][s], tok(s)))
+        if 'B' in phases:
+            for s in range(S):
+                fi, ft = server.extract(cur['images'][s], tok(s))
+                g_img.index_copy_(0, cur['d_idx'][s], fi)
+                g_txt.index_copy_(0, cur['d_idx'][s], ft)
+        g_img16, g_txt16 = ops.to_bf16(g_img), ops.to_bf16(g_txt)
+        if 'C' in phases:
+            client.begin_round()
+            losses.append(client.private_step(cur['priv_images'], cur['priv_caps'], lens))
+            for s in range(S):
+                losses.append(client.contrast_step(cur['images'][s], cur['caps'][s], lens, cur['d_idx'][s], g_img, g_txt,
+                                                   g_img16, g_txt16))
+        if 'D' in phases:
+            for s in range(S):
+                ci, ct = client.generate(cur['images'][s], cur['caps'][s], lens)
+                c_img.index_copy_(0, cur['d_idx'][s], ci)
+                c_txt.index_copy_(0, cur['d_idx'][s], ct)
+        agg_img = agg_txt = None
+        if 'E' in phases:
+            agg_img = engine.exchange_and_aggregate(c_img, g_txt16)
+            agg_txt = engine.exchange_and_aggregate(c_txt, g_img16)
+        if 'F' in phases:
+            if agg_img is None:
+                agg_img, agg_txt = c_img, c_txt
+            for s in range(S):
+                losses.append(server.distill_step(cur['images'][s], tok(s), cur['d_idx'][s], agg_img, agg_txt))
+        return torch.stack([l.reshape(()) for l in losses]) if losses else torch.zeros(1, device=dev)
+
+    def timed(src, copy_in, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ops.launches()
+        t0.record()
+        out = None
+        for _ in range(n):
+            out = step(src, copy_in)
+            if copy_in:
+                out = out.cpu()           # device -> host read of the step's losses
+        t1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, ops.launches() - l0, out
+
+    for _ in range(args.warmup):
+        step(resident, False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ktimer.on = True
+    ms_res, launches, out = timed(resident, False, args.steps)
+    ktimer.on = False
+    clocks = sampler.stop()
+    step(host, True)
+    ms_e2e, _, out_e2e = timed(host, True, args.steps)
+    finite = bool(torch.isfinite(out_e2e).all())
+
+    pairs = S * B * world * args.steps
+    value = pairs / (ms_res / 1e3)
+    e2e = pairs / (ms_e2e / 1e3)
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / 'MEASURED_PEAKS.json').read_text())
+    except OSError:
+        pass
+    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+    roofline = None
+    km = ktimer.mean_ms()
+    if km:
+        flops = 2.0 * B * 14 * 14 * 256 * 9 * 256      # conv3x3 256->256 @14x14, B images
+        ach = flops / (km[0] * 1e-3) / 1e12
+        roofline = {'bound': 'tensor', 'kernel': 'conv_tc_kernel<128,0> fprop 3x3 256->256 @14x14 (22 of 104 ResNet101 convs)',
+                    'achieved': round(ach, 1), 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': round(ach / peak_tf, 4),
+                    'traffic': None, 'launches_timed': km[1], 'avg_launch_ms': round(km[0], 4),
+                    'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback'}
+    line = {
+        'metric': 'image-text pairs/sec per FL round', 'value': round(value, 1), 'unit': 'pairs/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms_res / args.steps, 2),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': 'configs[1]: ResNet101+BERT server, 1 multimodal client (ResNet18+GRU) per GPU, '
+                               'COCO-shape synthetic batch 128, inter+intra contrast vs N_pub=50000, con_w aggregation',
+                   'global_batch': B * world, 'sub_batches_per_step': S, 'n_pub': N_PUB, 'embed_dim': D,
+                   'bert_seq_len': BERT_L, 'phases': phases, 'l2': 'inputs_exceed_l2 (308 MB images + 0.6 GB '
+                   'parameters per step >> 126 MB L2)', 'parallelism': f'client-per-gpu x{world}, server replicated '
+                   'with flat-gradient all-reduce' if world > 1 else 'single gpu'},
+        'e2e': {'value': round(e2e, 1), 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d_bytes(host),
+                'd2h_bytes_per_step': int(out_e2e.numel() * 4), 'ms_per_step': round(ms_e2e / args.steps, 2)},
+        'gpu_launches': int(launches), 'clocks': clocks, 'losses_finite': finite,
+    }
+    if roofline:
+        line['roofline'] = roofline
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline(steps=1, warmup=0)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ===================================================================================================== reference arm
+def cpu_mini_round(B, n_conw, seed=0):
+    """The reference's per-round path on the host (fp32 torch, restated in oracle/): returns a closure running one
+    mini-round with S = 1 at batch B, con_w at n_conw rows, and the number of public pairs it processes."""
+    from oracle import torch_towers as RT, creamfl_oracle as O
+    from creamfl_b200.clients import GRUEncoderText
+    torch.manual_seed(seed)
+    server = RT.RefPCME('resnet101', D)
+    client_img = RT.RefEncoderImage('resnet18', D)
+    client_txt = GRUEncoderText(VOCAB, 300, D)
+    shift = torch.nn.Parameter(torch.tensor(15.0))
+    scale = torch.nn.Parameter(torch.tensor(15.0))
+    s_params = list(server.parameters()) + [shift, scale]
+    c_params = list(client_img.parameters()) + list(client_txt.parameters())
+    # AdamP is not installable here: torch Adam stands in for the optimizer cost on the host
+    s_opt = torch.optim.Adam(s_params, lr=2e-4)
+    c_opt = torch.optim.Adam(c_params, lr=2e-4)
+    host = make_host_batches(1, B, 7)
+    g = torch.Generator().manual_seed(5)
+    g_img = unit(torch.randn(N_PUB, D, generator=g))
+    g_txt = unit(0.7 * g_img + 0.5 * unit(torch.randn(N_PUB, D, generator=g)))
+    cv_i = unit(g_img[:n_conw] + 0.5 * unit(torch.randn(n_conw, D, generator=g)))
+    cv_t = unit(g_txt[:n_conw] + 0.5 * unit(torch.randn(n_conw, D, generator=g)))
+    import copy
+
+    def run():
+        images, ids, mask = host['images'][0], host['ids'][0], host['mask'][0]
+        caps, lens, d_idx = host['caps'][0], host['cap_lens'], host['d_idx'][0]
+        server.train()                                                    # A
+        o = server(images, ids, mask)
+        loss, _ = O.pcme_loss(o['image_features'], o['caption_features'], shift, scale)
+        s_opt.zero_grad(); loss.backward()
+        torch.nn.utils.clip_grad_norm_(server.parameters(), 2.0); s_opt.step()
+        server.eval()                                                     # B
+        with torch.no_grad():
+            o = server(images, ids, mask)
+            g_img[d_idx] = o['image_features']; g_txt[d_idx] = o['caption_features']
+        old_i, old_t = copy.deepcopy(client_img).eval(), copy.deepcopy(client_txt).eval()   # C
+        client_img.train(); client_txt.train()
+        zi, zt = client_img(host['priv_images'])['embedding'], client_txt(host['priv_caps'], lens)['embedding']
+        loss, _ = O.pcme_loss(zi, zt, shift, scale)
+        c_opt.zero_grad(); loss.backward()
+        torch.nn.utils.clip_grad_norm_(c_params, 2.0); c_opt.step()
+        zi, zt = client_img(images)['embedding'], client_txt(caps, lens)['embedding']
+        with torch.no_grad():
+            oi, ot = old_i(images)['embedding'], old_t(caps, lens)['embedding']
+        parts = O.mm_client_contrast_loss(zi, zt, oi, ot, g_img, g_txt, d_idx.tolist(), 0.5, False)
+        c_opt.zero_grad(); parts['loss'].backward()
+        torch.nn.utils.clip_grad_norm_(c_params, 2.0); c_opt.step()
+        client_img.eval(); client_txt.eval()                              # D
+        with torch.no_grad():
+            ci, ct = client_img(images)['embedding'], client_txt(caps, lens)['embedding']
+        t0 = time.perf_counter()                                          # E (at n_conw rows)
+        agg_i, _ = O.conw_aggregate([cv_i], g_txt[:n_conw])
+        agg_t, _ = O.conw_aggregate([cv_t], g_img[:n_conw])
+        t_conw = time.perf_counter() - t0
+        server.train()                                                    # F
+        o = server(images, ids, mask)
+        tgt = d_idx % n_conw
+        loss = 0.3 * O.distill_mse(o['image_features'], agg_i, tgt) + 0.3 * O.distill_mse(o['caption_features'], agg_t, tgt)
+        s_opt.zero_grad(); loss.backward()
+        torch.nn.utils.clip_grad_norm_(server.parameters(), 2.0); s_opt.step()
+        return t_conw
+    return run
+
+
+def cpu_baseline(steps=1, warmup=0, B=16, n_conw=8192, S=4, B_full=128):
+    """Seconds per public pair of the host path, put on the same accounting as the GPU arm: per-batch phases scale
+    with pairs; the con_w phase is measured at n_conw rows, scaled by (N_pub / n_conw)^2 and amortised over the
+    S * B_full pairs of a mini-round exactly like the GPU arm does."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    run = cpu_mini_round(B, n_conw)
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    t_conw = 0.0
+    for _ in range(steps):
+        t_conw += run()
+    total = time.perf_counter() - t0
+    per_pair = (total - t_conw) / (steps * B)
+    conw_full = (t_conw / steps) * (N_PUB / n_conw) ** 2
+    sec_per_pair = per_pair + conw_full / (S * B_full)
+    return {'value': round(1.0 / sec_per_pair, 3), 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
+            'sample': f'{steps} mini-round(s) of the torch-fp32 restatement (oracle/) at batch {B}, S=1: phases A-D,F '
+                      f'{total - t_conw:.1f} s; con_w at {n_conw} rows {t_conw:.1f} s scaled x{(N_PUB / n_conw) ** 2:.1f} '
+                      f'to N_pub={N_PUB} and amortised over {S}x{B_full} pairs; torch Adam stands in for AdamP',
+            'wall_s': round(total, 1)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    base = cpu_baseline(steps=max(1, args.steps), warmup=min(1, args.warmup))
+    wall = time.perf_counter() - t0
+    line = {
+        'impl': 'reference', 'metric': 'image-text pairs/sec per FL round', 'value': base['value'], 'unit': 'pairs/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': round(1e3 * wall / max(1, args.steps + min(1, args.warmup)), 1), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'configs[1] mini-round on the host: reference CPU path (torch fp32 restatement of '
+                               'src/networks + src/criterions + MMClientTrainer/MMFL loops), bounded sample'},
+        'cpu_baseline': base,
+        'e2e': {'value': base['value'], 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py: no CUDA device - the creamfl_b200 hot path has no CPU fallback '
+                             '(use --impl reference for the host baseline)')
+        run_ours(a)

@@ -1,0 +1,105 @@
+"""Client-side models of the hot path.
+
+ClientPCME mirrors the multimodal client's PCME(ResNet18 + GRU) (src/networks/models/pcme.py with
+`config.not_bert = True`, forced at MMFL.py:163): the image tower runs on the creamfl_b200 kernels
+(towers.EncoderImage), the text tower (Embedding -> packed bi-GRU -> PIENet, caption_encoder.py:29-116) stays on
+torch / cuDNN for now - SURVEY.md 8f ranks the GRU kernel as next row f2.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+
+from . import ops
+from .towers import EncoderImage, StoreMixin, ParamStore
+
+
+def get_pad_mask(max_length, lengths, set_pad_to_one=True):
+    """caption_encoder.py:19-26."""
+    ind = torch.arange(0, max_length).unsqueeze(0)
+    mask = (ind >= lengths.unsqueeze(1)) if set_pad_to_one else (ind < lengths.unsqueeze(1))
+    return mask
+
+
+class _TorchPIENet(nn.Module):
+    """pie_model.PIENet with the pad-mask path (text variant: d_in = 300, d_h = 150), plain torch."""
+
+    def __init__(self, d_in, d_out, d_h):
+        super().__init__()
+        self.attention = nn.Module()
+        self.attention.w_1 = nn.Linear(d_in, d_h, bias=False)
+        self.attention.w_2 = nn.Linear(d_h, 1, bias=False)
+        self.fc = nn.Linear(d_in, d_out)
+        self.layer_norm = nn.LayerNorm(d_out)
+        nn.init.xavier_uniform_(self.attention.w_1.weight)
+        nn.init.xavier_uniform_(self.attention.w_2.weight)
+        nn.init.xavier_uniform_(self.fc.weight)
+        nn.init.constant_(self.fc.bias, 0.0)
+
+    def forward(self, out, x, pad_mask):
+        attn = self.attention.w_2(torch.tanh(self.attention.w_1(x)))            # pie_model.py:30
+        attn = attn.masked_fill(pad_mask.unsqueeze(-1), float('-inf'))            # :31-34
+        attn = torch.softmax(attn, dim=1)
+        residual = torch.bmm(attn.transpose(1, 2), x).squeeze(1)                  # :37-39
+        residual = torch.sigmoid(self.fc(residual))                               # :63
+        return self.layer_norm(out + residual), attn, residual                    # :66
+
+
+class GRUEncoderText(nn.Module):
+    """caption_encoder.EncoderText (wemb_type None -> xavier init; GloVe vectors are data, not on the box)."""
+
+    def __init__(self, vocab_size, word_dim, embed_dim):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.embed = nn.Embedding(vocab_size, word_dim)
+        self.rnn = nn.GRU(word_dim, embed_dim // 2, bidirectional=True, batch_first=True)
+        self.pie_net = _TorchPIENet(word_dim, embed_dim, word_dim // 2)
+        nn.init.xavier_uniform_(self.embed.weight)
+
+    def forward(self, x, lengths):
+        lengths_cpu = lengths.cpu() if torch.is_tensor(lengths) else torch.as_tensor(lengths)
+        wemb_out = self.embed(x)
+        packed = pack_padded_sequence(wemb_out, lengths_cpu, batch_first=True)
+        rnn_out, _ = self.rnn(packed)
+        padded, _ = pad_packed_sequence(rnn_out, batch_first=True)
+        idx = (lengths_cpu - 1).to(x.device).view(-1, 1, 1).expand(-1, 1, self.embed_dim)
+        out = torch.gather(padded, 1, idx).squeeze(1)                             # caption_encoder.py:99-101
+        pad_mask = get_pad_mask(wemb_out.shape[1], lengths_cpu, True).to(x.device)
+        out, attn, residual = self.pie_net(out, wemb_out, pad_mask)
+        return {'embedding': torch.nn.functional.normalize(out, p=2, dim=-1)}     # :109
+
+
+class ClientPCME(StoreMixin, nn.Module):
+    """PCME(ResNet18 + GRU) of a multimodal client; same forward signature and output dict as pcme.PCME."""
+
+    def __init__(self, vocab_size=11755, embed_dim=256, cnn_type='resnet18', word_dim=300):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.n_embeddings = 1
+        self.img_enc = EncoderImage({'embed_dim': embed_dim, 'cnn_type': cnn_type})
+        self.txt_enc = GRUEncoderText(vocab_size, word_dim, embed_dim)
+
+    def store(self) -> ParamStore:       # only the CUDA image tower lives in the flat store
+        st = self.__dict__.get('_store')
+        first = next(self.img_enc.parameters())
+        if st is None or not st.intact() or st.params[0] is not first:
+            st = ParamStore(self.img_enc)
+            self.__dict__['_store'] = st
+        return st
+
+    def image_forward(self, images):
+        self.store()
+        return self.img_enc(images)
+
+    def forward(self, images, sentences, captions_word, lengths):
+        self.store()
+        image_output = self.img_enc(images)
+        caption_output = self.txt_enc(sentences, lengths)
+        return {
+            'image_features': image_output['embedding'], 'image_attentions': None, 'image_residuals': None,
+            'image_logsigma': None, 'image_logsigma_att': None,
+            'caption_features': caption_output['embedding'], 'caption_attentions': None, 'caption_residuals': None,
+            'caption_logsigma': None, 'caption_logsigma_att': None,
+        }

@@ -136,7 +136,8 @@ opt_decide_kernel(const OptTensor* __restrict__ tensors, int n_tensors, const fl
 
 // K3: moments + update (rows of tensors with flag 0 or 1); flag 2 rows only accumulate <p^, u> for K4.
 __global__ void __launch_bounds__(kOptThreads)
-opt_update_kernel(const OptRow* __restrict__ rows, int n_rows, const float* __restrict__ stats,
+opt_update_kernel(const OptRow* __restrict__ rows, const OptTensor* __restrict__ tensors, int n_rows,
+                  const float* __restrict__ stats,
                   const float* __restrict__ hyper, const float* __restrict__ state, const int* __restrict__ flag,
                   const float* __restrict__ tnorm, float* __restrict__ layer_acc) {
   __shared__ float red[4];
@@ -145,7 +146,7 @@ opt_update_kernel(const OptRow* __restrict__ rows, int n_rows, const float* __re
   const OptRow row = rows[r];
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], wd_ratio = hyper[6];
   const int mode = (int)hyper[8];
-  const float coef = state[1];
+  const float coef = tensors[row.tensor].clip ? state[1] : 1.0f;   // clip_grad_norm_ scales model gradients only
   if (mode == 2) {  // SGD with momentum (torch semantics: g += wd*p ; buf = mom*buf + g ; p -= lr*buf)
     for (int i = threadIdx.x; i < row.len; i += kOptThreads) {
       const float p = row.p[i];
@@ -237,7 +238,7 @@ int optimizer_step(const void* rows, int n_rows, const void* tensors, int n_tens
   const OptTensor* t = reinterpret_cast<const OptTensor*>(tensors);
   opt_row_stats_kernel<<<n_rows, kOptThreads, 0, st>>>(r, t, n_rows, stats, total_gg);
   opt_decide_kernel<<<n_tensors, 256, 0, st>>>(t, n_tensors, stats, hyper, state, total_gg, flag, tnorm, layer_acc);
-  opt_update_kernel<<<n_rows, kOptThreads, 0, st>>>(r, n_rows, stats, hyper, state, flag, tnorm, layer_acc);
+  opt_update_kernel<<<n_rows, kOptThreads, 0, st>>>(r, t, n_rows, stats, hyper, state, flag, tnorm, layer_acc);
   opt_layer_fix_kernel<<<n_rows, kOptThreads, 0, st>>>(r, n_rows, hyper, state, flag, tnorm, layer_acc, total_gg);
   return check_launch("optimizer_step");
 }

@@ -1,0 +1,169 @@
+"""Step drivers of the CreamFL hot path: what the reference's trainers do per batch, on the creamfl_b200 kernels.
+
+  ServerEngine.train_step    - retrieval_trainer.TrainerEngine.train body (retrieval_trainer.py:192-214)
+  ServerEngine.extract       - global public representations (MMFL.py:194-221)
+  ServerEngine.distill_step  - MMFL.distill body (MMFL.py:346-391)
+  MMClient.private_step      - MMClientTrainer.train_epoch, private pass (MMClientTrainer.py:118-143)
+  MMClient.contrast_step     - inter + intra contrast pass (MMClientTrainer.py:154-222)
+  MMClient.generate          - MMClientTrainer.generate_logits (MMClientTrainer.py:326-359)
+  aggregate                  - MMFL.distill.aggregation, `con_w` (MMFL.py:298-335)
+  exchange_*                 - the one real exchange of the path when clients are sharded one per GPU: all-gather of
+                               the public-set representations into the server ensemble
+
+Everything numerical happens in libcreamfl_b200.so; this file sequences calls and owns buffers.  Apex O2 loss
+scaling has no counterpart (bf16 needs none).
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .clients import ClientPCME
+from .criterions import get_criterion
+from .optim import FusedOptimizer
+from .towers import PCME
+
+PCME_CRITERION_CFG = {'init_shift': 15, 'init_negative_scale': 15, 'num_samples': 7}    # coco.yaml:41-47
+
+
+def _features(output: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+    return output['image_features'], output['caption_features']
+
+
+class ServerEngine:
+    def __init__(self, embed_dim: int = 256, cnn_type: str = 'resnet101', lr: float = 2e-4, grad_clip: float = 2.0,
+                 kd_weight: float = 0.3, device: Optional[torch.device] = None, data_parallel: bool = False):
+        self.device = device or torch.device('cuda', torch.cuda.current_device())
+        self.model = PCME(None, {'embed_dim': embed_dim, 'cnn_type': cnn_type, 'not_bert': False}).to(self.device)
+        self.criterion = get_criterion('pcme', PCME_CRITERION_CFG).to(self.device)
+        self.model.store()
+        params = [p for p in self.model.parameters() if p.requires_grad] + list(self.criterion.parameters())
+        self.optimizer = FusedOptimizer(params, lr=lr, max_norm=grad_clip, mode='adamp',
+                                        no_clip=list(self.criterion.parameters())).attach_stores(self.model)
+        self.kd_weight = kd_weight
+        self.data_parallel = data_parallel and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _sync_grads(self) -> None:
+        """Replicated server, batches sharded over ranks: average the flat gradient buffer (one NCCL call)."""
+        if self.data_parallel:
+            g = self.model.store().grad
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            g.mul_(1.0 / dist.get_world_size())
+            for p in self.criterion.parameters():
+                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
+                p.grad.mul_(1.0 / dist.get_world_size())
+
+    def train_step(self, images, tokens) -> torch.Tensor:
+        self.model.train()
+        output = self.model(images, None, tokens, None)
+        loss, _ = self.criterion(**output)
+        self.optimizer.zero_grad()
+        loss.backward()
+        self._sync_grads()
+        self.optimizer.step()
+        return loss.detach()
+
+    @torch.no_grad()
+    def extract(self, images, tokens) -> Tuple[torch.Tensor, torch.Tensor]:
+        self.model.eval()
+        return _features(self.model(images, None, tokens, None))
+
+    def distill_step(self, images, tokens, d_idx, agg_img, agg_txt, img_terms: int = 1, txt_terms: int = 1):
+        """`img_terms` / `txt_terms`: how many times the reference adds the image / text MSE - once per client type
+        that carries the modality (MMFL.py:361-378; 2 each when image, text and multimodal clients all exist)."""
+        self.model.train()
+        out_img, out_txt = _features(self.model(images, None, tokens, None))
+        loss = 0
+        if agg_img is not None and img_terms:
+            loss = loss + (self.kd_weight * img_terms) * ops.mse_gather_loss(out_img, agg_img, d_idx)
+        if agg_txt is not None and txt_terms:
+            loss = loss + (self.kd_weight * txt_terms) * ops.mse_gather_loss(out_txt, agg_txt, d_idx)
+        self.optimizer.zero_grad()
+        loss.backward()
+        self._sync_grads()
+        self.optimizer.step()
+        return loss.detach()
+
+
+class MMClient:
+    def __init__(self, embed_dim: int = 256, lr: float = 2e-4, grad_clip: float = 2.0, interintra_weight: float = 0.5,
+                 vocab_size: int = 11755, device: Optional[torch.device] = None):
+        self.device = device or torch.device('cuda', torch.cuda.current_device())
+        self.model = ClientPCME(vocab_size, embed_dim).to(self.device)
+        self.criterion = get_criterion('pcme', PCME_CRITERION_CFG).to(self.device)
+        self.model.store()
+        params = [p for p in self.model.parameters() if p.requires_grad] + list(self.criterion.parameters())
+        self.optimizer = FusedOptimizer(params, lr=lr, max_norm=grad_clip, mode='adamp',
+                                        no_clip=list(self.criterion.parameters())).attach_stores(self.model)
+        self.w = interintra_weight
+        self.old_model = None
+
+    def begin_round(self) -> None:
+        self.old_model = copy.deepcopy(self.model).eval()            # MMClientTrainer.py:92-93
+        self.old_model.store()
+        self.model.train()
+
+    def private_step(self, images, captions, lengths) -> torch.Tensor:
+        self.model.train()
+        output = self.model(images, captions, None, lengths)
+        loss, _ = self.criterion(**output)
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    def contrast_step(self, images, captions, lengths, d_idx, g_img, g_txt, g_img16, g_txt16, intra: bool = True,
+                      inter: bool = True, loss_scale: bool = False) -> torch.Tensor:
+        """g_img / g_txt: fp32 [N_pub, D] server features; g_*16 their bf16 copies (made once per round)."""
+        self.model.train()
+        self.optimizer.zero_grad()
+        out_img, out_txt = _features(self.model(images, captions, None, lengths))
+        b = images.shape[0]
+        loss_intra = loss_inter = None
+        if intra:
+            with torch.no_grad():
+                old_img, old_txt = _features(self.old_model(images, captions, None, lengths))
+            loss_intra = ops.moon_intra_loss(out_img, old_img, g_img, d_idx, 2.0, 2 * b) + \
+                ops.moon_intra_loss(out_txt, old_txt, g_txt, d_idx, 2.0, 2 * b)
+        if inter:
+            loss_inter = ops.infonce_loss(out_img, g_txt16, d_idx, 2.0) + ops.infonce_loss(out_txt, g_img16, d_idx, 2.0)
+        if intra and inter:
+            if not loss_scale:
+                loss = (loss_intra + loss_inter) * self.w
+            else:
+                loss = (loss_intra + loss_inter / (loss_inter / loss_intra).detach()) * self.w
+        else:
+            loss = loss_intra if intra else loss_inter                # MMClientTrainer.py:264,308: no weight
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    @torch.no_grad()
+    def generate(self, images, captions, lengths) -> Tuple[torch.Tensor, torch.Tensor]:
+        self.model.eval()
+        return _features(self.model(images, captions, None, lengths))
+
+
+def aggregate(vecs: Sequence[torch.Tensor], global_other: torch.Tensor) -> torch.Tensor:
+    """con_w aggregation of one modality on one device (MMFL.py:298-314)."""
+    return ops.conw_aggregate(list(vecs), global_other)
+
+
+def exchange_and_aggregate(own_vec: torch.Tensor, global_other16: torch.Tensor) -> torch.Tensor:
+    """Clients sharded one per rank: every rank scores its own client's [N_pub, D] representations against the
+    replicated server features (tcgen05, 1.28 TFLOP each), then the ranks all-gather scores (200 KB) and
+    representations (51 MB) and every rank forms the softmax-over-clients weighted sum - the single exchange step of
+    the path.  With one rank this is `aggregate([own_vec], ...)`."""
+    score = ops.conw_score(ops.to_bf16(own_vec), global_other16)
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return ops.conw_reduce([own_vec], score.unsqueeze(0))
+    world = dist.get_world_size()
+    scores = torch.empty((world,) + score.shape, dtype=score.dtype, device=score.device)
+    vecs = torch.empty((world,) + own_vec.shape, dtype=own_vec.dtype, device=own_vec.device)
+    dist.all_gather_into_tensor(scores, score.contiguous())
+    dist.all_gather_into_tensor(vecs, own_vec.contiguous())
+    return ops.conw_reduce([vecs[r] for r in range(world)], scores)
