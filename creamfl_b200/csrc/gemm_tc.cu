@@ -19,37 +19,64 @@
 // TMEM holds two accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "kernels.cuh"
 #include "ptx.cuh"
+#include <string.h>
 
 namespace cfl {
 
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
+constexpr int kGemmThreads = 384;   // 4 control warps + 8 epilogue warps
 
 template <int BN>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int kStages = (BN == 128) ? 4 : 6;
+  static constexpr int kOutBytes = kBM * BN * 2;            // bf16 output tile staged for the TMA store
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kOutBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t kTmemCols = 2 * BN;              // two accumulator buffers (power of two for BN 64/128)
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf with |error| <= 1.5e-7 (Abramowitz-Stegun 7.1.26): one ex2, one rcp, 6 FMA - the epilogue must not outlast
+// the MMAs of the next tile.
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float y = 1.0f - p * t * ex2_approx(-1.4426950408889634f * ax * ax);
+  return copysignf(y, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float dgelu_erf(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * ex2_approx(-0.72134752044448170f * x * x);
   return cdf + x * pdf;
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(256, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* sout = smem + Cfg::kStages * Cfg::kStageBytes;    // [2][kOutBytes], 1024-aligned (stage sizes are)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sout + 2 * Cfg::kOutBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::kStages;
   uint64_t* tfull = bars + 2 * Cfg::kStages;
@@ -68,6 +95,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_out) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
@@ -76,7 +104,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     fence_mbar_init();
   }
@@ -160,8 +188,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue
-    const int q = warp & 3;
+    // ------------------------------------------------------------ epilogue: 8 warps, thread = row, warp set = column half
+    constexpr int HC = BN / 2;             // columns per thread
+    const int q = warp & 3;                // TMEM lane group of this warp
+    const int half = (warp - 4) >> 2;      // column half
+    const int rloc = q * 32 + lane;
+    const bool issuer = (warp == 4 && lane == 0);
     int it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
       const int m_blk = u % num_m;
@@ -170,21 +202,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int buf = it & 1;
       const uint32_t bphase = (it >> 1) & 1;
       const bool has_k = ks * kb_per < nkb;
+      uint8_t* stile = sout + buf * Cfg::kOutBytes;
+      if (p.tma_out) {
+        // the TMA store that last read this staging buffer (two tiles ago) must have drained
+        if (issuer) tma_store_wait_read<1>();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
-      const int row = m_blk * kBM + q * 32 + lane;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+      const int row = m_blk * kBM + rloc;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + half * HC;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < HC / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
-        const int col0 = n_blk * BN + c * 32;
-        if (row < p.M && col0 < p.N && has_k) {
-          float f[32];
+        const int ctile = half * HC + c * 32;          // column offset inside the tile
+        const int col0 = n_blk * BN + ctile;
+        const bool live = row < p.M && col0 < p.N && has_k;
+        float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-          const bool full_chunk = (col0 + 32 <= p.N);
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        const bool full_chunk = (col0 + 32 <= p.N);
+        if (live) {
           if (p.bias != nullptr && ks == 0) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -193,9 +233,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.add != nullptr && ks == 0) {
             if (p.add_bf16) {
               const __nv_bfloat16* ar = reinterpret_cast<const __nv_bfloat16*>(p.add) + (long long)row * p.ld_add + col0;
+              if (full_chunk && ((reinterpret_cast<uintptr_t>(ar) & 15) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (full_chunk || col0 + j < p.N) f[j] += __bfloat162float(ar[j]);
+                for (int j = 0; j < 32; j += 8) {
+                  const uint4 pk = __ldg(reinterpret_cast<const uint4*>(ar + j));
+                  const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+                    f[j + 2 * i] += t2.x;
+                    f[j + 2 * i + 1] += t2.y;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (full_chunk || col0 + j < p.N) f[j] += __bfloat162float(ar[j]);
+              }
             } else {
               const float* ar = reinterpret_cast<const float*>(p.add) + (long long)row * p.ld_add + col0;
 #pragma unroll
@@ -204,10 +258,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           if (p.out2 != nullptr) {
-            __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + (long long)row * p.ldo + col0;
+            __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + (long long)row * p.ldo2 + col0;
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(o2) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full_chunk || col0 + j < p.N) o2[j] = __float2bfloat16(f[j]);
+              for (int j = 0; j < 32; j += 8)
+                *reinterpret_cast<uint4*>(o2 + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                                               pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (full_chunk || col0 + j < p.N) o2[j] = __float2bfloat16(f[j]);
+            }
           }
           if (p.act == 1) {
 #pragma unroll
@@ -217,20 +278,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           } else if (p.act == 3) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+            for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j]);
           } else if (p.act == 6) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = 1.0f / (1.0f + __expf(-f[j]));
+            for (int j = 0; j < 32; ++j) f[j] = __frcp_rn(1.0f + ex2_approx(-1.4426950408889634f * f[j]));
           } else if (p.act == 4 || p.act == 5) {
             const __nv_bfloat16* xr = p.aux + (long long)row * p.ld_aux + col0;
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(xr) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (full_chunk || col0 + j < p.N) {
-                const float x = __bfloat162float(xr[j]);
-                f[j] *= (p.act == 4) ? dgelu_erf(x) : (x > 0.0f ? 1.0f : 0.0f);
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 pk = __ldg(reinterpret_cast<const uint4*>(xr + j));
+                const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+                  f[j + 2 * i] *= (p.act == 4) ? dgelu_erf(t2.x) : (t2.x > 0.0f ? 1.0f : 0.0f);
+                  f[j + 2 * i + 1] *= (p.act == 4) ? dgelu_erf(t2.y) : (t2.y > 0.0f ? 1.0f : 0.0f);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (full_chunk || col0 + j < p.N) {
+                  const float x = __bfloat162float(xr[j]);
+                  f[j] *= (p.act == 4) ? dgelu_erf(x) : (x > 0.0f ? 1.0f : 0.0f);
+                }
               }
             }
           }
+        }
+        if (p.tma_out) {
+          // stage the bf16 row chunk: 128-byte rows, 16-byte units XOR-swizzled like the TMA store map expects
+          constexpr int kUnitsPerRow = (BN == 128) ? 8 : 8;   // a staged row is always 64 columns = 128 bytes
+          const int region = (BN == 128) ? half : 0;          // BN = 128: one 64-column region per half
+          const int unit0 = (BN == 128) ? c * 4 : half * 4;   // first 16-byte unit of this chunk inside the row
+          uint8_t* rbase = stile + region * (kBM * 128);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 pk = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                        pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+            *reinterpret_cast<uint4*>(rbase + sw128_offset(rloc, unit0 + j)) = pk;
+          }
+          (void)kUnitsPerRow;
+        } else if (live) {
           if (p.split_k > 1 || p.atomic_out) {
             float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
 #pragma unroll
@@ -240,18 +330,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0;
             if (full_chunk && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j + 0], f[j + 1]);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(o + j) = pk;
-              }
+              for (int j = 0; j < 32; j += 8)
+                *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                                              pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
@@ -271,10 +352,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      // accumulator is consumed: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (p.tma_out) {
+        fence_proxy_async_smem();                         // generic-proxy smem writes -> visible to the TMA engine
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (issuer && has_k) {
+#pragma unroll
+          for (int r = 0; r < BN / 64; ++r)
+            tma_store_2d(&tmC, stile + r * (kBM * 128), n_blk * BN + r * 64, m_blk * kBM);
+          tma_store_commit();
+        }
+      }
     }
+    if (p.tma_out && issuer) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -286,7 +379,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+                       cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
@@ -302,7 +396,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   const int num_n = (p.N + BN - 1) / BN;
   const int units = num_m * num_n * p.split_k;
   const int grid = units < sm_count() ? units : sm_count();
-  kern<<<grid, 256, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -331,8 +425,14 @@ int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long l
   }
   // Narrow outputs waste MMA columns: pick the tile width from N.
   const int BN = (p.N <= 64) ? 64 : 128;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc;
+  memset(&tc, 0, sizeof(tc));
   int rc;
+  // bf16 outputs that TMA can address leave through a staged, fully coalesced TMA store
+  p.tma_out = (p.out_bf16 && p.split_k == 1 && !p.atomic_out && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+               ((p.ldo * 2) & 15) == 0) ? 1 : 0;
+  if (p.out2 != nullptr && p.ldo2 == 0) p.ldo2 = p.ldo;
+  if (p.tma_out && (rc = make_tmap_2d(&tc, p.out, 2, p.M, p.N, p.ldo, 64, kBM))) return rc;
   if (!a_mn)
     rc = make_tmap_2d(&ta, a, 2, p.M, p.K, lda, kBK, kBM);
   else
@@ -346,10 +446,10 @@ int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long l
 
 #define CFL_DISPATCH(BNV)                                                                      \
   do {                                                                                         \
-    if (!a_mn && !b_mn) return launch_gemm<BNV, false, false>(ta, tb, p, stream);              \
-    if (!a_mn && b_mn) return launch_gemm<BNV, false, true>(ta, tb, p, stream);                \
-    if (a_mn && !b_mn) return launch_gemm<BNV, true, false>(ta, tb, p, stream);                \
-    return launch_gemm<BNV, true, true>(ta, tb, p, stream);                                    \
+    if (!a_mn && !b_mn) return launch_gemm<BNV, false, false>(ta, tb, tc, p, stream);          \
+    if (!a_mn && b_mn) return launch_gemm<BNV, false, true>(ta, tb, tc, p, stream);            \
+    if (a_mn && !b_mn) return launch_gemm<BNV, true, false>(ta, tb, tc, p, stream);            \
+    return launch_gemm<BNV, true, true>(ta, tb, tc, p, stream);                                \
   } while (0)
   if (BN == 64) CFL_DISPATCH(64);
   CFL_DISPATCH(128);

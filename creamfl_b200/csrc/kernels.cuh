@@ -20,6 +20,8 @@ struct GemmParams {
   const __nv_bfloat16* aux;
   long long ld_aux;
   int atomic_out;  // accumulate into the fp32 output with atomics even when split_k == 1
+  long long ldo2;  // pitch of out2 (0: same as ldo)
+  int tma_out;     // set by gemm_bf16: bf16 output leaves through a staged TMA store
 };
 int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, GemmParams p,
               cudaStream_t stream);

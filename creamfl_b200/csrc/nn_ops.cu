@@ -62,13 +62,23 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, double*
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.0f;
   if (r < rows) {
-    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
-      float f[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(x + p * C + g * 8), f);
+    const long long stride = (long long)gridDim.x * rows;
+    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += 4 * stride) {
+      bf16x8 raw[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s[i] += f[i];
-        q[i] = fmaf(f[i], f[i], q[i]);
+      for (int u = 0; u < 4; ++u)          // four independent 16-byte loads in flight per thread
+        if (p + u * stride < P) raw[u] = *reinterpret_cast<const bf16x8*>(x + (p + u * stride) * C + g * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (p + u * stride < P) {
+          float f[8];
+          unpack8(raw[u], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            s[i] += f[i];
+            q[i] = fmaf(f[i], f[i], q[i]);
+          }
+        }
       }
     }
 #pragma unroll
@@ -125,32 +135,46 @@ __global__ void bn_eval_affine_kernel(int C, const float* __restrict__ gamma, co
   shift[c] = beta[c] - running_mean[c] * sc;
 }
 
-// y = [relu]( x * scale[c] + shift[c] [+ res] )
+// y = [relu]( x * scale[c] + shift[c] [+ res] ) ; 4 x 16 bytes per thread per tensor, loads issued before use
+constexpr int kEwVec = 4;
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                 const __nv_bfloat16* __restrict__ res, int relu, long long total8, int C,
                 __nv_bfloat16* __restrict__ y) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total8) return;
-  const int c0 = (int)((t * 8) % C);
-  float f[8], r[8];
-  unpack8(reinterpret_cast<const bf16x8*>(x)[t], f);
-  const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
-  const float4 h0 = *reinterpret_cast<const float4*>(shift + c0), h1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
-  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-  const float sf[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  const long long t0 = (long long)blockIdx.x * (256 * kEwVec) + threadIdx.x;
+  bf16x8 xv[kEwVec], rv[kEwVec];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sf[i]);
-  if (res) {
-    unpack8(reinterpret_cast<const bf16x8*>(res)[t], r);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] += r[i];
+  for (int u = 0; u < kEwVec; ++u) {
+    const long long t = t0 + u * 256;
+    if (t < total8) {
+      xv[u] = reinterpret_cast<const bf16x8*>(x)[t];
+      if (res) rv[u] = reinterpret_cast<const bf16x8*>(res)[t];
+    }
   }
-  if (relu) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
+  for (int u = 0; u < kEwVec; ++u) {
+    const long long t = t0 + u * 256;
+    if (t >= total8) continue;
+    const int c0 = (int)((t * 8) % C);
+    float f[8], r[8];
+    unpack8(xv[u], f);
+    const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(shift + c0), h1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sf[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sf[i]);
+    if (res) {
+      unpack8(rv[u], r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += r[i];
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
+    }
+    reinterpret_cast<bf16x8*>(y)[t] = pack8(f);
   }
-  reinterpret_cast<bf16x8*>(y)[t] = pack8(f);
 }
 
 // sums[0..C) += sum_p g ; sums[C..2C) += sum_p g * xhat    with g = dy * (y > 0 if relu)
@@ -172,20 +196,36 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       mu[i] = mean[g * 8 + i];
       rs[i] = rstd[g * 8 + i];
     }
-    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
-      float d[8], xv[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(dy + p * C + g * 8), d);
-      unpack8(*reinterpret_cast<const bf16x8*>(x + p * C + g * 8), xv);
-      if (y) {
-        float yv[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(y + p * C + g * 8), yv);
+    const long long stride = (long long)gridDim.x * rows;
+    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += 2 * stride) {
+      bf16x8 rd[2], rx[2], ry[2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] = yv[i] > 0.0f ? d[i] : 0.0f;
+      for (int u = 0; u < 2; ++u) {
+        if (p + u * stride < P) {
+          const long long o = (p + u * stride) * C + g * 8;
+          rd[u] = *reinterpret_cast<const bf16x8*>(dy + o);
+          rx[u] = *reinterpret_cast<const bf16x8*>(x + o);
+          if (y) ry[u] = *reinterpret_cast<const bf16x8*>(y + o);
+        }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s[i] += d[i];
-        q[i] = fmaf(d[i], (xv[i] - mu[i]) * rs[i], q[i]);
+      for (int u = 0; u < 2; ++u) {
+        if (p + u * stride < P) {
+          float d[8], xv[8];
+          unpack8(rd[u], d);
+          unpack8(rx[u], xv);
+          if (y) {
+            float yv[8];
+            unpack8(ry[u], yv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = yv[i] > 0.0f ? d[i] : 0.0f;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            s[i] += d[i];
+            q[i] = fmaf(d[i], (xv[i] - mu[i]) * rs[i], q[i]);
+          }
+        }
       }
     }
 #pragma unroll
@@ -224,27 +264,42 @@ __global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, long long P, i
 }
 
 // dx = a*g + b*x + c0 ; optionally g itself is written out (gradient of the residual branch)
+constexpr int kBwdVec = 2;
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                     const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef, long long total8, int C,
                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ g_out) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total8) return;
-  const int c0 = (int)((t * 8) % C);
-  float d[8], xv[8];
-  unpack8(reinterpret_cast<const bf16x8*>(dy)[t], d);
-  unpack8(reinterpret_cast<const bf16x8*>(x)[t], xv);
-  if (y) {
-    float yv[8];
-    unpack8(reinterpret_cast<const bf16x8*>(y)[t], yv);
+  const long long t0 = (long long)blockIdx.x * (256 * kBwdVec) + threadIdx.x;
+  bf16x8 rd[kBwdVec], rx[kBwdVec], ry[kBwdVec];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = yv[i] > 0.0f ? d[i] : 0.0f;
+  for (int u = 0; u < kBwdVec; ++u) {
+    const long long t = t0 + u * 256;
+    if (t < total8) {
+      rd[u] = reinterpret_cast<const bf16x8*>(dy)[t];
+      rx[u] = reinterpret_cast<const bf16x8*>(x)[t];
+      if (y) ry[u] = reinterpret_cast<const bf16x8*>(y)[t];
+    }
   }
-  if (g_out) reinterpret_cast<bf16x8*>(g_out)[t] = pack8(d);
-  float o[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = fmaf(coef[c0 + i], d[i], fmaf(coef[C + c0 + i], xv[i], coef[2 * C + c0 + i]));
-  reinterpret_cast<bf16x8*>(dx)[t] = pack8(o);
+  for (int u = 0; u < kBwdVec; ++u) {
+    const long long t = t0 + u * 256;
+    if (t >= total8) continue;
+    const int c0 = (int)((t * 8) % C);
+    float d[8], xv[8];
+    unpack8(rd[u], d);
+    unpack8(rx[u], xv);
+    if (y) {
+      float yv[8];
+      unpack8(ry[u], yv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = yv[i] > 0.0f ? d[i] : 0.0f;
+    }
+    if (g_out) reinterpret_cast<bf16x8*>(g_out)[t] = pack8(d);
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(coef[c0 + i], d[i], fmaf(coef[C + c0 + i], xv[i], coef[2 * C + c0 + i]));
+    reinterpret_cast<bf16x8*>(dx)[t] = pack8(o);
+  }
 }
 
 static int bn_check(const char* who, long long P, int C) {
@@ -279,7 +334,7 @@ int bn_train_fwd(const void* x, long long P, int C, const float* gamma, const fl
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, beta, eps, momentum, running_mean,
                                                        running_var, mean, rstd, scale, shift);
   const long long total8 = P * C / 8;
-  bn_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
+  bn_apply_kernel<<<(unsigned)((total8 + 256 * kEwVec - 1) / (256 * kEwVec)), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(res), relu,
       total8, C, reinterpret_cast<__nv_bfloat16*>(y));
   return check_launch("bn_train_fwd");
@@ -292,7 +347,7 @@ int bn_eval_fwd(const void* x, long long P, int C, const float* gamma, const flo
   if (rc) return rc;
   bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, eps, running_mean, running_var, scale, shift);
   const long long total8 = P * C / 8;
-  bn_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
+  bn_apply_kernel<<<(unsigned)((total8 + 256 * kEwVec - 1) / (256 * kEwVec)), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(res), relu,
       total8, C, reinterpret_cast<__nv_bfloat16*>(y));
   return check_launch("bn_eval_fwd");
@@ -310,7 +365,7 @@ int bn_train_bwd(const void* dy, const void* y_or_null, const void* x, long long
       reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, P, C, sums);
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, mean, rstd, dgamma, dbeta, coef);
   const long long total8 = P * C / 8;
-  bn_bwd_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
+  bn_bwd_apply_kernel<<<(unsigned)((total8 + 256 * kBwdVec - 1) / (256 * kBwdVec)), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_or_null),
       reinterpret_cast<const __nv_bfloat16*>(x), coef, total8, C, reinterpret_cast<__nv_bfloat16*>(dx),
       reinterpret_cast<__nv_bfloat16*>(g_out));

@@ -44,6 +44,38 @@ if 'gemm' in which:
         ms_t = timeit(lambda: torch.matmul(a, b.t()))
         res[f'gemm_{m}x{n}x{k}'] = {'ms': ms, 'tflops': 2 * m * n * k / ms / 1e9, 'torch_ms': ms_t,
                                     'torch_tflops': 2 * m * n * k / ms_t / 1e9}
+if 'epi' in which:
+    # epilogue-heavy shapes of the server step
+    m, n, k = 4096, 3072, 768
+    a = torch.randn(m, k, device=dev).to(torch.bfloat16); b = torch.randn(n, k, device=dev).to(torch.bfloat16)
+    bias = torch.randn(n, device=dev)
+    ms = timeit(lambda: ops.gemm_bf16(a, b, bias=bias, act=ops.ACT_GELU, want_preact=True))
+    res['ffn1_gelu_preact'] = {'ms': ms, 'tflops': 2 * m * n * k / ms / 1e9}
+    m, n, k = 401408, 256, 64
+    a = torch.randn(m, k, device=dev).to(torch.bfloat16); b = torch.randn(k, n, device=dev).to(torch.bfloat16)
+    add = torch.randn(m, n, device=dev).to(torch.bfloat16)
+    ms = timeit(lambda: ops.gemm_bf16(a, b, b_mn=True, add=add))
+    res['conv1x1_dgrad_add_401408x256x64'] = {'ms': ms, 'GBps': (m * k + 2 * m * n) * 2 / ms / 1e6}
+    m, n, k = 100352, 512, 128
+    a = torch.randn(m, k, device=dev).to(torch.bfloat16); b = torch.randn(n, k, device=dev).to(torch.bfloat16)
+    ms = timeit(lambda: ops.gemm_bf16(a, b))
+    res['conv1x1_fprop_100352x512x128'] = {'ms': ms, 'GBps': (m * k + m * n) * 2 / ms / 1e6}
+    m, n, k = 256, 64, 401408      # wgrad layer1 conv1
+    a = torch.randn(k, m, device=dev).to(torch.bfloat16); b = torch.randn(k, n, device=dev).to(torch.bfloat16)
+    ms = timeit(lambda: ops.gemm_bf16(a, b, a_mn=True, b_mn=True, split_k=0, accumulate=True, out=torch.zeros(m, n, device=dev)))
+    res['conv1x1_wgrad_256x64x401408'] = {'ms': ms, 'GBps': (m * k + n * k) * 2 / ms / 1e6}
+if 'bn' in which:
+    from creamfl_b200 import tower_ops as T
+    x = torch.randn(128, 56, 56, 256, device=dev).to(torch.bfloat16)
+    g = torch.ones(256, device=dev); bta = torch.zeros(256, device=dev); rm = torch.zeros(256, device=dev); rv = torch.ones(256, device=dev)
+    sc = T.BNScratch(256, dev)
+    ms = timeit(lambda: T.bn_train_fwd(x, g, bta, rm, rv, sc, 1e-5, 0.1))
+    nb = x.numel() * 2
+    res['bn_train_fwd_128x56x56x256'] = {'ms': ms, 'GBps_algorithmic(3 passes)': 3 * nb / ms / 1e6}
+    y, mean, rstd = T.bn_train_fwd(x, g, bta, rm, rv, sc, 1e-5, 0.1)
+    dg = torch.zeros(256, device=dev); db = torch.zeros(256, device=dev)
+    ms = timeit(lambda: T.bn_train_bwd(x, y, x, g, mean, rstd, sc, dg, db, want_g=True))
+    res['bn_train_bwd_128x56x56x256'] = {'ms': ms, 'GBps_algorithmic(8 passes)': 8 * nb / ms / 1e6}
 if 'conw' in which:
     for n in (16384, 50000):
         v = unit(torch.randn(n, 256, device=dev)).to(torch.bfloat16)

@@ -70,8 +70,11 @@ def test_gemm_epilogues(ops, act):
             'sigmoid': ops.ACT_SIGMOID}[act]
     out, pre_g = ops.gemm_bf16(a.cuda(), b.cuda(), bias=bias.cuda(), add=add.cuda(), act=code, alpha=0.5,
                                out_dtype=torch.float32, want_preact=True)
-    assert rel_l2(out, fn(pre)) < 2e-5
+    assert rel_l2(out, fn(pre)) < (1e-3 if act == 'tanh' else 2e-5)      # tanh.approx.f32: 2^-11 relative
     assert rel_l2(pre_g, pre) < 4e-3
+    # bf16 output: leaves through the staged TMA store
+    out16 = ops.gemm_bf16(a.cuda(), b.cuda(), bias=bias.cuda(), add=add.cuda(), act=code, alpha=0.5)
+    assert out16.dtype == torch.bfloat16 and rel_l2(out16, fn(pre)) < 4e-3
 
 
 @pytest.mark.parametrize('act', ['dgelu', 'drelu'])
