@@ -253,9 +253,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (row_ok && has_k && col0 < n_extent) {
           if (MODE == 2) {
             float* o = reinterpret_cast<float*>(p.out) + row_off + col0;
+            if (col0 + 32 <= n_extent && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < n_extent) atomicAdd(o + j, __uint_as_float(v[j]));
+              for (int j = 0; j < 32; j += 4)
+                atomicAdd(reinterpret_cast<float4*>(o + j),
+                          make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                      __uint_as_float(v[j + 3])));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < n_extent) atomicAdd(o + j, __uint_as_float(v[j]));
+            }
           } else {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + col0;
             if (p.add != nullptr) {

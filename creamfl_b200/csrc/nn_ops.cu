@@ -135,45 +135,56 @@ __global__ void bn_eval_affine_kernel(int C, const float* __restrict__ gamma, co
   shift[c] = beta[c] - running_mean[c] * sc;
 }
 
-// y = [relu]( x * scale[c] + shift[c] [+ res] ) ; 4 x 16 bytes per thread per tensor, loads issued before use
+// y = [relu]( x * scale[c] + shift[c] [+ res] ).
+// Elementwise BatchNorm kernels: C/8 divides the block size, so with a grid stride that is a multiple of the block
+// size every 16-byte vector a thread touches belongs to the same 8 channels - the per-channel coefficients are
+// loaded once into registers and kEwVec vectors are in flight per thread per tensor.
 constexpr int kEwVec = 4;
-__global__ void __launch_bounds__(256)
+constexpr int kEwThreads = 256;
+__device__ __forceinline__ void load_coef8(const float* __restrict__ a, int c0, float (&o)[8]) {
+  const float4 lo = *reinterpret_cast<const float4*>(a + c0), hi = *reinterpret_cast<const float4*>(a + c0 + 4);
+  o[0] = lo.x; o[1] = lo.y; o[2] = lo.z; o[3] = lo.w; o[4] = hi.x; o[5] = hi.y; o[6] = hi.z; o[7] = hi.w;
+}
+
+__global__ void __launch_bounds__(kEwThreads)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                 const __nv_bfloat16* __restrict__ res, int relu, long long total8, int C,
                 __nv_bfloat16* __restrict__ y) {
-  const long long t0 = (long long)blockIdx.x * (256 * kEwVec) + threadIdx.x;
-  bf16x8 xv[kEwVec], rv[kEwVec];
+  const long long stride = (long long)gridDim.x * kEwThreads;
+  const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
+  float sc[8], sf[8];
+  const int c0 = (int)((first * 8) % C);
+  load_coef8(scale, c0, sc);
+  load_coef8(shift, c0, sf);
+  for (long long t0 = first; t0 < total8; t0 += kEwVec * stride) {
+    bf16x8 xv[kEwVec], rv[kEwVec];
 #pragma unroll
-  for (int u = 0; u < kEwVec; ++u) {
-    const long long t = t0 + u * 256;
-    if (t < total8) {
-      xv[u] = reinterpret_cast<const bf16x8*>(x)[t];
-      if (res) rv[u] = reinterpret_cast<const bf16x8*>(res)[t];
+    for (int u = 0; u < kEwVec; ++u) {
+      const long long t = t0 + u * stride;
+      if (t < total8) {
+        xv[u] = reinterpret_cast<const bf16x8*>(x)[t];
+        if (res) rv[u] = reinterpret_cast<const bf16x8*>(res)[t];
+      }
     }
-  }
 #pragma unroll
-  for (int u = 0; u < kEwVec; ++u) {
-    const long long t = t0 + u * 256;
-    if (t >= total8) continue;
-    const int c0 = (int)((t * 8) % C);
-    float f[8], r[8];
-    unpack8(xv[u], f);
-    const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
-    const float4 h0 = *reinterpret_cast<const float4*>(shift + c0), h1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sf[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    for (int u = 0; u < kEwVec; ++u) {
+      const long long t = t0 + u * stride;
+      if (t >= total8) continue;
+      float f[8], r[8];
+      unpack8(xv[u], f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sf[i]);
-    if (res) {
-      unpack8(rv[u], r);
+      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sf[i]);
+      if (res) {
+        unpack8(rv[u], r);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] += r[i];
+        for (int i = 0; i < 8; ++i) f[i] += r[i];
+      }
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
+      }
+      reinterpret_cast<bf16x8*>(y)[t] = pack8(f);
     }
-    if (relu) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
-    }
-    reinterpret_cast<bf16x8*>(y)[t] = pack8(f);
   }
 }
 
@@ -264,47 +275,63 @@ __global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, long long P, i
 }
 
 // dx = a*g + b*x + c0 ; optionally g itself is written out (gradient of the residual branch)
-constexpr int kBwdVec = 2;
-__global__ void __launch_bounds__(256)
+constexpr int kBwdVec = 4;
+__global__ void __launch_bounds__(kEwThreads)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                     const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef, long long total8, int C,
                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ g_out) {
-  const long long t0 = (long long)blockIdx.x * (256 * kBwdVec) + threadIdx.x;
-  bf16x8 rd[kBwdVec], rx[kBwdVec], ry[kBwdVec];
+  const long long stride = (long long)gridDim.x * kEwThreads;
+  const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
+  float ca[8], cb[8], cc[8];
+  const int c0 = (int)((first * 8) % C);
+  load_coef8(coef, c0, ca);
+  load_coef8(coef + C, c0, cb);
+  load_coef8(coef + 2 * C, c0, cc);
+  for (long long t0 = first; t0 < total8; t0 += kBwdVec * stride) {
+    bf16x8 rd[kBwdVec], rx[kBwdVec], ry[kBwdVec];
 #pragma unroll
-  for (int u = 0; u < kBwdVec; ++u) {
-    const long long t = t0 + u * 256;
-    if (t < total8) {
-      rd[u] = reinterpret_cast<const bf16x8*>(dy)[t];
-      rx[u] = reinterpret_cast<const bf16x8*>(x)[t];
-      if (y) ry[u] = reinterpret_cast<const bf16x8*>(y)[t];
+    for (int u = 0; u < kBwdVec; ++u) {
+      const long long t = t0 + u * stride;
+      if (t < total8) {
+        rd[u] = reinterpret_cast<const bf16x8*>(dy)[t];
+        rx[u] = reinterpret_cast<const bf16x8*>(x)[t];
+        if (y) ry[u] = reinterpret_cast<const bf16x8*>(y)[t];
+      }
     }
-  }
 #pragma unroll
-  for (int u = 0; u < kBwdVec; ++u) {
-    const long long t = t0 + u * 256;
-    if (t >= total8) continue;
-    const int c0 = (int)((t * 8) % C);
-    float d[8], xv[8];
-    unpack8(rd[u], d);
-    unpack8(rx[u], xv);
-    if (y) {
-      float yv[8];
-      unpack8(ry[u], yv);
+    for (int u = 0; u < kBwdVec; ++u) {
+      const long long t = t0 + u * stride;
+      if (t >= total8) continue;
+      float d[8], xv[8];
+      unpack8(rd[u], d);
+      unpack8(rx[u], xv);
+      if (y) {
+        float yv[8];
+        unpack8(ry[u], yv);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = yv[i] > 0.0f ? d[i] : 0.0f;
+        for (int i = 0; i < 8; ++i) d[i] = yv[i] > 0.0f ? d[i] : 0.0f;
+      }
+      if (g_out) reinterpret_cast<bf16x8*>(g_out)[t] = pack8(d);
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(ca[i], d[i], fmaf(cb[i], xv[i], cc[i]));
+      reinterpret_cast<bf16x8*>(dx)[t] = pack8(o);
     }
-    if (g_out) reinterpret_cast<bf16x8*>(g_out)[t] = pack8(d);
-    float o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = fmaf(coef[c0 + i], d[i], fmaf(coef[C + c0 + i], xv[i], coef[2 * C + c0 + i]));
-    reinterpret_cast<bf16x8*>(dx)[t] = pack8(o);
   }
 }
 
+// grid for the elementwise BatchNorm kernels: enough blocks to fill the machine, every thread loops
+static unsigned ew_grid(long long total8, int vec) {
+  long long blocks = (total8 + (long long)kEwThreads * vec - 1) / ((long long)kEwThreads * vec);
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
 static int bn_check(const char* who, long long P, int C) {
-  if (P <= 0 || C <= 0 || (C & 7) || C > 2048) {
-    set_error("%s: bad shape P=%lld C=%d (C %% 8 == 0, C <= 2048 required)", who, P, C);
+  if (P <= 0 || C < 8 || C > 2048 || (2048 % C) != 0) {
+    set_error("%s: bad shape P=%lld C=%d (C must be a power of two in [8, 2048])", who, P, C);
     return CFL_EINVAL;
   }
   return CFL_OK;
@@ -334,7 +361,7 @@ int bn_train_fwd(const void* x, long long P, int C, const float* gamma, const fl
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, beta, eps, momentum, running_mean,
                                                        running_var, mean, rstd, scale, shift);
   const long long total8 = P * C / 8;
-  bn_apply_kernel<<<(unsigned)((total8 + 256 * kEwVec - 1) / (256 * kEwVec)), 256, 0, st>>>(
+  bn_apply_kernel<<<ew_grid(total8, kEwVec), kEwThreads, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(res), relu,
       total8, C, reinterpret_cast<__nv_bfloat16*>(y));
   return check_launch("bn_train_fwd");
@@ -347,7 +374,7 @@ int bn_eval_fwd(const void* x, long long P, int C, const float* gamma, const flo
   if (rc) return rc;
   bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, eps, running_mean, running_var, scale, shift);
   const long long total8 = P * C / 8;
-  bn_apply_kernel<<<(unsigned)((total8 + 256 * kEwVec - 1) / (256 * kEwVec)), 256, 0, st>>>(
+  bn_apply_kernel<<<ew_grid(total8, kEwVec), kEwThreads, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(res), relu,
       total8, C, reinterpret_cast<__nv_bfloat16*>(y));
   return check_launch("bn_eval_fwd");
@@ -365,7 +392,7 @@ int bn_train_bwd(const void* dy, const void* y_or_null, const void* x, long long
       reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, P, C, sums);
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, mean, rstd, dgamma, dbeta, coef);
   const long long total8 = P * C / 8;
-  bn_bwd_apply_kernel<<<(unsigned)((total8 + 256 * kBwdVec - 1) / (256 * kBwdVec)), 256, 0, st>>>(
+  bn_bwd_apply_kernel<<<ew_grid(total8, kBwdVec), kEwThreads, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_or_null),
       reinterpret_cast<const __nv_bfloat16*>(x), coef, total8, C, reinterpret_cast<__nv_bfloat16*>(dx),
       reinterpret_cast<__nv_bfloat16*>(g_out));
@@ -508,34 +535,35 @@ im2col_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int
 }
 
 // Stem: fp32 NCHW images straight to the bf16 patch matrix (fuses the layout change and the cast).
-// Column order (r, s, c) to match [Cout, R, S, Cin] filters; one thread per (pixel, tap).
+// Column order (r, s, c) to match [Cout, R, S, Cin] filters.  One thread per (pixel, group of 8 columns): 8 gathered
+// reads (L1/L2 hits - every input value is reused R*S/stride^2 times) and one 16-byte store.
 __global__ void __launch_bounds__(256)
 im2col_nchw_f32_kernel(const float* __restrict__ x, int N, int C, int H, int W, int R, int S, int stride, int pad,
                        int Ho, int Wo, int ldc, __nv_bfloat16* __restrict__ col) {
+  const int groups = ldc >> 3;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int taps = R * S;
-  const int slots = ldc / C;  // taps plus zero-padding slots (tail handled below)
-  const long long total = (long long)N * Ho * Wo * slots;
+  const long long total = (long long)N * Ho * Wo * groups;
   if (t >= total) return;
-  const int tap = (int)(t % slots);
-  long long q = t / slots;
+  const int g = (int)(t % groups);
+  long long q = t / groups;
   const long long pix = q;
   const int wo = (int)(q % Wo); q /= Wo;
   const int ho = (int)(q % Ho);
   const int n = (int)(q / Ho);
-  __nv_bfloat16* dst = col + pix * ldc + (long long)tap * C;
-  if (tap >= taps) {
-    for (int c = 0; c < C; ++c) dst[c] = __float2bfloat16(0.f);
-    if (tap == slots - 1)
-      for (int c = slots * C; c < ldc; ++c) col[pix * ldc + c] = __float2bfloat16(0.f);
-    return;
+  const int kcols = R * S * C;
+  float f[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int e = g * 8 + i;
+    float v = 0.0f;
+    if (e < kcols) {
+      const int tap = e / C, c = e - tap * C;
+      const int h = ho * stride + tap / S - pad, w = wo * stride + tap % S - pad;
+      if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(x + (((long long)n * C + c) * H + h) * W + w);
+    }
+    f[i] = v;
   }
-  const int h = ho * stride + tap / S - pad, w = wo * stride + tap % S - pad;
-  const bool ok = h >= 0 && h < H && w >= 0 && w < W;
-  for (int c = 0; c < C; ++c)
-    dst[c] = __float2bfloat16(ok ? x[(((long long)n * C + c) * H + h) * W + w] : 0.f);
-  if (tap == slots - 1)
-    for (int c = slots * C; c < ldc; ++c) col[pix * ldc + c] = __float2bfloat16(0.f);
+  *reinterpret_cast<bf16x8*>(col + pix * ldc + g * 8) = pack8(f);
 }
 
 // dX (NHWC bf16) from dcol: gather over the taps that touch each input pixel.
@@ -603,8 +631,7 @@ int im2col_nchw_f32(const float* x, int N, int C, int H, int W, int R, int S, in
     return CFL_EINVAL;
   }
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
-  const int slots = ldc / C;
-  const long long total = (long long)N * Ho * Wo * slots;
+  const long long total = (long long)N * Ho * Wo * (ldc >> 3);
   im2col_nchw_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
       x, N, C, H, W, R, S, stride, pad, Ho, Wo, ldc, reinterpret_cast<__nv_bfloat16*>(col));
   return check_launch("im2col_nchw_f32");

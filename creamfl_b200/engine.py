@@ -94,6 +94,7 @@ class MMClient:
                  vocab_size: int = 11755, device: Optional[torch.device] = None):
         self.device = device or torch.device('cuda', torch.cuda.current_device())
         self.model = ClientPCME(vocab_size, embed_dim).to(self.device)
+        self.model.txt_enc.rnn.flatten_parameters()      # one contiguous cuDNN weight buffer; updated in place below
         self.criterion = get_criterion('pcme', PCME_CRITERION_CFG).to(self.device)
         self.model.store()
         params = [p for p in self.model.parameters() if p.requires_grad] + list(self.criterion.parameters())
@@ -104,6 +105,7 @@ class MMClient:
 
     def begin_round(self) -> None:
         self.old_model = copy.deepcopy(self.model).eval()            # MMClientTrainer.py:92-93
+        self.old_model.txt_enc.rnn.flatten_parameters()
         self.old_model.store()
         self.model.train()
 
