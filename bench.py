@@ -53,6 +53,7 @@ def parse():
     ap.add_argument('--sub-batches', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--phases', default='ABCDEF', help='debug: subset of phases to run')
+    ap.add_argument('--no-graphs', action='store_true', help='launch every kernel eagerly instead of CUDA graphs')
     return ap.parse_args()
 
 
@@ -180,8 +181,8 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     S, B = args.sub_batches, args.batch
     torch.manual_seed(1234 + rank)
-    server = engine.ServerEngine(D, 'resnet101', device=dev, data_parallel=world > 1)
-    client = engine.MMClient(D, device=dev)
+    server = engine.ServerEngine(D, 'resnet101', device=dev, data_parallel=world > 1, use_graphs=not args.no_graphs)
+    client = engine.MMClient(D, device=dev, use_graphs=not args.no_graphs)
     if world > 1:   # identical server replicas
         dist.broadcast(server.model.store().flat, 0)
         server.model.sync_shadow()
@@ -295,7 +296,7 @@ def run_ours(args):
         'config': {'workload': 'configs[1]: ResNet101+BERT server, 1 multimodal client (ResNet18+GRU) per GPU, '
                                'COCO-shape synthetic batch 128, inter+intra contrast vs N_pub=50000, con_w aggregation',
                    'global_batch': B * world, 'sub_batches_per_step': S, 'n_pub': N_PUB, 'embed_dim': D,
-                   'bert_seq_len': BERT_L, 'phases': phases, 'l2': 'inputs_exceed_l2 (308 MB images + 0.6 GB '
+                   'bert_seq_len': BERT_L, 'phases': phases, 'cuda_graphs': not args.no_graphs, 'l2': 'inputs_exceed_l2 (308 MB images + 0.6 GB '
                    'parameters per step >> 126 MB L2)', 'parallelism': f'client-per-gpu x{world}, server replicated '
                    'with flat-gradient all-reduce' if world > 1 else 'single gpu'},
         'e2e': {'value': round(e2e, 1), 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d_bytes(host),

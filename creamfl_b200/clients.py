@@ -57,16 +57,37 @@ class GRUEncoderText(nn.Module):
         self.rnn = nn.GRU(word_dim, embed_dim // 2, bidirectional=True, batch_first=True)
         self.pie_net = _TorchPIENet(word_dim, embed_dim, word_dim // 2)
         nn.init.xavier_uniform_(self.embed.weight)
+        self._len_cache = {}
+
+    def _length_tensors(self, lengths_cpu, seq_len, device):
+        """Device-side gather index and pad mask for one length profile (cached: built once per profile, so a
+        CUDA-graph capture of the step contains no host-to-device copy)."""
+        key = (tuple(lengths_cpu.tolist()), seq_len, str(device))
+        hit = self._len_cache.get(key)
+        if hit is None:
+            idx = (lengths_cpu - 1).to(device).view(-1, 1, 1).expand(-1, 1, self.embed_dim).contiguous()
+            hit = (idx, get_pad_mask(seq_len, lengths_cpu, True).to(device))
+            if len(self._len_cache) > 64:
+                self._len_cache.clear()
+            self._len_cache[key] = hit
+        return hit
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == '_len_cache' else copy.deepcopy(v, memo)
+        return new
 
     def forward(self, x, lengths):
         lengths_cpu = lengths.cpu() if torch.is_tensor(lengths) else torch.as_tensor(lengths)
         wemb_out = self.embed(x)
         packed = pack_padded_sequence(wemb_out, lengths_cpu, batch_first=True)
         rnn_out, _ = self.rnn(packed)
-        padded, _ = pad_packed_sequence(rnn_out, batch_first=True)
-        idx = (lengths_cpu - 1).to(x.device).view(-1, 1, 1).expand(-1, 1, self.embed_dim)
+        padded, _ = pad_packed_sequence(rnn_out, batch_first=True, total_length=wemb_out.shape[1])
+        idx, pad_mask = self._length_tensors(lengths_cpu, wemb_out.shape[1], x.device)
         out = torch.gather(padded, 1, idx).squeeze(1)                             # caption_encoder.py:99-101
-        pad_mask = get_pad_mask(wemb_out.shape[1], lengths_cpu, True).to(x.device)
         out, attn, residual = self.pie_net(out, wemb_out, pad_mask)
         return {'embedding': torch.nn.functional.normalize(out, p=2, dim=-1)}     # :109
 
@@ -92,6 +113,20 @@ class ClientPCME(StoreMixin, nn.Module):
     def image_forward(self, images):
         self.store()
         return self.img_enc(images)
+
+    @torch.no_grad()
+    def copy_weights_from(self, other: 'ClientPCME') -> None:
+        """In-place copy of every parameter and buffer (keeps addresses stable: the per-round `old_model` of
+        MMClientTrainer.py:92 is refreshed instead of re-allocated, so captured CUDA graphs stay valid)."""
+        a, b = self.store(), other.store()
+        a.flat.copy_(b.flat)
+        a.shadow.copy_(b.shadow)
+        for (dst, _), (src, _) in zip(a.padded, b.padded):
+            dst.copy_(src)
+        for p, q in zip(self.txt_enc.parameters(), other.txt_enc.parameters()):
+            p.copy_(q)
+        for p, q in zip(self.buffers(), other.buffers()):
+            p.copy_(q)
 
     def forward(self, images, sentences, captions_word, lengths):
         self.store()

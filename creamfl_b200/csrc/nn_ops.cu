@@ -542,10 +542,11 @@ im2col_nchw_f32_kernel(const float* __restrict__ x, int N, int C, int H, int W, 
                        int Ho, int Wo, int ldc, __nv_bfloat16* __restrict__ col) {
   const int groups = ldc >> 3;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)N * Ho * Wo * groups;
-  if (t >= total) return;
-  const int g = (int)(t % groups);
-  long long q = t / groups;
+  const long long pixels = (long long)N * Ho * Wo;
+  if (t >= pixels * groups) return;
+  // pixel index fastest: a warp reads 32 neighbouring output columns of the same filter taps (stride-2 coalesced)
+  const int g = (int)(t / pixels);
+  long long q = t % pixels;
   const long long pix = q;
   const int wo = (int)(q % Wo); q /= Wo;
   const int ho = (int)(q % Ho);

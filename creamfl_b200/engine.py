@@ -34,10 +34,42 @@ def _features(output: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, torch.Tens
     return output['image_features'], output['caption_features']
 
 
+class GraphedStep:
+    """One step function captured as a CUDA graph (the client steps issue ~1500 short kernels and are otherwise
+    bound by launch overhead).  Inputs are copied into static buffers, the graph is replayed, outputs are static."""
+
+    def __init__(self, fn, example: Dict[str, torch.Tensor], warmup: int = 3):
+        self.static = {k: v.clone() for k, v in example.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn(**self.static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = ops.launches()
+        with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
+            self.out = fn(**self.static)
+        self.launches = ops.launches() - l0          # kernels of ours inside one replay
+
+    def __call__(self, **inputs):
+        for k, v in inputs.items():
+            self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        ops._launches += self.launches
+        out = self.out
+        if torch.is_tensor(out) and out.numel() <= 16:
+            return out.clone()                       # scalars (losses) must survive the next replay
+        return out
+
+
 class ServerEngine:
     def __init__(self, embed_dim: int = 256, cnn_type: str = 'resnet101', lr: float = 2e-4, grad_clip: float = 2.0,
-                 kd_weight: float = 0.3, device: Optional[torch.device] = None, data_parallel: bool = False):
+                 kd_weight: float = 0.3, device: Optional[torch.device] = None, data_parallel: bool = False,
+                 use_graphs: bool = False):
         self.device = device or torch.device('cuda', torch.cuda.current_device())
+        self._graphs = {}
         self.model = PCME(None, {'embed_dim': embed_dim, 'cnn_type': cnn_type, 'not_bert': False}).to(self.device)
         self.criterion = get_criterion('pcme', PCME_CRITERION_CFG).to(self.device)
         self.model.store()
@@ -46,6 +78,15 @@ class ServerEngine:
                                         no_clip=list(self.criterion.parameters())).attach_stores(self.model)
         self.kd_weight = kd_weight
         self.data_parallel = data_parallel and dist.is_initialized() and dist.get_world_size() > 1
+        self.use_graphs = use_graphs and not self.data_parallel
+
+    def _graphed(self, name, fn, **tensors):
+        key = (name, tuple((k, tuple(t.shape)) for k, t in tensors.items()))
+        g = self._graphs.get(key)
+        if g is None:
+            self.optimizer.prepare()
+            g = self._graphs[key] = GraphedStep(fn, tensors)
+        return g(**tensors)
 
     def _sync_grads(self) -> None:
         """Replicated server, batches sharded over ranks: average the flat gradient buffer (one NCCL call)."""
@@ -58,6 +99,13 @@ class ServerEngine:
                 p.grad.mul_(1.0 / dist.get_world_size())
 
     def train_step(self, images, tokens) -> torch.Tensor:
+        if self.use_graphs and isinstance(tokens, dict):
+            return self._graphed('train', lambda images, ids, mask: self._train_step(
+                images, {'input_ids': ids, 'attention_mask': mask}), images=images, ids=tokens['input_ids'],
+                mask=tokens['attention_mask'])
+        return self._train_step(images, tokens)
+
+    def _train_step(self, images, tokens) -> torch.Tensor:
         self.model.train()
         output = self.model(images, None, tokens, None)
         loss, _ = self.criterion(**output)
@@ -67,14 +115,32 @@ class ServerEngine:
         self.optimizer.step()
         return loss.detach()
 
-    @torch.no_grad()
     def extract(self, images, tokens) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.use_graphs and isinstance(tokens, dict):
+            return self._graphed('extract', lambda images, ids, mask: self._extract(
+                images, {'input_ids': ids, 'attention_mask': mask}), images=images, ids=tokens['input_ids'],
+                mask=tokens['attention_mask'])
+        return self._extract(images, tokens)
+
+    @torch.no_grad()
+    def _extract(self, images, tokens) -> Tuple[torch.Tensor, torch.Tensor]:
         self.model.eval()
         return _features(self.model(images, None, tokens, None))
 
     def distill_step(self, images, tokens, d_idx, agg_img, agg_txt, img_terms: int = 1, txt_terms: int = 1):
         """`img_terms` / `txt_terms`: how many times the reference adds the image / text MSE - once per client type
         that carries the modality (MMFL.py:361-378; 2 each when image, text and multimodal clients all exist)."""
+        if self.use_graphs and isinstance(tokens, dict) and agg_img is not None and agg_txt is not None:
+            # aggregated targets are passed as graph inputs (they are re-created every round)
+            return self._graphed(('distill', img_terms, txt_terms),
+                                 lambda images, ids, mask, d_idx, agg_img, agg_txt: self._distill_step(
+                                     images, {'input_ids': ids, 'attention_mask': mask}, d_idx, agg_img, agg_txt,
+                                     img_terms, txt_terms),
+                                 images=images, ids=tokens['input_ids'], mask=tokens['attention_mask'], d_idx=d_idx,
+                                 agg_img=agg_img, agg_txt=agg_txt)
+        return self._distill_step(images, tokens, d_idx, agg_img, agg_txt, img_terms, txt_terms)
+
+    def _distill_step(self, images, tokens, d_idx, agg_img, agg_txt, img_terms: int = 1, txt_terms: int = 1):
         self.model.train()
         out_img, out_txt = _features(self.model(images, None, tokens, None))
         loss = 0
@@ -91,8 +157,10 @@ class ServerEngine:
 
 class MMClient:
     def __init__(self, embed_dim: int = 256, lr: float = 2e-4, grad_clip: float = 2.0, interintra_weight: float = 0.5,
-                 vocab_size: int = 11755, device: Optional[torch.device] = None):
+                 vocab_size: int = 11755, device: Optional[torch.device] = None, use_graphs: bool = False):
         self.device = device or torch.device('cuda', torch.cuda.current_device())
+        self.use_graphs = use_graphs
+        self._graphs = {}
         self.model = ClientPCME(vocab_size, embed_dim).to(self.device)
         self.model.txt_enc.rnn.flatten_parameters()      # one contiguous cuDNN weight buffer; updated in place below
         self.criterion = get_criterion('pcme', PCME_CRITERION_CFG).to(self.device)
@@ -104,12 +172,31 @@ class MMClient:
         self.old_model = None
 
     def begin_round(self) -> None:
-        self.old_model = copy.deepcopy(self.model).eval()            # MMClientTrainer.py:92-93
-        self.old_model.txt_enc.rnn.flatten_parameters()
-        self.old_model.store()
+        """old_model = deepcopy(model) (MMClientTrainer.py:92-93); after the first round the copy is refreshed in
+        place so that its addresses - and any captured graph - stay valid."""
+        if self.old_model is None:
+            self.old_model = copy.deepcopy(self.model).eval()
+            self.old_model.txt_enc.rnn.flatten_parameters()
+            self.old_model.store()
+        else:
+            self.old_model.copy_weights_from(self.model)
         self.model.train()
 
+    def _graphed(self, name, lengths, fn, **tensors):
+        key = (name, tuple(int(v) for v in lengths), tuple((k, tuple(t.shape)) for k, t in tensors.items()))
+        g = self._graphs.get(key)
+        if g is None:
+            self.optimizer.prepare()
+            g = self._graphs[key] = GraphedStep(fn, tensors)
+        return g(**tensors)
+
     def private_step(self, images, captions, lengths) -> torch.Tensor:
+        if self.use_graphs:
+            return self._graphed('private', lengths, lambda images, captions: self._private_step(images, captions, lengths),
+                                 images=images, captions=captions)
+        return self._private_step(images, captions, lengths)
+
+    def _private_step(self, images, captions, lengths) -> torch.Tensor:
         self.model.train()
         output = self.model(images, captions, None, lengths)
         loss, _ = self.criterion(**output)
@@ -121,6 +208,20 @@ class MMClient:
     def contrast_step(self, images, captions, lengths, d_idx, g_img, g_txt, g_img16, g_txt16, intra: bool = True,
                       inter: bool = True, loss_scale: bool = False) -> torch.Tensor:
         """g_img / g_txt: fp32 [N_pub, D] server features; g_*16 their bf16 copies (made once per round)."""
+        if self.use_graphs:
+            # the banks are persistent buffers refreshed in place by the caller: captured by address
+            key_banks = (g_img.data_ptr(), g_txt.data_ptr(), g_img16.data_ptr(), g_txt16.data_ptr(), intra, inter,
+                         loss_scale)
+            return self._graphed(('contrast',) + key_banks, lengths,
+                                 lambda images, captions, d_idx: self._contrast_step(
+                                     images, captions, lengths, d_idx, g_img, g_txt, g_img16, g_txt16, intra, inter,
+                                     loss_scale),
+                                 images=images, captions=captions, d_idx=d_idx)
+        return self._contrast_step(images, captions, lengths, d_idx, g_img, g_txt, g_img16, g_txt16, intra, inter,
+                                   loss_scale)
+
+    def _contrast_step(self, images, captions, lengths, d_idx, g_img, g_txt, g_img16, g_txt16, intra: bool = True,
+                       inter: bool = True, loss_scale: bool = False) -> torch.Tensor:
         self.model.train()
         self.optimizer.zero_grad()
         out_img, out_txt = _features(self.model(images, captions, None, lengths))
@@ -144,8 +245,14 @@ class MMClient:
         self.optimizer.step()
         return loss.detach()
 
-    @torch.no_grad()
     def generate(self, images, captions, lengths) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.use_graphs:
+            return self._graphed('generate', lengths, lambda images, captions: self._generate(images, captions, lengths),
+                                 images=images, captions=captions)
+        return self._generate(images, captions, lengths)
+
+    @torch.no_grad()
+    def _generate(self, images, captions, lengths) -> Tuple[torch.Tensor, torch.Tensor]:
         self.model.eval()
         return _features(self.model(images, captions, None, lengths))
 
