@@ -91,12 +91,9 @@ class ServerEngine:
     def _sync_grads(self) -> None:
         """Replicated server, batches sharded over ranks: average the flat gradient buffer (one NCCL call)."""
         if self.data_parallel:
-            g = self.model.store().grad
-            dist.all_reduce(g, op=dist.ReduceOp.SUM)
-            g.mul_(1.0 / dist.get_world_size())
+            average_gradients(self.model.store().grad)
             for p in self.criterion.parameters():
-                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
-                p.grad.mul_(1.0 / dist.get_world_size())
+                average_gradients(p.grad)
 
     def train_step(self, images, tokens) -> torch.Tensor:
         if self.use_graphs and isinstance(tokens, dict):
@@ -262,17 +259,32 @@ def aggregate(vecs: Sequence[torch.Tensor], global_other: torch.Tensor) -> torch
     return ops.conw_aggregate(list(vecs), global_other)
 
 
+def gather_client_rows(score: torch.Tensor, vec: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The exchange step: every rank contributes its client's contrastive scores [N_pub] and representations
+    [N_pub, D]; every rank receives them stacked in rank order, [C, N_pub] and [C, N_pub, D] (C = world size).
+    Pure torch.distributed (NCCL on GPUs, gloo in the CPU tests); with one process it just adds the client axis."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return score.unsqueeze(0), vec.unsqueeze(0)
+    world = dist.get_world_size()
+    scores = torch.empty((world,) + tuple(score.shape), dtype=score.dtype, device=score.device)
+    vecs = torch.empty((world,) + tuple(vec.shape), dtype=vec.dtype, device=vec.device)
+    dist.all_gather_into_tensor(scores.view(-1), score.contiguous().view(-1))
+    dist.all_gather_into_tensor(vecs.view(-1), vec.contiguous().view(-1))
+    return scores, vecs
+
+
+def average_gradients(flat_grad: torch.Tensor) -> None:
+    """Replicated server with the public batches sharded over ranks: mean of the flat gradient buffer."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+        flat_grad.mul_(1.0 / dist.get_world_size())
+
+
 def exchange_and_aggregate(own_vec: torch.Tensor, global_other16: torch.Tensor) -> torch.Tensor:
     """Clients sharded one per rank: every rank scores its own client's [N_pub, D] representations against the
     replicated server features (tcgen05, 1.28 TFLOP each), then the ranks all-gather scores (200 KB) and
     representations (51 MB) and every rank forms the softmax-over-clients weighted sum - the single exchange step of
     the path.  With one rank this is `aggregate([own_vec], ...)`."""
     score = ops.conw_score(ops.to_bf16(own_vec), global_other16)
-    if not (dist.is_initialized() and dist.get_world_size() > 1):
-        return ops.conw_reduce([own_vec], score.unsqueeze(0))
-    world = dist.get_world_size()
-    scores = torch.empty((world,) + score.shape, dtype=score.dtype, device=score.device)
-    vecs = torch.empty((world,) + own_vec.shape, dtype=own_vec.dtype, device=own_vec.device)
-    dist.all_gather_into_tensor(scores, score.contiguous())
-    dist.all_gather_into_tensor(vecs, own_vec.contiguous())
-    return ops.conw_reduce([vecs[r] for r in range(world)], scores)
+    scores, vecs = gather_client_rows(score, own_vec)
+    return ops.conw_reduce([vecs[r] for r in range(vecs.shape[0])], scores)
