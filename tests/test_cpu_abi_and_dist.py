@@ -115,5 +115,5 @@ def test_exchange_gloo_world2_matches_single_process_oracle():
     want, _ = O.conw_aggregate([torch.from_numpy(v).double() for v in i_vecs], torch.from_numpy(g_txt).double())
     for rank, agg, s_shape, v_shape, grad in results:
         assert s_shape == (world, n) and v_shape == (world, n, d)
-        np.testing.assert_allclose(agg, want.numpy(), rtol=1e-5, atol=1e-8)     # every rank holds the full ensemble (fp32 scores on the wire)
+        np.testing.assert_allclose(agg, want.numpy(), rtol=1e-5, atol=1e-7)     # every rank holds the full ensemble (fp32 scores on the wire)
         np.testing.assert_allclose(grad, np.full(5, 1.5))                       # mean of the rank gradients
