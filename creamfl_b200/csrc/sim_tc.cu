@@ -7,58 +7,59 @@
 //   * con_w scoring                s[n] = X[n,n] - log sum_j exp X[n,j]   with Q = client reps, M = N_pub
 //                                  (MMFL.py:302-307 / 319-324; the reference builds the 50000x50000 matrix on the CPU)
 //
-// Work decomposition: a unit = (block of MT*128 query rows) x (chunk of consecutive 64-row tiles of G).
-// The query block stays resident in shared memory for the whole unit (MT*128 x D bf16), G tiles are streamed
-// through a TMA ring; every G tile is reused by MT MMAs (MT = 2 halves the L2->SM traffic of the compute-bound
-// con_w case).  S tiles (128 x 64 fp32) are double-buffered in TMEM; 4*MT epilogue warps own one accumulator row
-// per thread, so the running (max, sum) needs no cross-thread traffic at all.  Partial (max, sum) pairs per
-// (chunk, row) are merged by lse_combine_kernel, which also evaluates the positive logit <Q_i, G_label_i>.
+// Work decomposition: a unit = (block of 128 query rows) x (chunk of consecutive 256-row tiles of G).  The query
+// block stays resident in shared memory for the whole unit (128 x D bf16); G is streamed through a TMA ring in
+// (256 rows x 64 columns) stages.  Every S tile is ONE accumulator of 128 x 256 fp32 built by D/16 tcgen05.mma of
+// shape 128x256x16 - with N = 256 the shared-memory operand traffic is 96 B/clk per SM, below the 128 B/clk port
+// (N = 64 needs 192 B/clk and leaves the tensor pipe half idle).  Two S tiles fit in TMEM (512 columns), so the
+// epilogue of tile i overlaps the MMAs of tile i+1.  Eight epilogue warps: thread = accumulator row x column half,
+// running (max, sum) per thread, no cross-thread traffic.  Partial (max, sum) pairs per (chunk, half, row) are
+// merged by lse_combine_kernel, which also evaluates the positive logit <Q_i, G_label_i>.
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace cfl {
 
-constexpr int kSimBN = 64;   // G rows per tile
+constexpr int kSimBN = 256;  // G rows per tile (= UMMA N)
 constexpr int kSimKC = 64;   // bf16 elements per 128-byte swizzled row
+constexpr int kSimThreads = 384;
+constexpr int kSimStages = 4;
 
 struct SimParams {
   int M, N, D;            // Q [M, D], G [N, D]
   int m_blocks, n_chunks; // units = m_blocks * n_chunks
-  int tiles_per_chunk;    // G tiles (of 64 rows) per chunk
+  int tiles_per_chunk;    // G tiles (of 256 rows) per chunk
   float scale_log2;       // inv_tau * log2(e)
-  float2* partial;        // MODE 0: [n_chunks, M] (running max, running sum) in the log2 domain
+  float2* partial;        // MODE 0: [n_chunks * 2, M] (running max, running sum) in the log2 domain
   const float* lse2;      // MODE 1: [M] log2-domain LSE
   const long long* labels;// MODE 1: [M] positive column (or null)
   __nv_bfloat16* P;       // MODE 1: [M, ldp] softmax(X) - onehot(label)
   long long ldp;
 };
 
-template <int MT>
 struct SimCfg {
-  static constexpr int kStages = (MT == 2) ? 3 : 4;
-  static constexpr int kABytes = MT * 128 * 256 * 2;       // resident query block (D <= 256)
-  static constexpr int kBStageBytes = kSimBN * 256 * 2;    // one G tile
-  static constexpr int kSmemBytes = kABytes + kStages * kBStageBytes + 1024 + 256;
-  static constexpr int kThreads = 128 + 128 * MT;
-  static constexpr uint32_t kTmemCols = (MT == 2) ? 256 : 128;
+  static constexpr int kABytes = 128 * 256 * 2;            // resident query block (D <= 256)
+  static constexpr int kBStageBytes = kSimBN * kSimKC * 2; // one (256 x 64) slice of a G tile
+  static constexpr int kSmemBytes = kABytes + kSimStages * kBStageBytes + 1024 + 256;
+  static constexpr uint32_t kTmemCols = 512;
 };
 
-template <int MT, int MODE>
-__global__ void __launch_bounds__(SimCfg<MT>::kThreads, 1)
+template <int MODE>
+__global__ void __launch_bounds__(kSimThreads, 1)
 sim_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG, SimParams p) {
-  using Cfg = SimCfg<MT>;
+  using Cfg = SimCfg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + Cfg::kStages * Cfg::kBStageBytes);
-  uint64_t* full = bars;                       // [kStages]  TMA -> MMA
-  uint64_t* empty = full + Cfg::kStages;       // [kStages]  MMA -> TMA
-  uint64_t* a_full = empty + Cfg::kStages;     // [1]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kSimStages * Cfg::kBStageBytes);
+  uint64_t* full = bars;                       // [kSimStages]  TMA -> MMA
+  uint64_t* empty = full + kSimStages;         // [kSimStages]  MMA -> TMA
+  uint64_t* a_full = empty + kSimStages;       // [1]
   uint64_t* a_empty = a_full + 1;              // [1]
-  uint64_t* tfull = a_empty + 1;               // [MT*2]     MMA -> epilogue
-  uint64_t* tempty = tfull + MT * 2;           // [MT*2]     epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + MT * 2);
+  uint64_t* tfull = a_empty + 1;               // [2]           MMA -> epilogue
+  uint64_t* tempty = tfull + 2;                // [2]           epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -71,15 +72,15 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     tma_prefetch_desc(&tmG);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < Cfg::kStages; ++i) {
+    for (int i = 0; i < kSimStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int i = 0; i < MT * 2; ++i) {
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     fence_mbar_init();
   }
@@ -101,18 +102,17 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int t0 = ch * p.tiles_per_chunk;
         const int t1 = min(n_tiles_total, t0 + p.tiles_per_chunk);
         mbar_wait(a_empty, (ui & 1) ^ 1);
-        mbar_arrive_expect_tx(a_full, MT * 128 * p.D * 2);
-        for (int t = 0; t < MT; ++t)
-          for (int c = 0; c < dc; ++c)
-            tma_load_2d(&tmQ, a_full, sA + (t * 4 + c) * 16384, c * kSimKC, (mb * MT + t) * 128);
+        mbar_arrive_expect_tx(a_full, 128 * p.D * 2);
+        for (int c = 0; c < dc; ++c) tma_load_2d(&tmQ, a_full, sA + c * 16384, c * kSimKC, mb * 128);
         for (int nt = t0; nt < t1; ++nt) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], kSimBN * p.D * 2);
-          uint8_t* sb = sB + stage * Cfg::kBStageBytes;
-          for (int c = 0; c < dc; ++c) tma_load_2d(&tmG, &full[stage], sb + c * 8192, c * kSimKC, nt * kSimBN);
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
+          for (int c = 0; c < dc; ++c) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], Cfg::kBStageBytes);
+            tma_load_2d(&tmG, &full[stage], sB + stage * Cfg::kBStageBytes, c * kSimKC, nt * kSimBN);
+            if (++stage == kSimStages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
@@ -131,48 +131,45 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int t1 = min(n_tiles_total, t0 + p.tiles_per_chunk);
         mbar_wait(a_full, ui & 1);
         tc_fence_after();
+        const uint32_t sa = smem_u32(sA);
         for (int nt = t0; nt < t1; ++nt, ++it) {
           const uint32_t buf = it & 1;
           const uint32_t bphase = (it >> 1) & 1;
-          mbar_wait(&full[stage], phase);
+          mbar_wait(&tempty[buf], bphase ^ 1);
           tc_fence_after();
-          const uint32_t sb = smem_u32(sB + stage * Cfg::kBStageBytes);
-#pragma unroll
-          for (int t = 0; t < MT; ++t) {
-            mbar_wait(&tempty[t * 2 + buf], bphase ^ 1);
+          const uint32_t tmem_d = tmem_base + buf * kSimBN;
+          for (int c = 0; c < dc; ++c) {
+            mbar_wait(&full[stage], phase);
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (t * 2 + buf) * kSimBN;
-            const uint32_t sa = smem_u32(sA + t * 4 * 16384);
-            for (int c = 0; c < dc; ++c) {
+            const uint32_t sb = smem_u32(sB + stage * Cfg::kBStageBytes);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t da = make_smem_desc(sa + c * 16384 + k * 32, 16, 1024);
-                const uint64_t db = make_smem_desc(sb + c * 8192 + k * 32, 16, 1024);
-                umma_f16_ss(tmem_d, da, db, idesc, (c > 0 || k > 0) ? 1u : 0u);
-              }
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = make_smem_desc(sa + c * 16384 + k * 32, 16, 1024);
+              const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024);
+              umma_f16_ss(tmem_d, da, db, idesc, (c > 0 || k > 0) ? 1u : 0u);
             }
-            umma_commit(&tfull[t * 2 + buf]);
+            umma_commit(&empty[stage]);
+            if (++stage == kSimStages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
-          umma_commit(&empty[stage]);
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          umma_commit(&tfull[buf]);
         }
         umma_commit(a_empty);
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue: thread == accumulator row
-    const int t = (warp - 4) >> 2;
+    // ------------------------------------------------------------ epilogue: thread = (accumulator row, column half)
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
     uint32_t it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int mb = u % p.m_blocks;
       const int ch = u / p.m_blocks;
       const int t0 = ch * p.tiles_per_chunk;
       const int t1 = min(n_tiles_total, t0 + p.tiles_per_chunk);
-      const int row = (mb * MT + t) * 128 + q * 32 + lane;
+      const int row = mb * 128 + q * 32 + lane;
       float run_m = -INFINITY, run_l = 0.0f;
       float my_lse2 = 0.0f;
       long long my_label = -1;
@@ -183,85 +180,86 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       for (int nt = t0; nt < t1; ++nt, ++it) {
         const uint32_t buf = it & 1;
         const uint32_t bphase = (it >> 1) & 1;
-        mbar_wait(&tfull[t * 2 + buf], bphase);
+        mbar_wait(&tfull[buf], bphase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (t * 2 + buf) * kSimBN;
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(taddr, v0);
-        tmem_ld_32x32(taddr + 32, v1);
-        tmem_ld_wait();
-        // the accumulator is in registers: hand the TMEM buffer back before doing the math
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[t * 2 + buf]);
-
-        const int n0 = nt * kSimBN;
-        const int valid = min(kSimBN, p.N - n0);
-        if (MODE == 0) {
-          float x[64];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kSimBN + half * 128;
+        const int nbase = nt * kSimBN + half * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int n0 = nbase + c * 32;
+          const int valid = min(32, p.N - n0);   // may be <= 0 for the ragged last tile
+          if (MODE == 0) {
+            if (valid <= 0) continue;
+            float tm = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            x[j] = __uint_as_float(v0[j]) * p.scale_log2;
-            x[32 + j] = __uint_as_float(v1[j]) * p.scale_log2;
-          }
-          if (valid < kSimBN) {
+            for (int j = 0; j < 32; ++j)
+              if (valid == 32 || j < valid) tm = fmaxf(tm, __uint_as_float(v[j]));
+            const float new_m = fmaxf(run_m, tm * p.scale_log2);     // scale > 0: max commutes with the scaling
+            if (new_m > run_m) {
+              run_l *= ex2_approx(run_m - new_m);
+              run_m = new_m;
+            }
+            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+            if (valid == 32) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j)
-              if (j >= valid) x[j] = -INFINITY;
-          }
-          float tm = x[0];
-#pragma unroll
-          for (int j = 1; j < 64; ++j) tm = fmaxf(tm, x[j]);
-          const float new_m = fmaxf(run_m, tm);
-          float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#pragma unroll
-          for (int j = 0; j < 64; j += 4) {
-            s0 += ex2_approx(x[j] - new_m);
-            s1 += ex2_approx(x[j + 1] - new_m);
-            s2 += ex2_approx(x[j + 2] - new_m);
-            s3 += ex2_approx(x[j + 3] - new_m);
-          }
-          run_l = run_l * ex2_approx(run_m - new_m) + ((s0 + s1) + (s2 + s3));
-          run_m = new_m;
-        } else {
-          if (row < p.M) {
-            __nv_bfloat16* prow = p.P + (long long)row * p.ldp + n0;
-            if (valid == kSimBN) {
-#pragma unroll
-              for (int j = 0; j < 64; j += 8) {
-                float e[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float s = __uint_as_float(j + i < 32 ? v0[(j + i) & 31] : v1[(j + i) & 31]);
-                  e[i] = ex2_approx(s * p.scale_log2 - my_lse2);
-                  if ((long long)(n0 + j + i) == my_label) e[i] -= 1.0f;
-                }
-                uint4 pk;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(e[0], e[1]);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(e[2], e[3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(e[4], e[5]);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(e[6], e[7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(prow + j) = pk;
+              for (int j = 0; j < 32; j += 4) {
+                s0 += ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -run_m));
+                s1 += ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -run_m));
+                s2 += ex2_approx(fmaf(__uint_as_float(v[j + 2]), p.scale_log2, -run_m));
+                s3 += ex2_approx(fmaf(__uint_as_float(v[j + 3]), p.scale_log2, -run_m));
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 64; ++j) {
-                if (j < valid) {
-                  const float s = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
-                  float e = ex2_approx(s * p.scale_log2 - my_lse2);
-                  if ((long long)(n0 + j) == my_label) e -= 1.0f;
-                  prow[j] = __float2bfloat16(e);
+              for (int j = 0; j < 32; ++j)
+                if (j < valid) s0 += ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -run_m));
+            }
+            run_l += (s0 + s1) + (s2 + s3);
+          } else {
+            if (row < p.M && valid > 0) {
+              __nv_bfloat16* prow = p.P + (long long)row * p.ldp + n0;
+              if (valid == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  float e[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    e[i] = ex2_approx(fmaf(__uint_as_float(v[j + i]), p.scale_log2, -my_lse2));
+                    if ((long long)(n0 + j + i) == my_label) e[i] -= 1.0f;
+                  }
+                  uint4 pk;
+                  __nv_bfloat162 h0 = __floats2bfloat162_rn(e[0], e[1]);
+                  __nv_bfloat162 h1 = __floats2bfloat162_rn(e[2], e[3]);
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(e[4], e[5]);
+                  __nv_bfloat162 h3 = __floats2bfloat162_rn(e[6], e[7]);
+                  pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                  pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                  pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                  *reinterpret_cast<uint4*>(prow + j) = pk;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (j < valid) {
+                    float e = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -my_lse2));
+                    if ((long long)(n0 + j) == my_label) e -= 1.0f;
+                    prow[j] = __float2bfloat16(e);
+                  }
                 }
               }
             }
           }
         }
+        // accumulator consumed: hand the TMEM buffer back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
       }
-      if (MODE == 0 && row < p.M) p.partial[(long long)ch * p.M + row] = make_float2(run_m, run_l);
+      if (MODE == 0 && row < p.M)
+        p.partial[((long long)ch * 2 + half) * p.M + row] = make_float2(run_m, run_l);
     }
   }
 
@@ -313,12 +311,10 @@ __global__ void lse_combine_kernel(const float2* __restrict__ partial, int n_chu
   }
 }
 
-// Choose the decomposition: rows per block (MT) and the number of G chunks so that the unit count fills the
-// SMs in whole waves.
-static void plan_units(int M, int N, int* mt, int* m_blocks, int* n_chunks, int* tiles_per_chunk) {
+// Choose the number of G chunks so that the unit count fills the SMs in whole waves.
+static void plan_units(int M, int N, int* m_blocks, int* n_chunks, int* tiles_per_chunk) {
   const int sms = sm_count();
-  *mt = (M > 128) ? 2 : 1;
-  *m_blocks = (M + 128 * (*mt) - 1) / (128 * (*mt));
+  *m_blocks = (M + 127) / 128;
   const int n_tiles = (N + kSimBN - 1) / kSimBN;
   int best_c = 1;
   double best_eff = -1.0;
@@ -328,8 +324,8 @@ static void plan_units(int M, int N, int* mt, int* m_blocks, int* n_chunks, int*
     const int cc = (n_tiles + per - 1) / per;  // chunks actually non-empty
     const long long units = (long long)(*m_blocks) * cc;
     const long long waves = (units + sms - 1) / sms;
-    // cost ~ waves * (tiles per chunk + fixed per-unit overhead of ~4 tiles for the A reload / drain)
-    const double cost = (double)waves * (per + 4.0);
+    // cost ~ waves * (tiles per chunk + fixed per-unit overhead of ~1 tile for the A reload / drain)
+    const double cost = (double)waves * (per + 1.0);
     const double ideal = (double)(*m_blocks) * n_tiles / sms;
     const double eff = ideal / cost;
     if (eff > best_eff + 1e-9) {
@@ -343,15 +339,15 @@ static void plan_units(int M, int N, int* mt, int* m_blocks, int* n_chunks, int*
 }
 
 size_t rowlse_workspace_bytes(int M, int N) {
-  int mt, mb, nc, tpc;
-  plan_units(M, N, &mt, &mb, &nc, &tpc);
-  return (size_t)nc * (size_t)M * sizeof(float2);
+  int mb, nc, tpc;
+  plan_units(M, N, &mb, &nc, &tpc);
+  return (size_t)nc * 2 * (size_t)M * sizeof(float2);
 }
 
-template <int MT, int MODE>
+template <int MODE>
 static int launch_sim(const CUtensorMap& tq, const CUtensorMap& tg, const SimParams& p, cudaStream_t stream) {
-  using Cfg = SimCfg<MT>;
-  auto kern = sim_tc_kernel<MT, MODE>;
+  using Cfg = SimCfg;
+  auto kern = sim_tc_kernel<MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -363,7 +359,7 @@ static int launch_sim(const CUtensorMap& tq, const CUtensorMap& tg, const SimPar
   }
   const int units = p.m_blocks * p.n_chunks;
   const int grid = units < sm_count() ? units : sm_count();
-  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tq, tg, p);
+  kern<<<grid, kSimThreads, Cfg::kSmemBytes, stream>>>(tq, tg, p);
   return check_launch("sim_tc_kernel");
 }
 
@@ -388,10 +384,13 @@ int rowlse_bf16(const void* Q, const void* G, const long long* labels, int M, in
                 float* score, float* lse2, void* workspace, size_t ws_bytes, cudaStream_t stream) {
   int rc = check_sim_args("rowlse", Q, G, M, N, D);
   if (rc) return rc;
+  if (!(scale > 0.0f)) {
+    set_error("rowlse: scale must be positive");
+    return CFL_EINVAL;
+  }
   SimParams p{};
-  int mt;
-  plan_units(M, N, &mt, &p.m_blocks, &p.n_chunks, &p.tiles_per_chunk);
-  const size_t need = (size_t)p.n_chunks * (size_t)M * sizeof(float2);
+  plan_units(M, N, &p.m_blocks, &p.n_chunks, &p.tiles_per_chunk);
+  const size_t need = (size_t)p.n_chunks * 2 * (size_t)M * sizeof(float2);
   if (ws_bytes < need || workspace == nullptr) {
     set_error("rowlse: workspace %zu B < %zu B", ws_bytes, need);
     return CFL_EWORKSPACE;
@@ -402,11 +401,11 @@ int rowlse_bf16(const void* Q, const void* G, const long long* labels, int M, in
   CUtensorMap tq, tg;
   if ((rc = make_tmap_2d(&tq, Q, 2, M, D, D, kSimKC, 128))) return rc;
   if ((rc = make_tmap_2d(&tg, G, 2, N, D, D, kSimKC, kSimBN))) return rc;
-  rc = (mt == 2) ? launch_sim<2, 0>(tq, tg, p, stream) : launch_sim<1, 0>(tq, tg, p, stream);
+  rc = launch_sim<0>(tq, tg, p, stream);
   if (rc) return rc;
   const int wpb = 8;
   lse_combine_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
-      p.partial, p.n_chunks, M, D, reinterpret_cast<const __nv_bfloat16*>(Q),
+      p.partial, p.n_chunks * 2, M, D, reinterpret_cast<const __nv_bfloat16*>(Q),
       reinterpret_cast<const __nv_bfloat16*>(G), labels, scale, lse2, score);
   return check_launch("lse_combine_kernel");
 }
@@ -421,8 +420,7 @@ int softmax_emit_bf16(const void* Q, const void* G, const long long* labels, con
     return CFL_EINVAL;
   }
   SimParams p{};
-  int mt;
-  plan_units(M, N, &mt, &p.m_blocks, &p.n_chunks, &p.tiles_per_chunk);
+  plan_units(M, N, &p.m_blocks, &p.n_chunks, &p.tiles_per_chunk);
   p.M = M; p.N = N; p.D = D;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse2 = lse2;
@@ -432,7 +430,7 @@ int softmax_emit_bf16(const void* Q, const void* G, const long long* labels, con
   CUtensorMap tq, tg;
   if ((rc = make_tmap_2d(&tq, Q, 2, M, D, D, kSimKC, 128))) return rc;
   if ((rc = make_tmap_2d(&tg, G, 2, N, D, D, kSimKC, kSimBN))) return rc;
-  return (mt == 2) ? launch_sim<2, 1>(tq, tg, p, stream) : launch_sim<1, 1>(tq, tg, p, stream);
+  return launch_sim<1>(tq, tg, p, stream);
 }
 
 }  // namespace cfl
