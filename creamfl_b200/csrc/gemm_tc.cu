@@ -28,15 +28,20 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kGemmThreads = 384;   // 4 control warps + 8 epilogue warps
 
-template <int BN>
+// ADD_TMA: the bf16 residual operand of the epilogue (`add`) is prefetched tile by tile into shared memory by the
+// TMA producer (two buffers), so its DRAM latency hides behind the previous tiles instead of stalling the epilogue.
+template <int BN, bool ADD_TMA = false>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 128) ? 4 : 6;
+  static constexpr int kStages = ADD_TMA ? 3 : ((BN == 256) ? 3 : (BN == 128 ? 4 : 6));
   static constexpr int kOutBytes = kBM * BN * 2;            // bf16 output tile staged for the TMA store
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kOutBytes + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr uint32_t kTmemCols = 2 * BN;              // two accumulator buffers (power of two for BN 64/128)
+  static constexpr int kOutBufs = (BN == 256) ? 1 : 2;      // staging buffers (BN = 256: 64 KB, single)
+  static constexpr int kAddBufs = ADD_TMA ? 2 : 0;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + (kOutBufs + kAddBufs) * kOutBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t kTmemCols = 2 * BN;              // two accumulator buffers (power of two)
 };
 
 // erf with |error| <= 1.5e-7 (Abramowitz-Stegun 7.1.26): one ex2, one rcp, 6 FMA - the epilogue must not outlast
@@ -68,20 +73,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool ADD_TMA>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, GemmParams p) {
+  using Cfg = GemmCfg<BN, ADD_TMA>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sout = smem + Cfg::kStages * Cfg::kStageBytes;    // [2][kOutBytes], 1024-aligned (stage sizes are)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sout + 2 * Cfg::kOutBytes);
+  uint8_t* sadd = sout + Cfg::kOutBufs * Cfg::kOutBytes;    // [kAddBufs][kOutBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sadd + Cfg::kAddBufs * Cfg::kOutBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::kStages;
   uint64_t* tfull = bars + 2 * Cfg::kStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* dfull = tempty + 2;                              // [2] residual tile landed
+  uint64_t* dempty = dfull + 2;                              // [2] residual tile consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,6 +104,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (p.tma_out) tma_prefetch_desc(&tmC);
+    if (ADD_TMA) tma_prefetch_desc(&tmD);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
@@ -105,6 +114,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 8);
+      mbar_init(&dfull[i], 1);
+      mbar_init(&dempty[i], 8);
     }
     fence_mbar_init();
   }
@@ -119,12 +130,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      int it = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
         const int m_blk = u % num_m;
         const int n_blk = (u / num_m) % num_n;
         const int ks = u / (num_m * num_n);
         const int kb0 = ks * kb_per;
         const int kb1 = min(nkb, kb0 + kb_per);
+        if (ADD_TMA) {
+          const int db = it & 1;
+          mbar_wait(&dempty[db], ((it >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&dfull[db], Cfg::kOutBytes);
+#pragma unroll
+          for (int r = 0; r < BN / 64; ++r)
+            tma_load_2d(&tmD, &dfull[db], sadd + db * Cfg::kOutBytes + r * (kBM * 128), n_blk * BN + r * 64,
+                        m_blk * kBM);
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
@@ -202,20 +223,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int buf = it & 1;
       const uint32_t bphase = (it >> 1) & 1;
       const bool has_k = ks * kb_per < nkb;
-      uint8_t* stile = sout + buf * Cfg::kOutBytes;
+      uint8_t* stile = sout + (Cfg::kOutBufs == 2 ? buf : 0) * Cfg::kOutBytes;
       if (p.tma_out) {
-        // the TMA store that last read this staging buffer (two tiles ago) must have drained
-        if (issuer) tma_store_wait_read<1>();
+        // the TMA store that last read this staging buffer must have drained
+        if (issuer) tma_store_wait_read<Cfg::kOutBufs - 1>();
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+      const int row = m_blk * kBM + rloc;
+      // residual operand (bf16): fetched one 32-column chunk ahead of its use, the first chunk before the
+      // accumulator is even ready, so the global-load latency hides behind the MMAs / the previous chunk
+      const bool add_fast = !ADD_TMA && p.add != nullptr && p.add_bf16 && ks == 0 && row < p.M && has_k &&
+                            ((p.ld_add & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.add) & 15) == 0);
+      const __nv_bfloat16* add_row =
+          add_fast ? reinterpret_cast<const __nv_bfloat16*>(p.add) + (long long)row * p.ld_add + n_blk * BN + half * HC
+                   : nullptr;
+      uint4 add_cur[4], add_nxt[4];
+      bool cur_ok = false, nxt_ok = false;
+      if (add_fast && n_blk * BN + half * HC + 32 <= p.N) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) add_cur[j] = __ldg(reinterpret_cast<const uint4*>(add_row) + j);
+        cur_ok = true;
+      }
+      if (ADD_TMA) mbar_wait(&dfull[buf], bphase);
       mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
-      const int row = m_blk * kBM + rloc;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + half * HC;
 #pragma unroll 1
       for (int c = 0; c < HC / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
+        nxt_ok = false;
+        if (add_fast && c + 1 < HC / 32 && n_blk * BN + half * HC + (c + 2) * 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) add_nxt[j] = __ldg(reinterpret_cast<const uint4*>(add_row + (c + 1) * 32) + j);
+          nxt_ok = true;
+        }
         tmem_ld_wait();
         const int ctile = half * HC + c * 32;          // column offset inside the tile
         const int col0 = n_blk * BN + ctile;
@@ -230,8 +272,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j)
               if (full_chunk || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
           }
-          if (p.add != nullptr && ks == 0) {
-            if (p.add_bf16) {
+          if (ADD_TMA) {
+            // residual tile staged by the producer: same 128-byte-row swizzled layout as the output staging
+            const uint8_t* dbase = sadd + buf * Cfg::kOutBytes + (ctile >> 6) * (kBM * 128);
+            const int du = (ctile & 63) >> 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 pk = *reinterpret_cast<const uint4*>(dbase + sw128_offset(rloc, du + j));
+              const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+                f[8 * j + 2 * i] += t2.x;
+                f[8 * j + 2 * i + 1] += t2.y;
+              }
+            }
+          } else if (p.add != nullptr && ks == 0) {
+            if (cur_ok) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t w[4] = {add_cur[j].x, add_cur[j].y, add_cur[j].z, add_cur[j].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+                  f[8 * j + 2 * i] += t2.x;
+                  f[8 * j + 2 * i + 1] += t2.y;
+                }
+              }
+            } else if (p.add_bf16) {
               const __nv_bfloat16* ar = reinterpret_cast<const __nv_bfloat16*>(p.add) + (long long)row * p.ld_add + col0;
               if (full_chunk && ((reinterpret_cast<uintptr_t>(ar) & 15) == 0)) {
 #pragma unroll
@@ -309,9 +377,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (p.tma_out) {
           // stage the bf16 row chunk: 128-byte rows, 16-byte units XOR-swizzled like the TMA store map expects
-          constexpr int kUnitsPerRow = (BN == 128) ? 8 : 8;   // a staged row is always 64 columns = 128 bytes
-          const int region = (BN == 128) ? half : 0;          // BN = 128: one 64-column region per half
-          const int unit0 = (BN == 128) ? c * 4 : half * 4;   // first 16-byte unit of this chunk inside the row
+          const int region = ctile >> 6;                      // staged regions are 64 columns (128 bytes) wide
+          const int unit0 = (ctile & 63) >> 3;                // first 16-byte unit of this chunk inside the row
           uint8_t* rbase = stile + region * (kBM * 128);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -319,7 +386,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
             *reinterpret_cast<uint4*>(rbase + sw128_offset(rloc, unit0 + j)) = pk;
           }
-          (void)kUnitsPerRow;
         } else if (live) {
           if (p.split_k > 1 || p.atomic_out) {
             float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
@@ -357,11 +423,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        cur_ok = nxt_ok;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) add_cur[j] = add_nxt[j];
       }
-      // accumulator is consumed: hand the TMEM buffer back to the MMA warp
+      // accumulator is consumed: hand the TMEM buffer (and the residual buffer) back
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (lane == 0) {
+        mbar_arrive(&tempty[buf]);
+        if (ADD_TMA) mbar_arrive(&dempty[buf]);
+      }
       if (p.tma_out) {
         fence_proxy_async_smem();                         // generic-proxy smem writes -> visible to the TMA engine
         asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -384,11 +456,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
-                       cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+template <int BN, bool A_MN, bool B_MN, bool ADD_TMA = false>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td,
+                       const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, ADD_TMA>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, ADD_TMA>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -402,7 +474,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const int num_n = (p.N + BN - 1) / BN;
   const int units = num_m * num_n * p.split_k;
   const int grid = units < sm_count() ? units : sm_count();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, td, p);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -429,35 +501,48 @@ int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long l
     set_error("gemm_bf16: act %d needs aux", p.act);
     return CFL_EINVAL;
   }
-  // Narrow outputs waste MMA columns: pick the tile width from N.
-  const int BN = (p.N <= 64) ? 64 : 128;
-  CUtensorMap ta, tb, tc;
+  // Narrow outputs waste MMA columns: pick the tile width from N.  128x256 tiles read 96 B/clk of operands from
+  // shared memory per SM (128x128: 128 B/clk, the port limit), so wide outputs use them whenever N fills them.
+  // (short-K problems are HBM-bound: they keep the 128-wide configuration with double-buffered output staging)
+  int BN = (p.N <= 64) ? 64 : ((((p.N >= 256 && p.N % 256 == 0) || p.N >= 1024) && p.K >= 512) ? 256 : 128);
+  // residual operand through TMA: needs the 128-wide configuration (two residual + two output staging buffers)
+  const bool add_tma = p.add != nullptr && p.add_bf16 && p.split_k == 1 && !a_mn && p.N > 64 &&
+                       (reinterpret_cast<uintptr_t>(p.add) & 15) == 0 && ((p.ld_add * 2) & 15) == 0;
+  if (add_tma) BN = 128;
+  CUtensorMap ta, tb, tc, td;
   memset(&tc, 0, sizeof(tc));
+  memset(&td, 0, sizeof(td));
   int rc;
   // bf16 outputs that TMA can address leave through a staged, fully coalesced TMA store
   p.tma_out = (p.out_bf16 && p.split_k == 1 && !p.atomic_out && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
                ((p.ldo * 2) & 15) == 0) ? 1 : 0;
   if (p.out2 != nullptr && p.ldo2 == 0) p.ldo2 = p.ldo;
   if (p.tma_out && (rc = make_tmap_2d(&tc, p.out, 2, p.M, p.N, p.ldo, 64, kBM))) return rc;
+  if (add_tma && (rc = make_tmap_2d(&td, p.add, 2, p.M, p.N, p.ld_add, 64, kBM))) return rc;
   if (!a_mn)
     rc = make_tmap_2d(&ta, a, 2, p.M, p.K, lda, kBK, kBM);
   else
     rc = make_tmap_2d(&ta, a, 2, p.K, p.M, lda, 64, kBK);
   if (rc) return rc;
   if (!b_mn)
-    rc = make_tmap_2d(&tb, b, 2, p.N, p.K, ldb, kBK, BN);
+    rc = make_tmap_2d(&tb, b, 2, p.N, p.K, ldb, kBK, BN);   // BN <= 256 rows per box
   else
     rc = make_tmap_2d(&tb, b, 2, p.K, p.N, ldb, 64, kBK);
   if (rc) return rc;
 
 #define CFL_DISPATCH(BNV)                                                                      \
   do {                                                                                         \
-    if (!a_mn && !b_mn) return launch_gemm<BNV, false, false>(ta, tb, tc, p, stream);          \
-    if (!a_mn && b_mn) return launch_gemm<BNV, false, true>(ta, tb, tc, p, stream);            \
-    if (a_mn && !b_mn) return launch_gemm<BNV, true, false>(ta, tb, tc, p, stream);            \
-    return launch_gemm<BNV, true, true>(ta, tb, tc, p, stream);                                \
+    if (!a_mn && !b_mn) return launch_gemm<BNV, false, false>(ta, tb, tc, td, p, stream);      \
+    if (!a_mn && b_mn) return launch_gemm<BNV, false, true>(ta, tb, tc, td, p, stream);        \
+    if (a_mn && !b_mn) return launch_gemm<BNV, true, false>(ta, tb, tc, td, p, stream);        \
+    return launch_gemm<BNV, true, true>(ta, tb, tc, td, p, stream);                            \
   } while (0)
+  if (add_tma) {
+    if (b_mn) return launch_gemm<128, false, true, true>(ta, tb, tc, td, p, stream);
+    return launch_gemm<128, false, false, true>(ta, tb, tc, td, p, stream);
+  }
   if (BN == 64) CFL_DISPATCH(64);
+  if (BN == 256) CFL_DISPATCH(256);
   CFL_DISPATCH(128);
 #undef CFL_DISPATCH
 }

@@ -535,36 +535,46 @@ im2col_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int
 }
 
 // Stem: fp32 NCHW images straight to the bf16 patch matrix (fuses the layout change and the cast).
-// Column order (r, s, c) to match [Cout, R, S, Cin] filters.  One thread per (pixel, group of 8 columns): 8 gathered
-// reads (L1/L2 hits - every input value is reused R*S/stride^2 times) and one 16-byte store.
+// Column order (r, s, c) to match [Cout, R, S, Cin] filters.  One CTA per output row (n, ho): the R input rows of
+// every channel are staged in shared memory with coalesced loads, then every thread assembles 16-byte column groups
+// from shared memory and the CTA writes its Wo x ldc slab of the patch matrix contiguously.
 __global__ void __launch_bounds__(256)
 im2col_nchw_f32_kernel(const float* __restrict__ x, int N, int C, int H, int W, int R, int S, int stride, int pad,
                        int Ho, int Wo, int ldc, __nv_bfloat16* __restrict__ col) {
-  const int groups = ldc >> 3;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long pixels = (long long)N * Ho * Wo;
-  if (t >= pixels * groups) return;
-  // pixel index fastest: a warp reads 32 neighbouring output columns of the same filter taps (stride-2 coalesced)
-  const int g = (int)(t / pixels);
-  long long q = t % pixels;
-  const long long pix = q;
-  const int wo = (int)(q % Wo); q /= Wo;
-  const int ho = (int)(q % Ho);
-  const int n = (int)(q / Ho);
-  const int kcols = R * S * C;
-  float f[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int e = g * 8 + i;
-    float v = 0.0f;
-    if (e < kcols) {
+  extern __shared__ float srow[];            // [C][R][W + 2*pad] (zero padded left/right and for rows outside the image)
+  const int n = blockIdx.x / Ho, ho = blockIdx.x % Ho;
+  const int Wp = W + 2 * pad;
+  const int h0 = ho * stride - pad;
+  int* soff = reinterpret_cast<int*>(srow + C * R * Wp);   // [ldc] column -> offset inside srow (or -1: zero tail)
+  for (int e = threadIdx.x; e < ldc; e += blockDim.x) {
+    int o = -1;
+    if (e < R * S * C) {
       const int tap = e / C, c = e - tap * C;
-      const int h = ho * stride + tap / S - pad, w = wo * stride + tap % S - pad;
-      if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(x + (((long long)n * C + c) * H + h) * W + w);
+      const int r = tap / S, s_ = tap - r * S;
+      o = (c * R + r) * Wp + s_;
     }
-    f[i] = v;
+    soff[e] = o;
   }
-  *reinterpret_cast<bf16x8*>(col + pix * ldc + g * 8) = pack8(f);
+  for (int e = threadIdx.x; e < C * R * Wp; e += blockDim.x) {
+    const int wp = e % Wp;
+    const int r = (e / Wp) % R;
+    const int c = e / (Wp * R);
+    const int h = h0 + r, w = wp - pad;
+    srow[e] = (h >= 0 && h < H && w >= 0 && w < W) ? __ldg(x + (((long long)n * C + c) * H + h) * W + w) : 0.0f;
+  }
+  __syncthreads();
+  const int groups = ldc >> 3;
+  __nv_bfloat16* out = col + ((long long)n * Ho + ho) * Wo * ldc;
+  for (int t = threadIdx.x; t < Wo * groups; t += blockDim.x) {
+    const int wo = t / groups, g = t % groups;
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int o = soff[g * 8 + i];
+      f[i] = o >= 0 ? srow[o + wo * stride] : 0.0f;
+    }
+    *reinterpret_cast<bf16x8*>(out + (long long)wo * ldc + g * 8) = pack8(f);
+  }
 }
 
 // dX (NHWC bf16) from dcol: gather over the taps that touch each input pixel.
@@ -632,8 +642,14 @@ int im2col_nchw_f32(const float* x, int N, int C, int H, int W, int R, int S, in
     return CFL_EINVAL;
   }
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
-  const long long total = (long long)N * Ho * Wo * (ldc >> 3);
-  im2col_nchw_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+  const size_t smem = (size_t)C * R * (W + 2 * pad) * sizeof(float) + (size_t)ldc * sizeof(int);
+  if (smem > 200 * 1024) {
+    set_error("im2col_nchw_f32: image row block of %zu B does not fit in shared memory", smem);
+    return CFL_EINVAL;
+  }
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(im2col_nchw_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  im2col_nchw_f32_kernel<<<(unsigned)(N * Ho), 256, smem, st>>>(
       x, N, C, H, W, R, S, stride, pad, Ho, Wo, ldc, reinterpret_cast<__nv_bfloat16*>(col));
   return check_launch("im2col_nchw_f32");
 }
