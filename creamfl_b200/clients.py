@@ -12,8 +12,8 @@ import torch
 import torch.nn as nn
 from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
 
-from . import ops
-from .towers import EncoderImage, StoreMixin, ParamStore
+from . import ops, tower_ops as T
+from .towers import EncoderImage, ResNet, StoreMixin, ParamStore, _Linear, grad_target
 
 
 def get_pad_mask(max_length, lengths, set_pad_to_one=True):
@@ -138,3 +138,111 @@ class ClientPCME(StoreMixin, nn.Module):
             'caption_features': caption_output['embedding'], 'caption_attentions': None, 'caption_residuals': None,
             'caption_logsigma': None, 'caption_logsigma_att': None,
         }
+
+
+# ===================================================================================================== unimodal image client
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 GEMM: x fp32/bf16 [R, K] (rounded to bf16), W a ParamStore parameter [N, K],
+    y fp32 [R, N].  dW / db accumulate into the flat gradient buffer."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x16 = ops.to_bf16(x.detach()) if x.dtype != torch.bfloat16 else x.detach()
+        y = ops.gemm_bf16(x16, weight._w16, bias=bias, out_dtype=torch.float32)
+        ctx.save_for_backward(x16)
+        ctx.weight, ctx.bias, ctx.x_dtype = weight, bias, x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x16,) = ctx.saved_tensors
+        w = ctx.weight
+        dy16 = ops.to_bf16(dy.contiguous().float())
+        ops.gemm_bf16(dy16, x16, a_mn=True, b_mn=True, out=grad_target(w), split_k=0, accumulate=True)
+        if ctx.bias is not None:
+            T.colsum_into(dy16, grad_target(ctx.bias))
+        dx = ops.gemm_bf16(dy16, w._w16, b_mn=True, out_dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        return (dx.to(ctx.x_dtype) if dx is not None else None), None, None
+
+
+class _GramFn(torch.autograd.Function):
+    """W W^T for the class-centre loss (ClientTrainer.py:353): fp32 [C, C]; gradient (dG + dG^T) W accumulated."""
+
+    @staticmethod
+    def forward(ctx, weight):
+        ctx.weight = weight
+        return ops.gemm_bf16(weight._w16, weight._w16, out_dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, dg):
+        w = ctx.weight
+        sym = ops.to_bf16((dg + dg.t()).contiguous().float())
+        # d/dW of sum(dG * W W^T) = (dG + dG^T) W ; entries the ReLU clamp zeroed carry no gradient (relu'(w) = 0)
+        gw = ops.gemm_bf16(sym, w._w16, b_mn=True, out_dtype=torch.float32)
+        grad_target(w).add_(gw * (w.data > 0))
+        return None
+
+
+class _PoolFn(torch.autograd.Function):
+    """avg_pool over H*W times `scale` (resnet_client.py:177-179): NHWC bf16 map -> fp32 [N, C]."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        y, _ = T.avgpool_fwd(x, scale)
+        ctx.shape, ctx.scale = tuple(x.shape), scale
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return T.avgpool_bwd(ops.to_bf16(dy.contiguous().float()), ctx.shape, ctx.scale), None
+
+
+class ImageClient(StoreMixin, nn.Module):
+    """Mirror of src/networks/resnet_client.py ResNet (resnet18_client, :220-232): trunk on the creamfl_b200
+    kernels, `x * scale`, Linear(512, D); `phase == 'extract_conv_feature'` returns the L2-normalised embedding,
+    otherwise the classifier heads with ReLU-clamped weights (:193-201)."""
+
+    def __init__(self, num_class=100, embed_dim=256, scale=128, is_train=True, phase='none', arch='resnet18'):
+        super().__init__()
+        trunk = ResNet(arch)
+        # same attribute names as the reference so that state_dict keys match
+        self.conv1, self.bn1 = trunk.conv1, trunk.bn1
+        self.layer1, self.layer2, self.layer3, self.layer4 = trunk.layer1, trunk.layer2, trunk.layer3, trunk.layer4
+        self._trunk = [trunk]                      # not a registered submodule (parameters are registered above)
+        self.embed_dim = embed_dim
+        if embed_dim != 512:
+            self.linear = _Linear(512, embed_dim)
+        self.class_fc_2 = _Linear(embed_dim, num_class)
+        self.class_fc_22 = _Linear(embed_dim, 80)
+        self.is_train, self.scale, self.phase = bool(is_train), int(scale), str(phase)
+
+    def forward(self, x):
+        self.store()
+        fmap = self._trunk[0](x)
+        feat = _PoolFn.apply(fmap, float(self.scale))
+        if self.embed_dim != 512:
+            feat = _LinearFn.apply(feat, self.linear.weight, self.linear.bias)
+        if self.phase == 'extract_conv_feature':
+            return ops.l2_normalize(feat)
+        if self.is_train:
+            for fc in (self.class_fc_2, self.class_fc_22):
+                T.relu_inplace(fc.weight.data, fc.weight._w16)
+            x1 = _LinearFn.apply(feat, self.class_fc_2.weight, self.class_fc_2.bias)
+            x2 = _LinearFn.apply(feat, self.class_fc_22.weight, self.class_fc_22.bias)
+            return x1, x2, self.class_fc_2.weight, self.class_fc_22.weight
+        return feat
+
+
+def resnet18_client(pretrained=False, **kwargs):
+    """src/networks/resnet_client.py:220-232 (ImageNet weights are not on the box: `pretrained` is ignored)."""
+    return ImageClient(num_class=kwargs.get('num_class', 100), embed_dim=kwargs.get('embed_dim', 256),
+                       scale=kwargs.get('scale', 128), is_train=kwargs.get('is_train', True),
+                       phase=kwargs.get('phase', 'none'))
+
+
+def unimodal_supervised_loss(model: ImageClient, inputs, labels, inter_distance: float = 4.0):
+    """ClientTrainer.tra supervised pass (ClientTrainer.py:322-356): CE(fvec - 4*onehot, y) + 0.5 * CE(W W^T, arange)."""
+    fvec, _, class_weight, _ = model(inputs)
+    loss = ops.cross_entropy(fvec, labels, inter_distance)
+    center = ops.cross_entropy(_GramFn.apply(class_weight), None, 0.0)
+    return 0.5 * center + loss, fvec

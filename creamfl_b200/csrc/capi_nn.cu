@@ -299,6 +299,39 @@ int creamfl_pie_pool_bwd(const void* x, const void* h, const float* w2, const fl
   return pie_pool_bwd(x, h, w2, attn, d_r, d_pooled, B, P, C, Hd, dx, dpre, dw2, S(stream));
 }
 
+int creamfl_avgpool_fwd(const void* x, int N, int P, int C, float scale, float* y, void* y16, void* stream) {
+  if (!x || (!y && !y16)) {
+    set_error("avgpool_fwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return avgpool_fwd(x, N, P, C, scale, y, y16, S(stream));
+}
+
+int creamfl_avgpool_bwd(const void* dy, int N, int P, int C, float scale, void* dx, void* stream) {
+  if (!dy || !dx) {
+    set_error("avgpool_bwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return avgpool_bwd(dy, N, P, C, scale, dx, S(stream));
+}
+
+int creamfl_ce_fwd(const float* x, int64_t ldx, const int64_t* labels, int R, int C, float margin, float* loss_rows,
+                   float* dlogits, float* loss, void* stream) {
+  if (!x || !loss_rows || !dlogits) {
+    set_error("ce_fwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return ce_fwd(x, ldx, reinterpret_cast<const long long*>(labels), R, C, margin, loss_rows, dlogits, loss, S(stream));
+}
+
+int creamfl_relu_inplace(float* x, void* shadow, int64_t n, void* stream) {
+  if (!x) {
+    set_error("relu_inplace: null pointer");
+    return CFL_EINVAL;
+  }
+  return relu_inplace(x, shadow, n, S(stream));
+}
+
 int creamfl_optimizer_step(const void* rows, int n_rows, const void* tensors, int n_tensors, const float* hyper,
                            float* state, double* total_gg, float* stats, int32_t* flag, float* tnorm,
                            float* layer_acc, void* stream) {

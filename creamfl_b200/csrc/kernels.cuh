@@ -89,4 +89,8 @@ int pie_pool_bwd(const void*, const void*, const float*, const float*, const voi
 // optim.cu
 int optimizer_step(const void*, int, const void*, int, const float*, float*, double*, float*, int*, float*, float*,
                    cudaStream_t);
+int avgpool_fwd(const void*, int, int, int, float, float*, void*, cudaStream_t);
+int avgpool_bwd(const void*, int, int, int, float, void*, cudaStream_t);
+int ce_fwd(const float*, long long, const long long*, int, int, float, float*, float*, float*, cudaStream_t);
+int relu_inplace(float*, void*, long long, cudaStream_t);
 }  // namespace cfl

@@ -195,6 +195,34 @@ __global__ void moon_bwd_kernel(const float* __restrict__ zold, const float* __r
   dz[e] = gout[0] * coef[r] * (zold[e] - bank[idx[r] * D + k]);
 }
 
+// --------------------------------------------------------------------------------------------- softmax cross-entropy
+// Row r: logits z = x[r, :] - margin * onehot(label_r)   (ClientTrainer.py:346-350: "fvec - inter_distance * one_hot"),
+// loss_r = logsumexp(z) - z[label_r]; out: loss_rows[r] = loss_r / R and dlogits[r, :] = (softmax(z) - onehot) / R
+// (nn.CrossEntropyLoss mean reduction).  One warp per row, C <= 4096.
+__global__ void __launch_bounds__(256)
+ce_fwd_kernel(const float* __restrict__ x, long long ldx, const long long* __restrict__ labels, int R, int C,
+              float margin, float* __restrict__ loss_rows, float* __restrict__ dlogits) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const long long lab = labels ? labels[r] : (long long)r;
+  const float* xr = x + (long long)r * ldx;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, xr[c] - (c == lab ? margin : 0.0f));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.0f;
+  for (int c = lane; c < C; c += 32) s += __expf(xr[c] - (c == lab ? margin : 0.0f) - m);
+  s = warp_sum(s);
+  const float lse = m + __logf(s);
+  const float inv_r = 1.0f / (float)R;
+  for (int c = lane; c < C; c += 32) {
+    const float z = xr[c] - (c == lab ? margin : 0.0f);
+    dlogits[(long long)r * C + c] = (__expf(z - lse) - (c == lab ? 1.0f : 0.0f)) * inv_r;
+  }
+  if (lane == 0) loss_rows[r] = (lse - (xr[lab] - margin)) * inv_r;
+}
+
 // --------------------------------------------------------------------------------------------- distill MSE
 // loss = mean_{r,k} (x[r,k] - bank[idx_r,k])^2 ; two-stage fixed-order reduction.
 __global__ void __launch_bounds__(256)
@@ -356,6 +384,32 @@ int moon_bwd(const float* zold, const float* bank, const long long* idx, const f
   const long long n = (long long)R * D;
   moon_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(zold, bank, idx, coef, gout, R, D, dz);
   return check_launch("moon_bwd");
+}
+
+int ce_fwd(const float* x, long long ldx, const long long* labels, int R, int C, float margin, float* loss_rows,
+           float* dlogits, float* loss_out, cudaStream_t st) {
+  if (R <= 0 || C <= 0) {
+    set_error("ce_fwd: empty problem");
+    return CFL_EINVAL;
+  }
+  ce_fwd_kernel<<<(R + 7) / 8, 256, 0, st>>>(x, ldx, labels, R, C, margin, loss_rows, dlogits);
+  if (loss_out) sum_finish_kernel<<<1, 256, 0, st>>>(loss_rows, R, 1.0f, loss_out);
+  return check_launch("ce_fwd");
+}
+
+// x = max(x, 0) in place on the fp32 master and its bf16 shadow (resnet_client.py:193-197 clamps class_fc weights)
+__global__ void relu_inplace_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ shadow, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = fmaxf(x[i], 0.0f);
+  x[i] = v;
+  if (shadow) shadow[i] = __float2bfloat16(v);
+}
+
+int relu_inplace(float* x, void* shadow, long long n, cudaStream_t st) {
+  if (n <= 0) return CFL_OK;
+  relu_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(shadow), n);
+  return check_launch("relu_inplace");
 }
 
 int mse_gather_fwd(const float* x, const float* bank, const long long* idx, int R, int D, float* loss_out,

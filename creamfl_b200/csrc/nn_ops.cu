@@ -1342,6 +1342,69 @@ int pie_pool_bwd(const void* x, const void* h, const float* w2, const float* att
   return check_launch("pie_pool_bwd");
 }
 
+// ------------------------------------------------------------------------------------------------ global average pool
+// y[n, c] = scale * mean_p x[n, p, c]   (resnet_client.py:177-179: avg_pool then `x * self.scale`), fp32 out
+__global__ void __launch_bounds__(256)
+avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int P, int C, float scale, float* __restrict__ y,
+                   __nv_bfloat16* __restrict__ y16) {
+  const int n = blockIdx.x;
+  const float k = scale / (float)P;
+  for (int c8 = threadIdx.x * 8; c8 < C; c8 += 256 * 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+    for (int p = 0; p < P; ++p) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + ((long long)n * P + p) * C + c8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= k;
+    if (y) store8<float>(y + (long long)n * C + c8, acc);
+    if (y16) *reinterpret_cast<bf16x8*>(y16 + (long long)n * C + c8) = pack8(acc);
+  }
+}
+
+// dx[n, p, c] = scale / P * dy[n, c]
+__global__ void __launch_bounds__(256)
+avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int P, int C, float scale, long long total8,
+                   __nv_bfloat16* __restrict__ dx) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total8) return;
+  const int groups = C >> 3;
+  const int g = (int)(t % groups);
+  const long long n = t / groups / P;
+  float f[8];
+  unpack8(*reinterpret_cast<const bf16x8*>(dy + n * C + g * 8), f);
+  const float k = scale / (float)P;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] *= k;
+  reinterpret_cast<bf16x8*>(dx)[t] = pack8(f);
+}
+
+int avgpool_fwd(const void* x, int N, int P, int C, float scale, float* y, void* y16, cudaStream_t st) {
+  if (N <= 0 || P <= 0 || (C & 7)) {
+    set_error("avgpool_fwd: bad shape");
+    return CFL_EINVAL;
+  }
+  avgpool_fwd_kernel<<<N, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), P, C, scale, y,
+                                        reinterpret_cast<__nv_bfloat16*>(y16));
+  return check_launch("avgpool_fwd");
+}
+
+int avgpool_bwd(const void* dy, int N, int P, int C, float scale, void* dx, cudaStream_t st) {
+  if (N <= 0 || P <= 0 || (C & 7)) {
+    set_error("avgpool_bwd: bad shape");
+    return CFL_EINVAL;
+  }
+  const long long total8 = (long long)N * P * (C >> 3);
+  avgpool_bwd_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), P, C,
+                                                                       scale, total8,
+                                                                       reinterpret_cast<__nv_bfloat16*>(dx));
+  return check_launch("avgpool_bwd");
+}
+
 // ------------------------------------------------------------------------------------------------ misc elementwise
 // y_bf16 = a_bf16 + b_bf16
 __global__ void __launch_bounds__(256)

@@ -370,6 +370,41 @@ def mse_gather_loss(x, bank, idx):
     return _MseGather.apply(x, bank, idx)
 
 
+# --------------------------------------------------------------------------------------------------- cross-entropy
+class _CrossEntropy(torch.autograd.Function):
+    """nn.CrossEntropyLoss()(x - margin * onehot(labels), labels)  (ClientTrainer.py:346-352; labels None -> arange,
+    the class-centre loss on W W^T)."""
+
+    @staticmethod
+    def forward(ctx, x, labels, margin):
+        _need_cuda(x, labels)
+        x32 = x.detach().float()
+        if x32.stride(1) != 1:
+            x32 = x32.contiguous()
+        R, Cn = x32.shape
+        if labels is not None:
+            labels = _contig(labels, torch.int64)
+        rows = torch.empty(R, dtype=torch.float32, device=x.device)
+        dlog = torch.empty((R, Cn), dtype=torch.float32, device=x.device)
+        loss = torch.empty(1, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().creamfl_ce_fwd(_p(x32), x32.stride(0), _p(labels), R, Cn, float(margin), _p(rows),
+                                              _p(dlog), _p(loss), _stream()), "ce_fwd")
+        global _launches
+        _launches += 2
+        ctx.save_for_backward(dlog)
+        ctx.x_dtype = x.dtype
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        (dlog,) = ctx.saved_tensors
+        return (dlog * gout).to(ctx.x_dtype), None, None
+
+
+def cross_entropy(x: torch.Tensor, labels: Optional[torch.Tensor], margin: float = 0.0) -> torch.Tensor:
+    return _CrossEntropy.apply(x, labels, margin)
+
+
 # --------------------------------------------------------------------------------------------------- L2 norm
 class _L2Norm(torch.autograd.Function):
     """F.normalize(x, p=2, dim=-1)  (src/utils/tensor_utils.py:25-27)."""

@@ -244,3 +244,24 @@ def pie_pool_bwd(x, h, w2, attn, d_r, d_pooled, dw2):
     _chk(_lib.load().creamfl_pie_pool_bwd(_p(x), _p(h), _p(w2), _p(attn), _p(d_r), _p(d_pooled), b, p, c, hd, _p(dx),
                                           _p(dpre), _p(dw2), _stream()), "pie_pool_bwd")
     return dx, dpre
+
+
+# --------------------------------------------------------------------------------------------------- unimodal heads
+def avgpool_fwd(x, scale=1.0):
+    """x [N, H, W, C] bf16 -> (fp32 [N, C], bf16 [N, C]) = scale * mean over H*W."""
+    n, h, w, c = x.shape
+    y = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    y16 = torch.empty((n, c), dtype=BF16, device=x.device)
+    _chk(_lib.load().creamfl_avgpool_fwd(_p(x), n, h * w, c, float(scale), _p(y), _p(y16), _stream()), "avgpool_fwd")
+    return y, y16
+
+
+def avgpool_bwd(dy16, shape, scale=1.0):
+    n, h, w, c = shape
+    dx = torch.empty(shape, dtype=BF16, device=dy16.device)
+    _chk(_lib.load().creamfl_avgpool_bwd(_p(dy16), n, h * w, c, float(scale), _p(dx), _stream()), "avgpool_bwd")
+    return dx
+
+
+def relu_inplace(master, shadow):
+    _chk(_lib.load().creamfl_relu_inplace(_p(master), _p(shadow), master.numel(), _stream()), "relu_inplace")

@@ -196,6 +196,17 @@ int creamfl_pie_pool_bwd(const void* x_bf16, const void* h_bf16, const float* w2
                          const void* d_r_bf16, const void* d_pooled_bf16, int B, int P, int C, int Hd, void* dx_bf16,
                          void* dpre_bf16, float* dw2, void* stream);
 
+/* ---- unimodal client heads (src/networks/resnet_client.py:175-201, src/algorithms/ClientTrainer.py:322-363) ------
+ * global average pool of an NHWC map times `scale` ([N, P, C] bf16 -> [N, C] fp32 and/or bf16) and its backward */
+int creamfl_avgpool_fwd(const void* x_bf16, int N, int P, int C, float scale, float* y, void* y_bf16, void* stream);
+int creamfl_avgpool_bwd(const void* dy_bf16, int N, int P, int C, float scale, void* dx_bf16, void* stream);
+/* nn.CrossEntropyLoss()(x - margin * onehot(labels), labels): loss_rows[r] (already / R), dlogits = d(loss)/dx,
+ * loss (optional) = sum of loss_rows.  labels == NULL means labels[r] = r (the class-centre loss on W W^T). */
+int creamfl_ce_fwd(const float* x, int64_t ldx, const int64_t* labels, int R, int C, float margin, float* loss_rows,
+                   float* dlogits, float* loss, void* stream);
+/* in-place ReLU clamp of a parameter and its bf16 shadow (class_fc weights, resnet_client.py:193-197) */
+int creamfl_relu_inplace(float* x, void* shadow_bf16, int64_t n, void* stream);
+
 /* ---- fused optimizer step: global-norm clipping + AdamP / Adam / SGD-momentum + bf16 shadow refresh in four
  * launches for any number of tensors.  Replaces adamp.AdamP.step (third-party adamp==0.3.0, call site
  * src/algorithms/optimizers.py:24-28), clip_grad_norm_ (retrieval_trainer.py:211-214) and torch.optim.SGD

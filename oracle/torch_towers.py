@@ -131,3 +131,48 @@ def fill_deterministic(module: nn.Module, seed: int = 0) -> None:
             else:
                 v = torch.randn(shape, generator=g) * (1.0 / shape[-1]) ** 0.5
             t.copy_(v.to(t.dtype))
+
+
+class RefImageClient(nn.Module):
+    """reference src/networks/resnet_client.py:100-201 (ResNet with BasicBlock [2,2,2,2] = resnet18_client) on
+    torchvision's resnet18 trunk (same graph and parameter names)."""
+
+    def __init__(self, num_class=100, embed_dim=256, scale=128, is_train=True, phase='none'):
+        super().__init__()
+        import torchvision
+        tv = torchvision.models.resnet18(weights=None)
+        self.conv1, self.bn1, self.relu, self.maxpool = tv.conv1, tv.bn1, nn.ReLU(inplace=False), tv.maxpool
+        self.layer1, self.layer2, self.layer3, self.layer4 = tv.layer1, tv.layer2, tv.layer3, tv.layer4
+        self.avg_pool = nn.AdaptiveAvgPool2d((1, 1))
+        self.embed_dim = embed_dim
+        if embed_dim != 512:
+            self.linear = nn.Linear(512, embed_dim)
+        self.class_fc_2 = nn.Linear(embed_dim, num_class)
+        self.class_fc_22 = nn.Linear(embed_dim, 80)
+        self.is_train, self.scale, self.phase = bool(is_train), int(scale), str(phase)
+
+    def forward(self, x):
+        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))            # resnet_client.py:164-167
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        x = self.avg_pool(x).flatten(1) * self.scale                      # :176-179
+        if self.embed_dim != 512:
+            x = self.linear(x)
+        if self.phase == 'extract_conv_feature':
+            return F.normalize(x, p=2, dim=1)                             # :188
+        if self.is_train:
+            w2 = self.relu(self.class_fc_2.weight)                        # :193-197
+            self.class_fc_2.weight.data = w2
+            w22 = self.relu(self.class_fc_22.weight)
+            self.class_fc_22.weight.data = w22
+            return self.class_fc_2(x), self.class_fc_22(x), w2, w22
+        return x
+
+
+def ref_unimodal_supervised_loss(model, inputs, labels, num_class, inter_distance=4.0):
+    """reference src/algorithms/ClientTrainer.py:344-355."""
+    fvec, _, class_weight, _ = model(inputs)
+    onehot = F.one_hot(labels, num_class).to(fvec.dtype)
+    fvec = fvec - inter_distance * onehot
+    loss = F.cross_entropy(fvec, labels)
+    center = F.cross_entropy(class_weight @ class_weight.t(), torch.arange(num_class, device=fvec.device))
+    return 0.5 * center + loss, fvec
