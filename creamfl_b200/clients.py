@@ -141,6 +141,28 @@ class ClientPCME(StoreMixin, nn.Module):
 
 
 # ===================================================================================================== unimodal image client
+def _pad_cols(t: torch.Tensor, mult: int = 8) -> torch.Tensor:
+    """Zero-pad the last dimension to a multiple of `mult` (TMA needs 16-byte row pitches; class counts such as 100
+    or 4 are not multiples of 8).  Head tensors only - a few KB."""
+    c = t.shape[1]
+    cp = (c + mult - 1) // mult * mult
+    if cp == c:
+        return t
+    out = torch.zeros((t.shape[0], cp), dtype=t.dtype, device=t.device)
+    out[:, :c] = t
+    return out
+
+
+def _pad_rows(t: torch.Tensor, mult: int = 8) -> torch.Tensor:
+    r = t.shape[0]
+    rp = (r + mult - 1) // mult * mult
+    if rp == r:
+        return t
+    out = torch.zeros((rp, t.shape[1]), dtype=t.dtype, device=t.device)
+    out[:r] = t
+    return out
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x W^T + b on the tcgen05 GEMM: x fp32/bf16 [R, K] (rounded to bf16), W a ParamStore parameter [N, K],
     y fp32 [R, N].  dW / db accumulate into the flat gradient buffer."""
@@ -157,11 +179,23 @@ class _LinearFn(torch.autograd.Function):
     def backward(ctx, dy):
         (x16,) = ctx.saved_tensors
         w = ctx.weight
-        dy16 = ops.to_bf16(dy.contiguous().float())
-        ops.gemm_bf16(dy16, x16, a_mn=True, b_mn=True, out=grad_target(w), split_k=0, accumulate=True)
+        n = w.shape[0]
+        dy16 = _pad_cols(ops.to_bf16(dy.contiguous().float()))
+        if dy16.shape[1] == n:
+            ops.gemm_bf16(dy16, x16, a_mn=True, b_mn=True, out=grad_target(w), split_k=0, accumulate=True)
+            w16 = w._w16
+        else:                                            # ragged class count: go through padded temporaries
+            gw = ops.gemm_bf16(dy16, x16, a_mn=True, b_mn=True, out_dtype=torch.float32)
+            grad_target(w).add_(gw[:n])
+            w16 = _pad_rows(w._w16)
         if ctx.bias is not None:
-            T.colsum_into(dy16, grad_target(ctx.bias))
-        dx = ops.gemm_bf16(dy16, w._w16, b_mn=True, out_dtype=torch.float32) if ctx.needs_input_grad[0] else None
+            if dy16.shape[1] == n:
+                T.colsum_into(dy16, grad_target(ctx.bias))
+            else:
+                tmp = torch.zeros(dy16.shape[1], dtype=torch.float32, device=dy16.device)
+                T.colsum_into(dy16, tmp)
+                grad_target(ctx.bias).add_(tmp[:n])
+        dx = ops.gemm_bf16(dy16, w16, b_mn=True, out_dtype=torch.float32) if ctx.needs_input_grad[0] else None
         return (dx.to(ctx.x_dtype) if dx is not None else None), None, None
 
 
@@ -176,9 +210,9 @@ class _GramFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dg):
         w = ctx.weight
-        sym = ops.to_bf16((dg + dg.t()).contiguous().float())
+        sym = _pad_cols(ops.to_bf16((dg + dg.t()).contiguous().float()))
         # d/dW of sum(dG * W W^T) = (dG + dG^T) W ; entries the ReLU clamp zeroed carry no gradient (relu'(w) = 0)
-        gw = ops.gemm_bf16(sym, w._w16, b_mn=True, out_dtype=torch.float32)
+        gw = ops.gemm_bf16(sym, _pad_rows(w._w16), b_mn=True, out_dtype=torch.float32)
         grad_target(w).add_(gw * (w.data > 0))
         return None
 
