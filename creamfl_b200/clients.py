@@ -280,3 +280,50 @@ def unimodal_supervised_loss(model: ImageClient, inputs, labels, inter_distance:
     loss = ops.cross_entropy(fvec, labels, inter_distance)
     center = ops.cross_entropy(_GramFn.apply(class_weight), None, 0.0)
     return 0.5 * center + loss, fvec
+
+
+# ===================================================================================================== unimodal text client
+class TextClient(nn.Module):
+    """Mirror of src/networks/language_model.py EncoderText (:28-130): Embedding -> packed bi-GRU -> PIENet ->
+    `* scale` -> ReLU -> classifier heads (training) or L2-normalised embedding.  Runs on torch / cuDNN (SURVEY 8f-f2:
+    the GRU kernel is the next row); the losses on top of it use the creamfl_b200 kernels."""
+
+    def __init__(self, vocab_size=11755, word_dim=300, embed_dim=256, num_class=4, scale=128):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.embed = nn.Embedding(vocab_size, word_dim)
+        self.rnn = nn.GRU(word_dim, embed_dim // 2, bidirectional=True, batch_first=True)
+        self.pie_net = _TorchPIENet(word_dim, embed_dim, word_dim // 2)
+        self.class_fc = nn.Linear(embed_dim, num_class)
+        self.class_fc_2 = nn.Linear(embed_dim, 80)
+        nn.init.xavier_uniform_(self.embed.weight)
+        self.is_train, self.phase, self.scale = True, '', scale
+        self._len_cache = {}
+
+    _length_tensors = GRUEncoderText._length_tensors
+
+    def forward(self, x, lengths):
+        lengths_cpu = lengths.cpu() if torch.is_tensor(lengths) else torch.as_tensor(lengths)
+        wemb_out = self.embed(x)
+        packed = pack_padded_sequence(wemb_out, lengths_cpu, batch_first=True)
+        rnn_out, _ = self.rnn(packed)
+        padded, _ = pad_packed_sequence(rnn_out, batch_first=True, total_length=wemb_out.shape[1])
+        idx, pad_mask = self._length_tensors(lengths_cpu, wemb_out.shape[1], x.device)
+        out = torch.gather(padded, 1, idx).squeeze(1)
+        out, _, _ = self.pie_net(out, wemb_out, pad_mask)
+        out = torch.relu(out * self.scale)                                     # language_model.py:111-112
+        if self.is_train:
+            w1 = torch.relu(self.class_fc.weight)                              # :115-121
+            self.class_fc.weight.data.clamp_(min=0)      # same values as `.data = relu(w)`, address kept (optimizer table)
+            w2 = torch.relu(self.class_fc_2.weight)
+            self.class_fc_2.weight.data.clamp_(min=0)
+            return self.class_fc(out), self.class_fc_2(out), w1, w2
+        return torch.nn.functional.normalize(out, p=2, dim=1)                  # :128
+
+
+def text_supervised_loss(model: TextClient, captions, lengths, labels, inter_distance: float = 4.0):
+    """ClientTrainer.tra supervised pass for the text clients (ClientTrainer.py:335-356)."""
+    fvec, _, class_weight, _ = model(captions, lengths)
+    loss = ops.cross_entropy(fvec, labels, inter_distance)
+    center = ops.cross_entropy(torch.mm(class_weight, class_weight.t()), None, 0.0)
+    return 0.5 * center + loss, fvec

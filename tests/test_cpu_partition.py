@@ -1,0 +1,34 @@
+"""CPU tests: the product's index producers (creamfl_b200/partition.py) are bit-identical to the reference's
+(golden vectors in tests/golden/partition.npz were produced by the reference's own functions)."""
+import numpy as np
+import pytest
+import torch
+
+from creamfl_b200 import partition as P
+from oracle import creamfl_oracle as O
+
+
+@pytest.mark.parametrize('tag', ['synth', 'cifar', 'agnews'])
+def test_hetero_partition_bit_exact(golden, tag):
+    g = golden('partition')
+    n, k, nets, seed = (int(v) for v in g[f'{tag}_args'])
+    name = {'synth': 'synth', 'cifar': 'cifar100', 'agnews': 'AG_NEWS'}[tag]
+    part = P.data_partitioner(name, n, nets, 'hetero', float(g[f'{tag}_alpha']), np.arange(n) % k, seed=seed)
+    assert [len(part[j]) for j in range(nets)] == list(g[f'{tag}_sizes'])
+    assert O.partition_digest(part) == str(g[f'{tag}_sha256'])
+
+
+def test_flickr_shards_bit_exact(golden):
+    g = golden('partition')
+    part = P.shard_partition(145000, 15, 150, seed=2021)
+    assert O.partition_digest(part) == str(g['f30k_sha256'])
+
+
+def test_distill_lookup_matches_dict_semantics():
+    rng = np.random.default_rng(0)
+    distill_index = rng.permutation(5000)[:777].tolist()
+    d = {b: a for a, b in enumerate(distill_index)}                      # MMFL.py:343
+    lut = P.distill_lookup(distill_index)
+    batch = [distill_index[i] for i in (5, 700, 0, 42)]
+    assert lut[torch.tensor(batch)].tolist() == [d[b] for b in batch]
+    assert lut[torch.tensor(batch[:1])].tolist() == [d[batch[0]]]        # batch of one (itemgetter returns a bare int)
