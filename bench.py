@@ -192,6 +192,10 @@ def run_ours(args):
         c_img, c_txt = make_banks(dev, 100 + rank)[2:]        # every client has its own representations
     resident = {k: (v.to(dev) if k != 'cap_lens' else v) for k, v in host.items()}
     phases = args.phases
+    # bf16 copies of the server banks: persistent buffers refreshed in place once per mini-round (captured CUDA
+    # graphs of the client steps reference them by address)
+    g_img16 = torch.empty_like(g_img, dtype=torch.bfloat16)
+    g_txt16 = torch.empty_like(g_txt, dtype=torch.bfloat16)
 
     ktimer = KernelTimer(T, ((B, 14, 14, 256), 256, 3, 1))
     ktimer.install()
@@ -212,7 +216,8 @@ def run_ours(args):
                 fi, ft = server.extract(cur['images'][s], tok(s))
                 g_img.index_copy_(0, cur['d_idx'][s], fi)
                 g_txt.index_copy_(0, cur['d_idx'][s], ft)
-        g_img16, g_txt16 = ops.to_bf16(g_img), ops.to_bf16(g_txt)
+        ops.cast_into(g_img.view(-1), g_img16.view(-1))
+        ops.cast_into(g_txt.view(-1), g_txt16.view(-1))
         if 'C' in phases:
             client.begin_round()
             losses.append(client.private_step(cur['priv_images'], cur['priv_caps'], lens))
@@ -263,10 +268,14 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    ktimer.on = True
     ms_res, launches, out = timed(resident, False, args.steps)
-    ktimer.on = False
     clocks = sampler.stop()
+    # roofline of the dominant convolution shape: one eager (un-graphed) server step with CUDA events recorded on
+    # the launching stream around each of its launches, right after the timed region (same process, warm)
+    ktimer.on = True
+    server._train_step(resident['images'][0], {'input_ids': resident['ids'][0], 'attention_mask': resident['mask'][0]})
+    ktimer.on = False
+    torch.cuda.synchronize()
     step(host, True)
     ms_e2e, _, out_e2e = timed(host, True, args.steps)
     finite = bool(torch.isfinite(out_e2e).all())
