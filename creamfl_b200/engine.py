@@ -78,7 +78,7 @@ class ServerEngine:
                                         no_clip=list(self.criterion.parameters())).attach_stores(self.model)
         self.kd_weight = kd_weight
         self.data_parallel = data_parallel and dist.is_initialized() and dist.get_world_size() > 1
-        self.use_graphs = use_graphs and not self.data_parallel
+        self.use_graphs = use_graphs          # NCCL all-reduce of the flat gradient buffer is captured with the step
 
     def _graphed(self, name, fn, **tensors):
         key = (name, tuple((k, tuple(t.shape)) for k, t in tensors.items()))
