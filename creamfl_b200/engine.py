@@ -78,7 +78,8 @@ class ServerEngine:
                                         no_clip=list(self.criterion.parameters())).attach_stores(self.model)
         self.kd_weight = kd_weight
         self.data_parallel = data_parallel and dist.is_initialized() and dist.get_world_size() > 1
-        self.use_graphs = use_graphs          # NCCL all-reduce of the flat gradient buffer is captured with the step
+        # the data-parallel step stays eager: capturing the NCCL all-reduce inside the step graph deadlocked on 2 GPUs
+        self.use_graphs = use_graphs and not self.data_parallel
 
     def _graphed(self, name, fn, **tensors):
         key = (name, tuple((k, tuple(t.shape)) for k, t in tensors.items()))
