@@ -180,13 +180,14 @@ int creamfl_bn_eval_fwd(const void* x, int64_t P, int C, const float* gamma, con
 }
 
 int creamfl_bn_train_bwd(const void* dy, const void* y, const void* x, int64_t P, int C, const float* gamma,
-                         const float* mean, const float* rstd, double* sums, float* coef, float* dgamma, float* dbeta,
-                         void* dx, void* g_out, void* stream) {
+                         const float* beta, int relu_from_x, const float* mean, const float* rstd, double* sums,
+                         float* coef, float* dgamma, float* dbeta, void* dx, void* g_out, void* stream) {
   if (!dy || !x || !gamma || !mean || !rstd || !sums || !coef || !dx) {
     set_error("bn_train_bwd: null pointer");
     return CFL_EINVAL;
   }
-  return bn_train_bwd(dy, y, x, P, C, gamma, mean, rstd, sums, coef, dgamma, dbeta, dx, g_out, S(stream));
+  return bn_train_bwd(dy, y, x, P, C, gamma, beta, relu_from_x, mean, rstd, sums, coef, dgamma, dbeta, dx, g_out,
+                      S(stream));
 }
 
 int creamfl_maxpool_fwd(const void* x, int N, int H, int W, int C, void* y, void* idx, void* stream) {

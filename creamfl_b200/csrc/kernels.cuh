@@ -64,8 +64,8 @@ int bn_train_fwd(const void*, long long, int, const float*, const float*, float,
                  float*, float*, float*, float*, const void*, int, void*, cudaStream_t);
 int bn_eval_fwd(const void*, long long, int, const float*, const float*, float, const float*, const float*, float*,
                 float*, const void*, int, void*, cudaStream_t);
-int bn_train_bwd(const void*, const void*, const void*, long long, int, const float*, const float*, const float*,
-                 double*, float*, float*, float*, void*, void*, cudaStream_t);
+int bn_train_bwd(const void*, const void*, const void*, long long, int, const float*, const float*, int, const float*,
+                 const float*, double*, float*, float*, float*, void*, void*, cudaStream_t);
 int maxpool_fwd(const void*, int, int, int, int, void*, void*, cudaStream_t);
 int maxpool_bwd(const void*, const void*, int, int, int, int, void*, cudaStream_t);
 int im2col_nhwc(const void*, int, int, int, int, int, int, int, int, int, void*, cudaStream_t);

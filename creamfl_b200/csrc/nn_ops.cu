@@ -192,7 +192,8 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y /* null: no relu */,
                      const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
-                     const float* __restrict__ rstd, long long P, int C, double* __restrict__ sums) {
+                     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     int relu_from_x, long long P, int C, double* __restrict__ sums) {
   extern __shared__ float sh[];
   const int groups = C >> 3;
   const int rows = kBnThreads / groups;
@@ -201,11 +202,13 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.0f;
   if (r < rows) {
-    float mu[8], rs[8];
+    float mu[8], rs[8], ga[8], be[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       mu[i] = mean[g * 8 + i];
       rs[i] = rstd[g * 8 + i];
+      ga[i] = relu_from_x ? gamma[g * 8 + i] : 0.0f;
+      be[i] = relu_from_x ? beta[g * 8 + i] : 0.0f;
     }
     const long long stride = (long long)gridDim.x * rows;
     for (long long p = (long long)blockIdx.x * rows + r; p < P; p += 2 * stride) {
@@ -230,6 +233,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
             unpack8(ry[u], yv);
 #pragma unroll
             for (int i = 0; i < 8; ++i) d[i] = yv[i] > 0.0f ? d[i] : 0.0f;
+          } else if (relu_from_x) {
+            // the ReLU gate recomputed from the BatchNorm input: y = relu(gamma*xhat + beta) > 0 (no residual)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = fmaf((xv[i] - mu[i]) * rs[i], ga[i], be[i]) > 0.0f ? d[i] : 0.0f;
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -258,8 +265,9 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 //   a = gamma*rstd, b = -gamma*rstd^2*S2/P, c0 = -a*S1/P - b*mean     (train mode)
 __global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, long long P, int C, const float* __restrict__ gamma,
                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                       const float* __restrict__ beta /* non-null: also emit the gate affine */,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       float* __restrict__ coef /* [3, C] */) {
+                                       float* __restrict__ coef /* [5, C] */) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double s1 = sums[c], s2 = sums[C + c];
@@ -272,21 +280,30 @@ __global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, long long P, i
   coef[c] = (float)a;
   coef[C + c] = (float)b;
   coef[2 * C + c] = (float)(-a * s1 / (double)P - b * mean[c]);
+  if (beta) {   // affine of the forward output as a function of x: y_pre = gs*x + gb (the ReLU gate of bn_bwd_apply)
+    coef[3 * C + c] = gamma[c] * rstd[c];
+    coef[4 * C + c] = beta[c] - mean[c] * gamma[c] * rstd[c];
+  }
 }
 
 // dx = a*g + b*x + c0 ; optionally g itself is written out (gradient of the residual branch)
 constexpr int kBwdVec = 4;
 __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
-                    const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef, long long total8, int C,
+                    const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef,
+                    const float* __restrict__ gate /* [2, C] affine of the ReLU gate, or null */, long long total8, int C,
                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ g_out) {
   const long long stride = (long long)gridDim.x * kEwThreads;
   const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
-  float ca[8], cb[8], cc[8];
+  float ca[8], cb[8], cc[8], gs[8], gb[8];
   const int c0 = (int)((first * 8) % C);
   load_coef8(coef, c0, ca);
   load_coef8(coef + C, c0, cb);
   load_coef8(coef + 2 * C, c0, cc);
+  if (gate) {
+    load_coef8(gate, c0, gs);
+    load_coef8(gate + C, c0, gb);
+  }
   for (long long t0 = first; t0 < total8; t0 += kBwdVec * stride) {
     bf16x8 rd[kBwdVec], rx[kBwdVec], ry[kBwdVec];
 #pragma unroll
@@ -310,6 +327,9 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
         unpack8(ry[u], yv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[i] = yv[i] > 0.0f ? d[i] : 0.0f;
+      } else if (gate) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = fmaf(xv[i], gs[i], gb[i]) > 0.0f ? d[i] : 0.0f;
       }
       if (g_out) reinterpret_cast<bf16x8*>(g_out)[t] = pack8(d);
       float o[8];
@@ -381,21 +401,23 @@ int bn_eval_fwd(const void* x, long long P, int C, const float* gamma, const flo
 }
 
 int bn_train_bwd(const void* dy, const void* y_or_null, const void* x, long long P, int C, const float* gamma,
-                 const float* mean, const float* rstd, double* sums, float* coef, float* dgamma, float* dbeta,
-                 void* dx, void* g_out, cudaStream_t st) {
+                 const float* beta, int relu_from_x, const float* mean, const float* rstd, double* sums, float* coef,
+                 float* dgamma, float* dbeta, void* dx, void* g_out, cudaStream_t st) {
   int rc = bn_check("bn_train_bwd", P, C);
   if (rc) return rc;
+  const int gate_from_x = (relu_from_x && y_or_null == nullptr && beta != nullptr) ? 1 : 0;
   const int rows = kBnThreads / (C >> 3);
   const size_t smem = (size_t)(rows > 0 ? rows : 1) * 2 * C * sizeof(float);
   bn_bwd_reduce_kernel<<<bn_reduce_grid(P, C), kBnThreads, smem, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_or_null),
-      reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, P, C, sums);
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, mean, rstd, dgamma, dbeta, coef);
+      reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, gamma, beta, gate_from_x, P, C, sums);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, mean, rstd, gate_from_x ? beta : nullptr,
+                                                          dgamma, dbeta, coef);
   const long long total8 = P * C / 8;
   bn_bwd_apply_kernel<<<ew_grid(total8, kBwdVec), kEwThreads, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_or_null),
-      reinterpret_cast<const __nv_bfloat16*>(x), coef, total8, C, reinterpret_cast<__nv_bfloat16*>(dx),
-      reinterpret_cast<__nv_bfloat16*>(g_out));
+      reinterpret_cast<const __nv_bfloat16*>(x), coef, gate_from_x ? coef + 3 * C : nullptr, total8, C,
+      reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(g_out));
   return check_launch("bn_train_bwd");
 }
 

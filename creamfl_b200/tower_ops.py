@@ -102,7 +102,7 @@ class BNScratch:
         self.sums = torch.zeros(2 * c, dtype=torch.float64, device=device)
         self.scale = torch.empty(c, dtype=torch.float32, device=device)
         self.shift = torch.empty(c, dtype=torch.float32, device=device)
-        self.coef = torch.empty(3 * c, dtype=torch.float32, device=device)
+        self.coef = torch.empty(5 * c, dtype=torch.float32, device=device)
 
 
 def bn_train_fwd(x, gamma, beta, running_mean, running_var, sc: BNScratch, eps, momentum, res=None, relu=True):
@@ -127,14 +127,17 @@ def bn_eval_fwd(x, gamma, beta, running_mean, running_var, sc: BNScratch, eps, r
     return y
 
 
-def bn_train_bwd(dy, y_mask, x, gamma, mean, rstd, sc: BNScratch, dgamma, dbeta, want_g=False):
-    """Returns (dx, g) where g = dy * (y_mask > 0) (only if want_g)."""
+def bn_train_bwd(dy, y_mask, x, gamma, mean, rstd, sc: BNScratch, dgamma, dbeta, want_g=False, beta=None,
+                 relu_from_x=False):
+    """Returns (dx, g) where g = dy * gate (only if want_g).  gate = (y_mask > 0) if y_mask is given; recomputed from
+    x (no residual, ReLU applied) if relu_from_x and beta are given; 1 otherwise."""
     c = x.shape[-1]
     p = x.numel() // c
     dx = torch.empty_like(x)
     g = torch.empty_like(x) if want_g else None
-    _chk(_lib.load().creamfl_bn_train_bwd(_p(dy), _p(y_mask), _p(x), p, c, _p(gamma), _p(mean), _p(rstd), _p(sc.sums),
-                                          _p(sc.coef), _p(dgamma), _p(dbeta), _p(dx), _p(g), _stream()),
+    _chk(_lib.load().creamfl_bn_train_bwd(_p(dy), _p(y_mask), _p(x), p, c, _p(gamma), _p(beta), int(relu_from_x),
+                                          _p(mean), _p(rstd), _p(sc.sums), _p(sc.coef), _p(dgamma), _p(dbeta), _p(dx),
+                                          _p(g), _stream()),
          "bn_train_bwd", 3)
     return dx, g
 

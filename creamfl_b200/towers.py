@@ -213,12 +213,14 @@ class BN(nn.Module):
         return T.bn_eval_fwd(x, self.weight, self.bias, self.running_mean, self.running_var, self.scratch(), self.eps,
                              res=res, relu=relu), None
 
-    def bwd(self, dy, y_mask, x, saved, want_g=False):
+    def bwd(self, dy, y_mask, x, saved, want_g=False, relu_from_x=False):
+        """`y_mask`: the forward output when a residual was added before the ReLU; `relu_from_x`: ReLU without
+        residual - the gate is recomputed from x inside the kernels and the output is not read."""
         if saved is None:
             raise RuntimeError('BatchNorm backward needs a training-mode forward (batch statistics)')
         mean, rstd = saved
         return T.bn_train_bwd(dy, y_mask, x, self.weight, mean, rstd, self.scratch(), grad_target(self.weight),
-                              grad_target(self.bias), want_g=want_g)
+                              grad_target(self.bias), want_g=want_g, beta=self.bias, relu_from_x=relu_from_x)
 
 
 def _conv_f(c: Conv, x):
@@ -268,9 +270,9 @@ class Bottleneck(nn.Module):
         x, o1, a1, s1, o2, a2, s2, o3, s3, od, sd, y = saved
         do3, g = self.bn3.bwd(dy, y, o3, s3, want_g=True)
         da2 = _conv_b(self.conv3, do3, a2)
-        do2, _ = self.bn2.bwd(da2, a2, o2, s2)
+        do2, _ = self.bn2.bwd(da2, None, o2, s2, relu_from_x=True)
         da1 = _conv_b(self.conv2, do2, a1)
-        do1, _ = self.bn1.bwd(da1, a1, o1, s1)
+        do1, _ = self.bn1.bwd(da1, None, o1, s1, relu_from_x=True)
         if self.downsample is not None:
             dod, _ = self.downsample[1].bwd(g, None, od, sd)
             dxd = _conv_b(self.downsample[0], dod, x)
@@ -311,7 +313,7 @@ class BasicBlock(nn.Module):
         x, o1, a1, s1, o2, s2, od, sd, y = saved
         do2, g = self.bn2.bwd(dy, y, o2, s2, want_g=True)
         da1 = _conv_b(self.conv2, do2, a1)
-        do1, _ = self.bn1.bwd(da1, a1, o1, s1)
+        do1, _ = self.bn1.bwd(da1, None, o1, s1, relu_from_x=True)
         if self.downsample is not None:
             dod, _ = self.downsample[1].bwd(g, None, od, sd)
             dxd = _conv_b(self.downsample[0], dod, x)
@@ -362,7 +364,7 @@ class _StemFn(torch.autograd.Function):
         images, o, a, s, idx = ctx.saved
         ctx.saved = None
         da = T.maxpool_bwd(dy.contiguous(), idx, a.shape)
-        do, _ = net.bn1.bwd(da, a, o, s)
+        do, _ = net.bn1.bwd(da, None, o, s, relu_from_x=True)
         w16 = net.stem_shadow()
         col = T.im2col_images(images, 7, 7, 2, 3, w16.shape[1])
         g = grad_target(net.conv1.weight)                         # [64, 147] fp32

@@ -152,11 +152,14 @@ int creamfl_bn_train_fwd(const void* x_bf16, int64_t P, int C, const float* gamm
 int creamfl_bn_eval_fwd(const void* x_bf16, int64_t P, int C, const float* gamma, const float* beta, float eps,
                         const float* running_mean, const float* running_var, float* scale, float* shift,
                         const void* res_bf16, int relu, void* y_bf16, void* stream);
-/* g = dy * (y > 0) if y_bf16 != null else dy;  dgamma += sum g*xhat, dbeta += sum g;  dx = BN'(g);
- * g_out (optional) receives g (gradient of the residual branch).  coef: 3*C floats scratch. */
+/* g = dy * gate;  dgamma += sum g*xhat, dbeta += sum g;  dx = BN'(g).  The ReLU gate is (y > 0) when y_bf16 is
+ * given (needed when a residual was added before the ReLU), (gamma*xhat + beta > 0) recomputed from x when y_bf16 is
+ * null and relu_from_x != 0 (saves reading y), and 1 otherwise.  g_out (optional) receives g (gradient of the
+ * residual branch).  coef: 5*C floats scratch. */
 int creamfl_bn_train_bwd(const void* dy_bf16, const void* y_bf16, const void* x_bf16, int64_t P, int C,
-                         const float* gamma, const float* mean, const float* rstd, double* sums, float* coef,
-                         float* dgamma, float* dbeta, void* dx_bf16, void* g_out_bf16, void* stream);
+                         const float* gamma, const float* beta, int relu_from_x, const float* mean, const float* rstd,
+                         double* sums, float* coef, float* dgamma, float* dbeta, void* dx_bf16, void* g_out_bf16,
+                         void* stream);
 
 /* ---- 3x3 / stride 2 / pad 1 max pooling (ResNet stem); idx: one byte per output element */
 int creamfl_maxpool_fwd(const void* x_bf16, int N, int H, int W, int C, void* y_bf16, void* idx_u8, void* stream);

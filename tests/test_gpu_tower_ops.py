@@ -117,6 +117,11 @@ def test_batchnorm_train(T, shape, relu, with_res):
     dg, db = torch.full((c,), 0.25, device='cuda'), torch.full((c,), 0.25, device='cuda')
     dx, gout = T.bn_train_bwd(dy.cuda(), y if relu else None, x.cuda(), gamma.cuda(), mean, rstd, sc, dg, db,
                               want_g=True)
+    if relu and not with_res:      # gate recomputed from x instead of read from y: same result up to sign ties at 0
+        dg2, db2 = torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
+        dx2, _ = T.bn_train_bwd(dy.cuda(), None, x.cuda(), gamma.cuda(), mean, rstd, sc, dg2, db2, beta=beta.cuda(),
+                                relu_from_x=True)
+        assert rel_l2(dx2, dx) < 2e-3 and rel_l2(dg2, dg - 0.25) < 2e-3
     assert rel_l2(dx, x64.grad.permute(0, 2, 3, 1)) < 6e-3
     assert rel_l2(dg - 0.25, g64.grad) < 1e-3 and rel_l2(db - 0.25, b64.grad) < 1e-3
     assert rel_l2(gout, dy.double() * (mask.permute(0, 2, 3, 1) if relu else 1.0)) < 1e-6
