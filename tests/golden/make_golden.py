@@ -394,7 +394,69 @@ def case_partition():
     np.savez_compressed(OUT / 'partition.npz', **out)
 
 
-CASES = {'pcme': case_pcme, 'mm_contrast': case_mm_contrast, 'uni_contrast': case_uni_contrast,
+def case_towers():
+    """The reference's own PCME (ResNet18 + BERT glue, pcme.py / image_encoder.py / pie_model.py) and resnet18_client
+    (resnet_client.py) on deterministic weights: pins oracle/torch_towers.py (the restatement the CUDA towers are
+    tested against).  torchvision / transformers are the versions in this image (the reference pins older ones)."""
+    import torchvision
+    from transformers import BertConfig, BertModel
+    import importlib.util          # by path: /root/repo must not join sys.path (its `src` package would shadow the reference's)
+    spec = importlib.util.spec_from_file_location('oracle_torch_towers', OUT.parent.parent / 'oracle' / 'torch_towers.py')
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    fill_deterministic = mod.fill_deterministic
+    orig18 = torchvision.models.resnet18
+    torchvision.models.resnet18 = lambda pretrained=True, **k: orig18(weights=None)
+    import src.networks.models.pcme as ref_pcme
+    cfg = BertConfig(num_hidden_layers=2)
+
+    class FakeTokenizer:
+        """Captions are strings of space-separated ids; pads with 0 like BertTokenizer(padding=True)."""
+
+        def __call__(self, captions, padding=True, return_tensors='pt'):
+            rows = [[int(t) for t in c.split()] for c in captions]
+            width = max(len(r) for r in rows)
+            ids = torch.tensor([r + [0] * (width - len(r)) for r in rows])
+            mask = torch.tensor([[1] * len(r) + [0] * (width - len(r)) for r in rows])
+            return {'input_ids': ids, 'token_type_ids': torch.zeros_like(ids), 'attention_mask': mask}
+
+    ref_pcme.BertModel.from_pretrained = staticmethod(lambda name: BertModel(cfg))
+    ref_pcme.BertTokenizer.from_pretrained = staticmethod(lambda name: FakeTokenizer())
+    model = ref_pcme.PCME(None, Munch(embed_dim=64, cnn_type='resnet18', not_bert=False, n_samples_inference=0), False)
+    fill_deterministic(model, seed=31)
+    g = torch.Generator().manual_seed(32)
+    images = torch.randn(2, 3, 224, 224, generator=g)
+    ids = torch.randint(1000, 30000, (2, 8), generator=g)
+    ids[:, 0] = 101
+    captions = (' '.join(str(int(t)) for t in ids[0]), ' '.join(str(int(t)) for t in ids[1][:5]))
+    model.eval()
+    with torch.no_grad():
+        o = model(images, None, captions, None)
+    model.img_enc.train()
+    with torch.no_grad():
+        tr = model.img_enc(images)['embedding']
+    out = {'images': images.numpy(), 'ids': ids.numpy(), 'len1': np.int64(5),
+           'eval_image_features': o['image_features'].numpy(), 'eval_caption_features': o['caption_features'].numpy(),
+           'train_image_embedding': tr.numpy(), 'none_keys': np.array(sorted(k for k, v in o.items() if v is None))}
+    # unimodal image client
+    import src.networks.resnet_client as rc
+    rc.model_zoo.load_url = lambda url: {}
+    client = rc.resnet18_client(pretrained=False, num_class=10, is_train=True, scale=128, embed_dim=64)
+    fill_deterministic(client, seed=33)
+    with torch.no_grad():
+        client.linear.weight.mul_(0.05)
+    small = torch.randn(4, 3, 64, 64, generator=g)
+    client.train()
+    x1, x2, w1, w2 = client(small)
+    client.phase, client.is_train = 'extract_conv_feature', False
+    with torch.no_grad():
+        emb = client(small)
+    out.update({'client_images': small.numpy(), 'client_x1': x1.detach().numpy(), 'client_w_min': np.float64(w1.min().item()),
+                'client_embedding': emb.numpy()})
+    np.savez_compressed(OUT / 'towers.npz', **out)
+
+
+CASES = {'towers': case_towers, 'pcme': case_pcme, 'mm_contrast': case_mm_contrast, 'uni_contrast': case_uni_contrast,
          'recall': case_recall, 'partition': case_partition, 'conw': case_conw}
 
 if __name__ == '__main__':

@@ -164,3 +164,41 @@ def test_conw_full_size_against_reference(golden):
     np.testing.assert_allclose(agg_t.numpy()[rows], g['txt_rows'], rtol=2e-5, atol=2e-7)
     assert agg_i.double().abs().sum().item() == pytest.approx(float(g['img_abs_sum']), rel=1e-6)
     assert agg_t.double().abs().sum().item() == pytest.approx(float(g['txt_abs_sum']), rel=1e-6)
+
+
+def test_tower_restatement_matches_reference_modules(golden):
+    """oracle/torch_towers.py against the reference's own PCME / EncoderImage / PIENet / resnet18_client (executed by
+    tests/golden/make_golden.py::case_towers on the same deterministic weights): fp32, rel 1e-5."""
+    from transformers import BertConfig
+    from oracle import torch_towers as RT
+    g = golden('towers')
+    model = RT.RefPCME('resnet18', 64, BertConfig(num_hidden_layers=2))
+    RT.fill_deterministic(model, seed=31)
+    images, ids = T(g['images']), T(g['ids'])
+    mask = torch.ones_like(ids)
+    mask[1, int(g['len1']):] = 0
+    model.eval()
+    with torch.no_grad():
+        o = model(images, ids * mask, mask, torch.zeros_like(ids))
+    np.testing.assert_allclose(o['image_features'].numpy(), g['eval_image_features'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(o['caption_features'].numpy(), g['eval_caption_features'], rtol=1e-4, atol=1e-6)
+    model.img_enc.train()
+    with torch.no_grad():
+        tr = model.img_enc(images)['embedding']
+    np.testing.assert_allclose(tr.numpy(), g['train_image_embedding'], rtol=1e-4, atol=1e-6)
+    assert list(g['none_keys']) == sorted(['image_attentions', 'image_residuals', 'image_logsigma', 'image_logsigma_att',
+                                           'caption_attentions', 'caption_residuals', 'caption_logsigma',
+                                           'caption_logsigma_att'])
+    client = RT.RefImageClient(num_class=10, embed_dim=64)
+    RT.fill_deterministic(client, seed=33)
+    with torch.no_grad():
+        client.linear.weight.mul_(0.05)
+    small = T(g['client_images'])
+    client.train()
+    x1, _, w1, _ = client(small)
+    np.testing.assert_allclose(x1.detach().numpy(), g['client_x1'], rtol=1e-4, atol=1e-5)
+    assert float(w1.min()) == float(g['client_w_min']) == 0.0
+    client.phase, client.is_train = 'extract_conv_feature', False
+    with torch.no_grad():
+        emb = client(small)
+    np.testing.assert_allclose(emb.numpy(), g['client_embedding'], rtol=1e-4, atol=1e-6)
