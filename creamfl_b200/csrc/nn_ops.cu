@@ -1030,75 +1030,139 @@ int embed_bwd(const long long* ids, const long long* tt, const void* dh, int T, 
 // ------------------------------------------------------------------------------------------------ BERT attention
 // qkv [B*L, 3*H*64] bf16 (Q | K | V blocks of H*64 columns), mask [B, L] (1 = attend), ctx [B*L, H*64] bf16,
 // probs [B, H, L, L] bf16 kept for the backward.  One CTA of 128 threads per (sequence, head); L <= 64.
+// Captions are 12-40 tokens: a 32x32x64 problem per head is far below a tcgen05 tile (and 0.7 % of BERT's FLOPs), so
+// the contractions run on the FMA pipes out of shared memory with 4x4 register tiles and 16-byte shared loads
+// (0.125 LDS.128 per FMA).
 constexpr int kAttD = 64;
 constexpr int kAttMaxL = 64;
+constexpr int kAttPitch = kAttD + 4;   // floats; keeps float4 alignment, rows land on distinct bank groups
+
+// acc[a][b] += sum_k A[i0+a][k] * B[j0+b][k]   (both row-major with pitch kAttPitch, k in [0, 64))
+__device__ __forceinline__ void tile_nt(const float* __restrict__ A, const float* __restrict__ B, int i0, int j0,
+                                        float (&acc)[4][4]) {
+#pragma unroll 4
+  for (int k = 0; k < kAttD; k += 4) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      a[r] = *reinterpret_cast<const float4*>(A + (i0 + r) * kAttPitch + k);
+      b[r] = *reinterpret_cast<const float4*>(B + (j0 + r) * kAttPitch + k);
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y)
+        acc[x][y] += a[x].x * b[y].x + a[x].y * b[y].y + a[x].z * b[y].z + a[x].w * b[y].w;
+  }
+}
+
+// acc[a][b] += sum_j P[i0+a][j] * V[j][d0+b]   (P pitch lp, V pitch kAttPitch, j in [0, Lp))
+__device__ __forceinline__ void tile_nn(const float* __restrict__ P, int lp, const float* __restrict__ V, int Lp, int i0,
+                                        int d0, float (&acc)[4][4]) {
+  for (int j = 0; j < Lp; j += 4) {
+    float4 pr[4], v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      pr[r] = *reinterpret_cast<const float4*>(P + (i0 + r) * lp + j);
+      v[r] = *reinterpret_cast<const float4*>(V + (j + r) * kAttPitch + d0);
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      acc[x][0] += pr[x].x * v[0].x + pr[x].y * v[1].x + pr[x].z * v[2].x + pr[x].w * v[3].x;
+      acc[x][1] += pr[x].x * v[0].y + pr[x].y * v[1].y + pr[x].z * v[2].y + pr[x].w * v[3].y;
+      acc[x][2] += pr[x].x * v[0].z + pr[x].y * v[1].z + pr[x].z * v[2].z + pr[x].w * v[3].z;
+      acc[x][3] += pr[x].x * v[0].w + pr[x].y * v[1].w + pr[x].z * v[2].w + pr[x].w * v[3].w;
+    }
+  }
+}
+
+// rows [0, L) of a [L, 64] bf16 slice (row pitch ld) -> fp32 smem [Lp][kAttPitch]; rows [L, Lp) zero
+__device__ __forceinline__ void load_rows(const __nv_bfloat16* __restrict__ src, long long ld, int L, int Lp,
+                                          float* __restrict__ dst) {
+  for (int e = threadIdx.x; e < Lp * (kAttD / 8); e += blockDim.x) {
+    const int r = e / (kAttD / 8), k = (e % (kAttD / 8)) * 8;
+    float f[8];
+    if (r < L) {
+      unpack8(*reinterpret_cast<const bf16x8*>(src + (long long)r * ld + k), f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = 0.0f;
+    }
+    *reinterpret_cast<float4*>(dst + r * kAttPitch + k) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(dst + r * kAttPitch + k + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  }
+}
 
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ mask, int L, int H, float scale,
                 __nv_bfloat16* __restrict__ ctx, __nv_bfloat16* __restrict__ probs) {
-  extern __shared__ float att_sm[];
-  typedef float (*RowD)[kAttD + 1];
-  typedef float (*RowL)[kAttMaxL + 1];
-  RowD sq = reinterpret_cast<RowD>(att_sm);
-  RowD sk = sq + L;
-  RowD sv = sk + L;
-  RowL sp = reinterpret_cast<RowL>(sv + L);
+  extern __shared__ __align__(16) float att_sm[];
+  const int Lp = (L + 3) & ~3;
+  const int lp = Lp + 4;
+  float* sq = att_sm;
+  float* sk = sq + Lp * kAttPitch;
+  float* sv = sk + Lp * kAttPitch;
+  float* sp = sv + Lp * kAttPitch;          // [Lp][lp]
   const int b = blockIdx.x / H, h = blockIdx.x % H;
-  const int ld = 3 * H * kAttD;
+  const long long ld = 3LL * H * kAttD;
   const __nv_bfloat16* base = qkv + (long long)b * L * ld + h * kAttD;
-  for (int e = threadIdx.x; e < L * (kAttD / 8); e += blockDim.x) {
-    const int r = e / (kAttD / 8), k = (e % (kAttD / 8)) * 8;
-    float f[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)r * ld + k), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sq[r][k + i] = f[i];
-    unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)r * ld + H * kAttD + k), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sk[r][k + i] = f[i];
-    unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)r * ld + 2 * H * kAttD + k), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sv[r][k + i] = f[i];
-  }
+  load_rows(base, ld, L, Lp, sq);
+  load_rows(base + H * kAttD, ld, L, Lp, sk);
+  load_rows(base + 2 * H * kAttD, ld, L, Lp, sv);
   __syncthreads();
-  for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
-    const int i = e / L, j = e % L;
-    float acc = 0.0f;
-#pragma unroll 16
-    for (int k = 0; k < kAttD; ++k) acc = fmaf(sq[i][k], sk[j][k], acc);
-    // HF extended attention mask: (1 - mask) * finfo.min added to the scores
-    sp[i][j] = acc * scale + (mask[b * L + j] > 0.5f ? 0.0f : -3.0e38f);
+  const int tiles = Lp / 4;
+  for (int t = threadIdx.x; t < tiles * tiles; t += blockDim.x) {
+    const int i0 = (t / tiles) * 4, j0 = (t % tiles) * 4;
+    float acc[4][4] = {};
+    tile_nt(sq, sk, i0, j0, acc);
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) {
+        const int j = j0 + y;
+        // HF extended attention mask: (1 - mask) * finfo.min added to the scores; padded key columns get -inf
+        const float m = (j < L) ? (mask[b * L + j] > 0.5f ? 0.0f : -3.0e38f) : -INFINITY;
+        sp[(i0 + x) * lp + j] = acc[x][y] * scale + m;
+      }
   }
   __syncthreads();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = w; i < L; i += 4) {
+  for (int i = w; i < Lp; i += 4) {
+    if (i >= L) {
+      for (int j = lane; j < Lp; j += 32) sp[i * lp + j] = 0.0f;
+      continue;
+    }
     float m = -INFINITY;
-    for (int j = lane; j < L; j += 32) m = fmaxf(m, sp[i][j]);
+    for (int j = lane; j < Lp; j += 32) m = fmaxf(m, sp[i * lp + j]);
     m = warp_max_f(m);
     float s = 0.0f;
-    for (int j = lane; j < L; j += 32) {
-      const float e = __expf(sp[i][j] - m);
-      sp[i][j] = e;
+    for (int j = lane; j < Lp; j += 32) {
+      const float e = __expf(sp[i * lp + j] - m);
+      sp[i * lp + j] = e;
       s += e;
     }
     s = warp_sum_f(s);
     const float inv = 1.0f / s;
-    for (int j = lane; j < L; j += 32) {
+    for (int j = lane; j < Lp; j += 32) {
       // round to bf16 once: forward PV product and the backward use the very same probabilities
-      const __nv_bfloat16 pb = __float2bfloat16(sp[i][j] * inv);
-      sp[i][j] = __bfloat162float(pb);
-      probs[(((long long)b * H + h) * L + i) * L + j] = pb;
+      const __nv_bfloat16 pb = __float2bfloat16(sp[i * lp + j] * inv);
+      sp[i * lp + j] = __bfloat162float(pb);
+      if (j < L) probs[(((long long)b * H + h) * L + i) * L + j] = pb;
     }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < L * (kAttD / 2); e += blockDim.x) {
-    const int i = e / (kAttD / 2), k = (e % (kAttD / 2)) * 2;
-    float a0 = 0.0f, a1 = 0.0f;
-    for (int j = 0; j < L; ++j) {
-      a0 = fmaf(sp[i][j], sv[j][k], a0);
-      a1 = fmaf(sp[i][j], sv[j][k + 1], a1);
+  for (int t = threadIdx.x; t < tiles * (kAttD / 4); t += blockDim.x) {
+    const int i0 = (t / (kAttD / 4)) * 4, d0 = (t % (kAttD / 4)) * 4;
+    float acc[4][4] = {};
+    tile_nn(sp, lp, sv, Lp, i0, d0, acc);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      if (i0 + x < L) {
+        __nv_bfloat16* o = ctx + ((long long)b * L + i0 + x) * (H * kAttD) + h * kAttD + d0;
+        *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(acc[x][0], acc[x][1]);
+        *reinterpret_cast<__nv_bfloat162*>(o + 2) = __floats2bfloat162_rn(acc[x][2], acc[x][3]);
+      }
     }
-    *reinterpret_cast<__nv_bfloat162*>(ctx + ((long long)b * L + i) * (H * kAttD) + h * kAttD + k) =
-        __floats2bfloat162_rn(a0, a1);
   }
 }
 
@@ -1106,71 +1170,80 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__
 __global__ void __launch_bounds__(128)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ probs,
                 const __nv_bfloat16* __restrict__ dctx, int L, int H, float scale, __nv_bfloat16* __restrict__ dqkv) {
-  extern __shared__ float att_sm[];
-  typedef float (*RowD)[kAttD + 1];
-  typedef float (*RowL)[kAttMaxL + 1];
-  RowD sq = reinterpret_cast<RowD>(att_sm);
-  RowD sk = sq + L;
-  RowD sv = sk + L;
-  RowD sdo = sv + L;
-  RowL sp = reinterpret_cast<RowL>(sdo + L);
-  RowL sds = sp + L;
+  extern __shared__ __align__(16) float att_sm[];
+  const int Lp = (L + 3) & ~3;
+  const int lp = Lp + 4;
+  float* sq = att_sm;
+  float* sk = sq + Lp * kAttPitch;
+  float* sv = sk + Lp * kAttPitch;
+  float* sdo = sv + Lp * kAttPitch;
+  float* sp = sdo + Lp * kAttPitch;     // P      [Lp][lp]
+  float* spt = sp + Lp * lp;            // P^T
+  float* sds = spt + Lp * lp;           // dS
+  float* sdst = sds + Lp * lp;          // dS^T
   const int b = blockIdx.x / H, h = blockIdx.x % H;
-  const int ld = 3 * H * kAttD;
+  const long long ld = 3LL * H * kAttD;
   const __nv_bfloat16* base = qkv + (long long)b * L * ld + h * kAttD;
-  for (int e = threadIdx.x; e < L * (kAttD / 8); e += blockDim.x) {
-    const int r = e / (kAttD / 8), k = (e % (kAttD / 8)) * 8;
-    float f[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)r * ld + k), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sq[r][k + i] = f[i];
-    unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)r * ld + H * kAttD + k), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sk[r][k + i] = f[i];
-    unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)r * ld + 2 * H * kAttD + k), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sv[r][k + i] = f[i];
-    unpack8(*reinterpret_cast<const bf16x8*>(dctx + ((long long)b * L + r) * (H * kAttD) + h * kAttD + k), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sdo[r][k + i] = f[i];
+  load_rows(base, ld, L, Lp, sq);
+  load_rows(base + H * kAttD, ld, L, Lp, sk);
+  load_rows(base + 2 * H * kAttD, ld, L, Lp, sv);
+  load_rows(dctx + (long long)b * L * (H * kAttD) + h * kAttD, (long long)H * kAttD, L, Lp, sdo);
+  for (int e = threadIdx.x; e < Lp * Lp; e += blockDim.x) {
+    const int i = e / Lp, j = e % Lp;
+    const float pv = (i < L && j < L) ? __bfloat162float(probs[((long long)b * H + h) * L * L + i * L + j]) : 0.0f;
+    sp[i * lp + j] = pv;
+    spt[j * lp + i] = pv;
   }
-  for (int e = threadIdx.x; e < L * L; e += blockDim.x)
-    sp[e / L][e % L] = __bfloat162float(probs[((long long)b * H + h) * L * L + e]);
   __syncthreads();
+  const int tiles = Lp / 4;
   // dP = dO V^T
-  for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
-    const int i = e / L, j = e % L;
-    float acc = 0.0f;
-#pragma unroll 16
-    for (int k = 0; k < kAttD; ++k) acc = fmaf(sdo[i][k], sv[j][k], acc);
-    sds[i][j] = acc;
+  for (int t = threadIdx.x; t < tiles * tiles; t += blockDim.x) {
+    const int i0 = (t / tiles) * 4, j0 = (t % tiles) * 4;
+    float acc[4][4] = {};
+    tile_nt(sdo, sv, i0, j0, acc);
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) sds[(i0 + x) * lp + j0 + y] = acc[x][y];
   }
   __syncthreads();
   // dS = P * (dP - rowsum(dP * P)) * scale
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = w; i < L; i += 4) {
+  for (int i = w; i < Lp; i += 4) {
     float s = 0.0f;
-    for (int j = lane; j < L; j += 32) s = fmaf(sds[i][j], sp[i][j], s);
+    for (int j = lane; j < Lp; j += 32) s = fmaf(sds[i * lp + j], sp[i * lp + j], s);
     s = warp_sum_f(s);
-    for (int j = lane; j < L; j += 32) sds[i][j] = sp[i][j] * (sds[i][j] - s) * scale;
+    for (int j = lane; j < Lp; j += 32) {
+      const float v = sp[i * lp + j] * (sds[i * lp + j] - s) * scale;
+      sds[i * lp + j] = v;
+      sdst[j * lp + i] = v;
+    }
   }
   __syncthreads();
   __nv_bfloat16* obase = dqkv + (long long)b * L * ld + h * kAttD;
-  for (int e = threadIdx.x; e < L * (kAttD / 2); e += blockDim.x) {
-    const int i = e / (kAttD / 2), k = (e % (kAttD / 2)) * 2;
-    float q0 = 0.f, q1 = 0.f, k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
-    for (int j = 0; j < L; ++j) {
-      q0 = fmaf(sds[i][j], sk[j][k], q0);
-      q1 = fmaf(sds[i][j], sk[j][k + 1], q1);
-      k0 = fmaf(sds[j][i], sq[j][k], k0);
-      k1 = fmaf(sds[j][i], sq[j][k + 1], k1);
-      v0 = fmaf(sp[j][i], sdo[j][k], v0);
-      v1 = fmaf(sp[j][i], sdo[j][k + 1], v1);
+  // dQ = dS K ; dK = dS^T Q ; dV = P^T dO     (three [L, 64] outputs, 4x4 tiles each)
+  for (int t = threadIdx.x; t < 3 * tiles * (kAttD / 4); t += blockDim.x) {
+    const int which = t / (tiles * (kAttD / 4));
+    const int u = t % (tiles * (kAttD / 4));
+    const int i0 = (u / (kAttD / 4)) * 4, d0 = (u % (kAttD / 4)) * 4;
+    float acc[4][4] = {};
+    if (which == 0) tile_nn(sds, lp, sk, Lp, i0, d0, acc);
+    else if (which == 1) tile_nn(sdst, lp, sq, Lp, i0, d0, acc);
+    else tile_nn(spt, lp, sdo, Lp, i0, d0, acc);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      if (i0 + x < L) {
+        __nv_bfloat16* o = obase + (long long)(i0 + x) * ld + which * H * kAttD + d0;
+        *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(acc[x][0], acc[x][1]);
+        *reinterpret_cast<__nv_bfloat162*>(o + 2) = __floats2bfloat162_rn(acc[x][2], acc[x][3]);
+      }
     }
-    *reinterpret_cast<__nv_bfloat162*>(obase + (long long)i * ld + k) = __floats2bfloat162_rn(q0, q1);
-    *reinterpret_cast<__nv_bfloat162*>(obase + (long long)i * ld + H * kAttD + k) = __floats2bfloat162_rn(k0, k1);
-    *reinterpret_cast<__nv_bfloat162*>(obase + (long long)i * ld + 2 * H * kAttD + k) = __floats2bfloat162_rn(v0, v1);
   }
+}
+
+static size_t attn_smem(int L, int mats, int sq_mats) {
+  const int Lp = (L + 3) & ~3;
+  return (size_t)(mats * Lp * kAttPitch + sq_mats * Lp * (Lp + 4)) * sizeof(float);
 }
 
 int attn_fwd(const void* qkv, const float* mask, int B, int L, int H, int dh, void* ctx, void* probs, cudaStream_t st) {
@@ -1180,13 +1253,12 @@ int attn_fwd(const void* qkv, const float* mask, int B, int L, int H, int dh, vo
   }
   static bool set = false;
   if (!set) {
-    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)((3 * kAttMaxL * (kAttD + 1) + kAttMaxL * (kAttMaxL + 1)) * sizeof(float)));
+    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(kAttMaxL, 3, 1));
     set = true;
   }
-  const size_t smem = (size_t)(3 * L * (kAttD + 1) + L * (kAttMaxL + 1)) * sizeof(float);
-  attn_fwd_kernel<<<B * H, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), mask, L, H, 0.125f,
-                                         reinterpret_cast<__nv_bfloat16*>(ctx), reinterpret_cast<__nv_bfloat16*>(probs));
+  attn_fwd_kernel<<<B * H, 128, attn_smem(L, 3, 1), st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), mask, L, H,
+                                                          0.125f, reinterpret_cast<__nv_bfloat16*>(ctx),
+                                                          reinterpret_cast<__nv_bfloat16*>(probs));
   return check_launch("attn_fwd");
 }
 
@@ -1198,15 +1270,13 @@ int attn_bwd(const void* qkv, const void* probs, const void* dctx, int B, int L,
   }
   static bool set = false;
   if (!set) {
-    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)((4 * kAttMaxL * (kAttD + 1) + 2 * kAttMaxL * (kAttMaxL + 1)) * sizeof(float)));
+    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(kAttMaxL, 4, 4));
     set = true;
   }
-  const size_t smem = (size_t)(4 * L * (kAttD + 1) + 2 * L * (kAttMaxL + 1)) * sizeof(float);
-  attn_bwd_kernel<<<B * H, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                         reinterpret_cast<const __nv_bfloat16*>(probs),
-                                         reinterpret_cast<const __nv_bfloat16*>(dctx), L, H, 0.125f,
-                                         reinterpret_cast<__nv_bfloat16*>(dqkv));
+  attn_bwd_kernel<<<B * H, 128, attn_smem(L, 4, 4), st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                          reinterpret_cast<const __nv_bfloat16*>(probs),
+                                                          reinterpret_cast<const __nv_bfloat16*>(dctx), L, H, 0.125f,
+                                                          reinterpret_cast<__nv_bfloat16*>(dqkv));
   return check_launch("attn_bwd");
 }
 
