@@ -59,7 +59,8 @@ size_t creamfl_conv2d_workspace_bytes(int N, int H, int W, int Cin, int Cout, in
 }
 
 int creamfl_conv2d_fprop(const void* x, const void* w, int N, int H, int W, int Cin, int Cout, int R, int S_,
-                         int stride, int pad, int64_t w_pitch, void* y, void* ws, size_t ws_bytes, void* stream) {
+                         int stride, int pad, int64_t w_pitch, void* y, double* bn_sums, void* ws, size_t ws_bytes,
+                         void* stream) {
   const ConvShape c = shape_of(N, H, W, Cin, Cout, R, S_, stride, pad);
   int rc = check_shape("conv2d_fprop", c);
   if (rc) return rc;
@@ -67,10 +68,14 @@ int creamfl_conv2d_fprop(const void* x, const void* w, int N, int H, int W, int 
     set_error("conv2d_fprop: null pointer");
     return CFL_EINVAL;
   }
-  if (c.is_same && w_pitch == c.kcols) return conv_same_fprop(x, w, N, H, W, Cin, Cout, R, S_, y, S(stream));
+  if (c.is_same && w_pitch == c.kcols) {
+    if ((rc = conv_same_fprop(x, w, N, H, W, Cin, Cout, R, S_, y, S(stream)))) return rc;
+    return bn_sums ? bn_stats_only(y, c.P_out, Cout, bn_sums, S(stream)) : CFL_OK;
+  }
   GemmParams p{};
   p.M = (int)c.P_out; p.N = Cout; p.split_k = 1;
   p.out = y; p.ldo = Cout; p.out_bf16 = 1; p.alpha = 1.0f;
+  p.stats = bn_sums;
   if (c.is_1x1) {
     p.K = Cin;
     return gemm_bf16(x, Cin, 0, w, w_pitch, 0, p, S(stream));
@@ -160,13 +165,14 @@ int creamfl_im2col_nchw_f32(const float* images, int N, int C, int H, int W, int
 
 int creamfl_bn_train_fwd(const void* x, int64_t P, int C, const float* gamma, const float* beta, float eps,
                          float momentum, float* running_mean, float* running_var, double* sums, float* mean,
-                         float* rstd, float* scale, float* shift, const void* res, int relu, void* y, void* stream) {
+                         float* rstd, float* scale, float* shift, const void* res, int relu, int stats_ready, void* y,
+                         void* stream) {
   if (!x || !gamma || !beta || !sums || !mean || !rstd || !scale || !shift || !y) {
     set_error("bn_train_fwd: null pointer");
     return CFL_EINVAL;
   }
   return bn_train_fwd(x, P, C, gamma, beta, eps, momentum, running_mean, running_var, sums, mean, rstd, scale, shift,
-                      res, relu, y, S(stream));
+                      res, relu, stats_ready, y, S(stream));
 }
 
 int creamfl_bn_eval_fwd(const void* x, int64_t P, int C, const float* gamma, const float* beta, float eps,

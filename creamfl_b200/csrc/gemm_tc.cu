@@ -39,8 +39,9 @@ struct GemmCfg {
   static constexpr int kOutBytes = kBM * BN * 2;            // bf16 output tile staged for the TMA store
   static constexpr int kOutBufs = (BN == 256) ? 1 : 2;      // staging buffers (BN = 256: 64 KB, single)
   static constexpr int kAddBufs = ADD_TMA ? 2 : 0;
+  static constexpr int kStatBytes = ADD_TMA ? 0 : 2 * BN * 4;   // per-column (sum, sum of squares) accumulators
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + (kOutBufs + kAddBufs) * kOutBytes + 1024 /*align*/ + 256 /*barriers*/;
+      kStages * kStageBytes + (kOutBufs + kAddBufs) * kOutBytes + 1024 /*align*/ + 256 /*barriers*/ + kStatBytes;
   static constexpr uint32_t kTmemCols = 2 * BN;              // two accumulator buffers (power of two)
 };
 
@@ -73,7 +74,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BN, bool A_MN, bool B_MN, bool ADD_TMA>
+template <int BN, bool A_MN, bool B_MN, bool ADD_TMA, bool STATS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, GemmParams p) {
@@ -90,6 +91,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* dfull = tempty + 2;                              // [2] residual tile landed
   uint64_t* dempty = dfull + 2;                              // [2] residual tile consumed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
+  float* s_csum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [BN] (only if kStatBytes)
+  float* s_csq = s_csum + BN;                                                          // [BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -215,6 +218,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = (warp - 4) >> 2;      // column half
     const int rloc = q * 32 + lane;
     const bool issuer = (warp == 4 && lane == 0);
+    // fused BatchNorm statistics of the bf16 output (per-column sum / sum of squares): accumulated per CTA in shared
+    // memory over consecutive tiles of the same column block, flushed with one fp64 atomic per column
+    const bool do_stats = STATS && !ADD_TMA && p.stats != nullptr && p.tma_out;
+    const int etid = threadIdx.x - 128;
+    int acc_n_blk = -1;
+    if (do_stats) {
+      if (etid < BN) { s_csum[etid] = 0.0f; s_csq[etid] = 0.0f; }
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+    }
     int it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
       const int m_blk = u % num_m;
@@ -228,6 +240,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // the TMA store that last read this staging buffer must have drained
         if (issuer) tma_store_wait_read<Cfg::kOutBufs - 1>();
         asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      if (do_stats && acc_n_blk != n_blk) {
+        if (acc_n_blk >= 0) {
+          if (etid < BN && acc_n_blk * BN + etid < p.N) {
+            atomicAdd(p.stats + acc_n_blk * BN + etid, (double)s_csum[etid]);
+            atomicAdd(p.stats + p.N + acc_n_blk * BN + etid, (double)s_csq[etid]);
+          }
+          if (etid < BN) { s_csum[etid] = 0.0f; s_csq[etid] = 0.0f; }
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+        }
+        acc_n_blk = n_blk;
       }
       const int row = m_blk * kBM + rloc;
       // residual operand (bf16): fetched one 32-column chunk ahead of its use, the first chunk before the
@@ -375,6 +398,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        if (do_stats) {
+          // column sums over the 32 rows of this warp by a transpose-reduce butterfly (31 shuffles per statistic);
+          // lane l ends up with column l of the chunk.  Values are the bf16-rounded outputs the next kernel reads.
+          float sv[32], qv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float r = (live && (full_chunk || col0 + j < p.N)) ? __bfloat162float(__float2bfloat16(f[j])) : 0.0f;
+            sv[j] = r;
+            qv[j] = r * r;
+          }
+#pragma unroll
+          for (int w_ = 16; w_ >= 1; w_ >>= 1) {
+            const bool up = (lane & w_) != 0;
+#pragma unroll
+            for (int j = 0; j < w_; ++j) {
+              const float s_send = up ? sv[j] : sv[j + w_], s_keep = up ? sv[j + w_] : sv[j];
+              const float q_send = up ? qv[j] : qv[j + w_], q_keep = up ? qv[j + w_] : qv[j];
+              sv[j] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, w_);
+              qv[j] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, w_);
+            }
+          }
+          atomicAdd(&s_csum[ctile + lane], sv[0]);
+          atomicAdd(&s_csq[ctile + lane], qv[0]);
+        }
         if (p.tma_out) {
           // stage the bf16 row chunk: 128-byte rows, 16-byte units XOR-swizzled like the TMA store map expects
           const int region = ctile >> 6;                      // staged regions are 64 columns (128 bytes) wide
@@ -445,6 +492,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    if (do_stats) {
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      if (acc_n_blk >= 0 && etid < BN && acc_n_blk * BN + etid < p.N) {
+        atomicAdd(p.stats + acc_n_blk * BN + etid, (double)s_csum[etid]);
+        atomicAdd(p.stats + p.N + acc_n_blk * BN + etid, (double)s_csq[etid]);
+      }
+    }
     if (p.tma_out && issuer) tma_store_wait<0>();
   }
 
@@ -456,11 +510,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, bool ADD_TMA = false>
+template <int BN, bool A_MN, bool B_MN, bool ADD_TMA = false, bool STATS = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td,
                        const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, ADD_TMA>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, ADD_TMA>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, ADD_TMA, STATS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -537,9 +591,30 @@ int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long l
     if (a_mn && !b_mn) return launch_gemm<BNV, true, false>(ta, tb, tc, td, p, stream);        \
     return launch_gemm<BNV, true, true>(ta, tb, tc, td, p, stream);                            \
   } while (0)
+  if (p.stats != nullptr && (!p.tma_out || add_tma || p.act != 0 || p.ldo != p.N)) {
+    // statistics cannot ride in the epilogue for this configuration: run the GEMM, then the stand-alone pass
+    double* stats = p.stats;
+    p.stats = nullptr;
+    if (!p.out_bf16 || p.ldo != p.N) {
+      set_error("gemm_bf16: BatchNorm statistics need a contiguous bf16 output");
+      return CFL_EINVAL;
+    }
+    rc = gemm_bf16(a, lda, a_mn, b, ldb, b_mn, p, stream);
+    if (rc) return rc;
+    return bn_stats_only(p.out, p.M, p.N, stats, stream);
+  }
   if (add_tma) {
     if (b_mn) return launch_gemm<128, false, true, true>(ta, tb, tc, td, p, stream);
     return launch_gemm<128, false, false, true>(ta, tb, tc, td, p, stream);
+  }
+  if (p.stats != nullptr) {
+    if (a_mn || b_mn) {
+      set_error("gemm_bf16: fused statistics are implemented for K-major operands (forward convolutions)");
+      return CFL_EINVAL;
+    }
+    if (BN == 64) return launch_gemm<64, false, false, false, true>(ta, tb, tc, td, p, stream);
+    if (BN == 256) return launch_gemm<256, false, false, false, true>(ta, tb, tc, td, p, stream);
+    return launch_gemm<128, false, false, false, true>(ta, tb, tc, td, p, stream);
   }
   if (BN == 64) CFL_DISPATCH(64);
   if (BN == 256) CFL_DISPATCH(256);

@@ -22,6 +22,7 @@ struct GemmParams {
   int atomic_out;  // accumulate into the fp32 output with atomics even when split_k == 1
   long long ldo2;  // pitch of out2 (0: same as ldo)
   int tma_out;     // set by gemm_bf16: bf16 output leaves through a staged TMA store
+  double* stats;   // optional [2N]: += per-column sum and sum of squares of the bf16 output (BatchNorm statistics)
 };
 int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, GemmParams p,
               cudaStream_t stream);
@@ -61,7 +62,8 @@ int conv_same_dgrad(const void*, const void*, int, int, int, int, int, int, int,
 int conv_same_wgrad(const void*, const void*, int, int, int, int, int, int, int, float*, cudaStream_t);
 // nn_ops.cu
 int bn_train_fwd(const void*, long long, int, const float*, const float*, float, float, float*, float*, double*,
-                 float*, float*, float*, float*, const void*, int, void*, cudaStream_t);
+                 float*, float*, float*, float*, const void*, int, int, void*, cudaStream_t);
+int bn_stats_only(const void*, long long, int, double*, cudaStream_t);
 int bn_eval_fwd(const void*, long long, int, const float*, const float*, float, const float*, const float*, float*,
                 float*, const void*, int, void*, cudaStream_t);
 int bn_train_bwd(const void*, const void*, const void*, long long, int, const float*, const float*, int, const float*,

@@ -368,18 +368,21 @@ static int bn_reduce_grid(long long P, int C) {
   return (int)want;
 }
 
-int bn_train_fwd(const void* x, long long P, int C, const float* gamma, const float* beta, float eps, float momentum,
-                 float* running_mean, float* running_var, double* sums, float* mean, float* rstd, float* scale,
-                 float* shift, const void* res, int relu, void* y, cudaStream_t st) {
-  int rc = bn_check("bn_train_fwd", P, C);
+int bn_stats_only(const void* x, long long P, int C, double* sums, cudaStream_t st) {
+  int rc = bn_check("bn_stats", P, C);
   if (rc) return rc;
-  if (C > 8 * kBnThreads) {
-    set_error("bn: C=%d too large", C);
-    return CFL_EINVAL;
-  }
   const int rows = kBnThreads / (C >> 3);
   const size_t smem = (size_t)(rows > 0 ? rows : 1) * 2 * C * sizeof(float);
   bn_stats_kernel<<<bn_reduce_grid(P, C), kBnThreads, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), P, C, sums);
+  return check_launch("bn_stats");
+}
+
+int bn_train_fwd(const void* x, long long P, int C, const float* gamma, const float* beta, float eps, float momentum,
+                 float* running_mean, float* running_var, double* sums, float* mean, float* rstd, float* scale,
+                 float* shift, const void* res, int relu, int stats_ready, void* y, cudaStream_t st) {
+  int rc = bn_check("bn_train_fwd", P, C);
+  if (rc) return rc;
+  if (!stats_ready && (rc = bn_stats_only(x, P, C, sums, st))) return rc;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, beta, eps, momentum, running_mean,
                                                        running_var, mean, rstd, scale, shift);
   const long long total8 = P * C / 8;

@@ -41,8 +41,10 @@ def conv_out_hw(h: int, w: int, r: int, s: int, stride: int, pad: int):
     return (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
 
 
-def conv_fprop(x: torch.Tensor, w2d: torch.Tensor, r: int, s: int, stride: int, pad: int) -> torch.Tensor:
-    """x [N,H,W,Cin] bf16, w2d [Cout, >= R*S*Cin] bf16 (row = one filter in (r, s, cin) order)."""
+def conv_fprop(x: torch.Tensor, w2d: torch.Tensor, r: int, s: int, stride: int, pad: int,
+               bn_sums: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [N,H,W,Cin] bf16, w2d [Cout, >= R*S*Cin] bf16 (row = one filter in (r, s, cin) order).  bn_sums (fp64
+    [2*Cout], zero on entry): receives the BatchNorm statistics of the output."""
     _need_cuda(x, w2d)
     n, h, w, cin = x.shape
     cout = w2d.shape[0]
@@ -51,8 +53,8 @@ def conv_fprop(x: torch.Tensor, w2d: torch.Tensor, r: int, s: int, stride: int, 
     lib = _lib.load()
     nb = lib.creamfl_conv2d_workspace_bytes(n, h, w, cin, cout, r, s, stride, pad)
     ws = workspace(nb, x.device) if nb else None
-    _chk(lib.creamfl_conv2d_fprop(_p(x), _p(w2d), n, h, w, cin, cout, r, s, stride, pad, w2d.stride(0), _p(y), _p(ws),
-                                  nb, _stream()), "conv2d_fprop", 2 if nb else 1)
+    _chk(lib.creamfl_conv2d_fprop(_p(x), _p(w2d), n, h, w, cin, cout, r, s, stride, pad, w2d.stride(0), _p(y),
+                                  _p(bn_sums), _p(ws), nb, _stream()), "conv2d_fprop", 2 if nb else 1)
     return y
 
 
@@ -105,7 +107,8 @@ class BNScratch:
         self.coef = torch.empty(5 * c, dtype=torch.float32, device=device)
 
 
-def bn_train_fwd(x, gamma, beta, running_mean, running_var, sc: BNScratch, eps, momentum, res=None, relu=True):
+def bn_train_fwd(x, gamma, beta, running_mean, running_var, sc: BNScratch, eps, momentum, res=None, relu=True,
+                 stats_ready=False):
     c = x.shape[-1]
     p = x.numel() // c
     mean = torch.empty(c, dtype=torch.float32, device=x.device)
@@ -113,7 +116,8 @@ def bn_train_fwd(x, gamma, beta, running_mean, running_var, sc: BNScratch, eps, 
     y = torch.empty_like(x)
     _chk(_lib.load().creamfl_bn_train_fwd(_p(x), p, c, _p(gamma), _p(beta), eps, momentum, _p(running_mean),
                                           _p(running_var), _p(sc.sums), _p(mean), _p(rstd), _p(sc.scale), _p(sc.shift),
-                                          _p(res), int(relu), _p(y), _stream()), "bn_train_fwd", 3)
+                                          _p(res), int(relu), int(stats_ready), _p(y), _stream()), "bn_train_fwd",
+         2 if stats_ready else 3)
     return y, mean, rstd
 
 

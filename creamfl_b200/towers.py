@@ -203,11 +203,13 @@ class BN(nn.Module):
             new.__dict__[k] = None if k == '_scratch' else copy.deepcopy(v, memo)
         return new
 
-    def fwd(self, x, res=None, relu=True):
-        """Returns (y, saved) - saved is (mean, rstd) in training mode, None in eval mode."""
+    def fwd(self, x, res=None, relu=True, stats_ready=False):
+        """Returns (y, saved) - saved is (mean, rstd) in training mode, None in eval mode.  stats_ready: the
+        producing convolution already accumulated the batch statistics into scratch().sums."""
         if self.training:
             y, mean, rstd = T.bn_train_fwd(x, self.weight, self.bias, self.running_mean, self.running_var,
-                                           self.scratch(), self.eps, self.momentum, res=res, relu=relu)
+                                           self.scratch(), self.eps, self.momentum, res=res, relu=relu,
+                                           stats_ready=stats_ready)
             self.num_batches_tracked += 1
             return y, (mean, rstd)
         return T.bn_eval_fwd(x, self.weight, self.bias, self.running_mean, self.running_var, self.scratch(), self.eps,
@@ -223,8 +225,10 @@ class BN(nn.Module):
                               grad_target(self.bias), want_g=want_g, beta=self.bias, relu_from_x=relu_from_x)
 
 
-def _conv_f(c: Conv, x):
-    return T.conv_fprop(x, c.weight._w16, c.k, c.k, c.stride, c.pad)
+def _conv_f(c: Conv, x, bn: 'BN' = None):
+    """Convolution; with `bn` (training mode) the batch statistics of the output are produced on the way out."""
+    sums = bn.scratch().sums if (bn is not None and bn.training) else None
+    return T.conv_fprop(x, c.weight._w16, c.k, c.k, c.stride, c.pad, bn_sums=sums)
 
 
 def _conv_b(c: Conv, dy, x, need_dx=True, add=None):
@@ -251,17 +255,17 @@ class Bottleneck(nn.Module):
         return _BlockFn.apply(x, self, *self.block_params())
 
     def run_fwd(self, x, save):
-        o1 = _conv_f(self.conv1, x)
-        a1, s1 = self.bn1.fwd(o1)
-        o2 = _conv_f(self.conv2, a1)
-        a2, s2 = self.bn2.fwd(o2)
-        o3 = _conv_f(self.conv3, a2)
+        o1 = _conv_f(self.conv1, x, self.bn1)
+        a1, s1 = self.bn1.fwd(o1, stats_ready=True)
+        o2 = _conv_f(self.conv2, a1, self.bn2)
+        a2, s2 = self.bn2.fwd(o2, stats_ready=True)
+        o3 = _conv_f(self.conv3, a2, self.bn3)
         if self.downsample is not None:
-            od = _conv_f(self.downsample[0], x)
-            idn, sd = self.downsample[1].fwd(od, relu=False)
+            od = _conv_f(self.downsample[0], x, self.downsample[1])
+            idn, sd = self.downsample[1].fwd(od, relu=False, stats_ready=True)
         else:
             od, idn, sd = None, x, None
-        y, s3 = self.bn3.fwd(o3, res=idn, relu=True)
+        y, s3 = self.bn3.fwd(o3, res=idn, relu=True, stats_ready=True)
         if save:
             return y, (x, o1, a1, s1, o2, a2, s2, o3, s3, od, sd, y)
         return y, None
@@ -296,15 +300,15 @@ class BasicBlock(nn.Module):
         return _BlockFn.apply(x, self, *self.block_params())
 
     def run_fwd(self, x, save):
-        o1 = _conv_f(self.conv1, x)
-        a1, s1 = self.bn1.fwd(o1)
-        o2 = _conv_f(self.conv2, a1)
+        o1 = _conv_f(self.conv1, x, self.bn1)
+        a1, s1 = self.bn1.fwd(o1, stats_ready=True)
+        o2 = _conv_f(self.conv2, a1, self.bn2)
         if self.downsample is not None:
-            od = _conv_f(self.downsample[0], x)
-            idn, sd = self.downsample[1].fwd(od, relu=False)
+            od = _conv_f(self.downsample[0], x, self.downsample[1])
+            idn, sd = self.downsample[1].fwd(od, relu=False, stats_ready=True)
         else:
             od, idn, sd = None, x, None
-        y, s2 = self.bn2.fwd(o2, res=idn, relu=True)
+        y, s2 = self.bn2.fwd(o2, res=idn, relu=True, stats_ready=True)
         if save:
             return y, (x, o1, a1, s1, o2, s2, od, sd, y)
         return y, None

@@ -126,9 +126,12 @@ int creamfl_recall_ranks(const float* q, const float* g, const int64_t* q_lab, c
 /* ---- convolution: implicit GEMM on tcgen05 for stride-1 "same" filters, plain GEMM for 1x1, im2col + GEMM
  * for strided filters (workspace = patch matrix).  w_pitch = elements between filter rows (>= R*S*Cin). */
 size_t creamfl_conv2d_workspace_bytes(int N, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad);
+/* bn_sums (optional, 2*Cout doubles, accumulated): per-channel sum and sum of squares of the bf16 output - the
+ * BatchNorm statistics of the layer that follows, produced by the GEMM epilogue where the output tile is on chip
+ * (pass stats_ready = 1 to creamfl_bn_train_fwd afterwards) */
 int creamfl_conv2d_fprop(const void* x_bf16, const void* w_bf16, int N, int H, int W, int Cin, int Cout, int R, int S,
-                         int stride, int pad, int64_t w_pitch, void* y_bf16, void* workspace, size_t workspace_bytes,
-                         void* stream);
+                         int stride, int pad, int64_t w_pitch, void* y_bf16, double* bn_sums, void* workspace,
+                         size_t workspace_bytes, void* stream);
 /* dx = conv_transpose(dy, w) [+ add] ; add (optional) is a bf16 tensor shaped like dx (residual-branch gradient) */
 int creamfl_conv2d_dgrad(const void* dy_bf16, const void* w_bf16, int N, int H, int W, int Cin, int Cout, int R, int S,
                          int stride, int pad, int64_t w_pitch, const void* add_bf16, void* dx_bf16, void* workspace,
@@ -147,8 +150,8 @@ int creamfl_im2col_nchw_f32(const float* images, int N, int C, int H, int W, int
  * updated with `momentum`; keeps mean/rstd for the backward.  scale/shift: C-float scratch each. */
 int creamfl_bn_train_fwd(const void* x_bf16, int64_t P, int C, const float* gamma, const float* beta, float eps,
                          float momentum, float* running_mean, float* running_var, double* sums, float* mean,
-                         float* rstd, float* scale, float* shift, const void* res_bf16, int relu, void* y_bf16,
-                         void* stream);
+                         float* rstd, float* scale, float* shift, const void* res_bf16, int relu, int stats_ready,
+                         void* y_bf16, void* stream);
 int creamfl_bn_eval_fwd(const void* x_bf16, int64_t P, int C, const float* gamma, const float* beta, float eps,
                         const float* running_mean, const float* running_var, float* scale, float* shift,
                         const void* res_bf16, int relu, void* y_bf16, void* stream);

@@ -61,6 +61,23 @@ def test_conv_fprop_dgrad_wgrad(T, n, h, w, cin, cout, r, stride, pad):
     assert rel_l2(dw - 0.5, w64.grad.permute(0, 2, 3, 1).reshape(cout, -1)) < 2e-4
 
 
+@pytest.mark.parametrize('n,h,w,cin,cout,r,stride,pad', [(128, 14, 14, 1024, 256, 1, 1, 0), (16, 56, 56, 64, 256, 1, 1, 0),
+                                                         (4, 28, 28, 128, 128, 3, 1, 1), (8, 56, 56, 256, 512, 1, 2, 0),
+                                                         (3, 14, 14, 256, 1024, 1, 1, 0), (2, 56, 56, 64, 64, 1, 1, 0)])
+def test_conv_fused_bn_statistics(T, n, h, w, cin, cout, r, stride, pad):
+    """BatchNorm statistics produced by the convolution (GEMM epilogue or stand-alone pass, chosen by the library)
+    equal the per-channel sum / sum of squares of the bf16 output it wrote: rel 1e-5 (fp32 partials, fp64 totals)."""
+    x = rnd(n, h, w, cin, seed=31)
+    wt = rnd(cout, r * r * cin, seed=32, scale=(r * r * cin) ** -0.5)
+    sums = torch.zeros(2 * cout, dtype=torch.float64, device='cuda')
+    y = T.conv_fprop(x.cuda(), wt.cuda(), r, r, stride, pad, bn_sums=sums)
+    y2 = T.conv_fprop(x.cuda(), wt.cuda(), r, r, stride, pad)
+    assert torch.equal(y, y2)
+    yd = y.double().reshape(-1, cout)
+    assert rel_l2(sums[:cout], yd.sum(0)) < 1e-5
+    assert rel_l2(sums[cout:], (yd * yd).sum(0)) < 1e-5
+
+
 def test_conv_is_linear_full_size(T):
     """Size-independent property at the ResNet101 layer3 size (B = 128): conv(x1 + x2) == conv(x1) + conv(x2) exactly
     when all partial sums are dyadic rationals."""
