@@ -39,7 +39,7 @@ struct GemmCfg {
   static constexpr int kOutBytes = kBM * BN * 2;            // bf16 output tile staged for the TMA store
   static constexpr int kOutBufs = (BN == 256) ? 1 : 2;      // staging buffers (BN = 256: 64 KB, single)
   static constexpr int kAddBufs = ADD_TMA ? 2 : 0;
-  static constexpr int kStatBytes = ADD_TMA ? 0 : 2 * BN * 4;   // per-column (sum, sum of squares) accumulators
+  static constexpr int kStatBytes = ADD_TMA ? 0 : 2 * BN * 8;   // per-column (sum, sum of squares) fp64 accumulators
   static constexpr int kSmemBytes =
       kStages * kStageBytes + (kOutBufs + kAddBufs) * kOutBytes + 1024 /*align*/ + 256 /*barriers*/ + kStatBytes;
   static constexpr uint32_t kTmemCols = 2 * BN;              // two accumulator buffers (power of two)
@@ -91,8 +91,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* dfull = tempty + 2;                              // [2] residual tile landed
   uint64_t* dempty = dfull + 2;                              // [2] residual tile consumed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
-  float* s_csum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [BN] (only if kStatBytes)
-  float* s_csq = s_csum + BN;                                                          // [BN]
+  double* s_csum = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [BN] (only if kStatBytes)
+  double* s_csq = s_csum + BN;                                                          // [BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -224,7 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int etid = threadIdx.x - 128;
     int acc_n_blk = -1;
     if (do_stats) {
-      if (etid < BN) { s_csum[etid] = 0.0f; s_csq[etid] = 0.0f; }
+      if (etid < BN) { s_csum[etid] = 0.0; s_csq[etid] = 0.0; }
       asm volatile("bar.sync 3, 256;" ::: "memory");
     }
     int it = 0;
@@ -244,10 +244,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (do_stats && acc_n_blk != n_blk) {
         if (acc_n_blk >= 0) {
           if (etid < BN && acc_n_blk * BN + etid < p.N) {
-            atomicAdd(p.stats + acc_n_blk * BN + etid, (double)s_csum[etid]);
-            atomicAdd(p.stats + p.N + acc_n_blk * BN + etid, (double)s_csq[etid]);
+            atomicAdd(p.stats + acc_n_blk * BN + etid, s_csum[etid]);
+            atomicAdd(p.stats + p.N + acc_n_blk * BN + etid, s_csq[etid]);
           }
-          if (etid < BN) { s_csum[etid] = 0.0f; s_csq[etid] = 0.0f; }
+          if (etid < BN) { s_csum[etid] = 0.0; s_csq[etid] = 0.0; }
           asm volatile("bar.sync 3, 256;" ::: "memory");
         }
         acc_n_blk = n_blk;
@@ -398,30 +398,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        if (do_stats) {
-          // column sums over the 32 rows of this warp by a transpose-reduce butterfly (31 shuffles per statistic);
-          // lane l ends up with column l of the chunk.  Values are the bf16-rounded outputs the next kernel reads.
-          float sv[32], qv[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float r = (live && (full_chunk || col0 + j < p.N)) ? __bfloat162float(__float2bfloat16(f[j])) : 0.0f;
-            sv[j] = r;
-            qv[j] = r * r;
-          }
-#pragma unroll
-          for (int w_ = 16; w_ >= 1; w_ >>= 1) {
-            const bool up = (lane & w_) != 0;
-#pragma unroll
-            for (int j = 0; j < w_; ++j) {
-              const float s_send = up ? sv[j] : sv[j + w_], s_keep = up ? sv[j + w_] : sv[j];
-              const float q_send = up ? qv[j] : qv[j + w_], q_keep = up ? qv[j + w_] : qv[j];
-              sv[j] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, w_);
-              qv[j] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, w_);
-            }
-          }
-          atomicAdd(&s_csum[ctile + lane], sv[0]);
-          atomicAdd(&s_csq[ctile + lane], qv[0]);
-        }
         if (p.tma_out) {
           // stage the bf16 row chunk: 128-byte rows, 16-byte units XOR-swizzled like the TMA store map expects
           const int region = ctile >> 6;                      // staged regions are 64 columns (128 bytes) wide
@@ -490,13 +466,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_2d(&tmC, stile + r * (kBM * 128), n_blk * BN + r * 64, m_blk * kBM);
           tma_store_commit();
         }
+        if (do_stats) {
+          // column sums of the staged bf16 tile (rows / columns outside the problem were staged as zeros): a thread
+          // owns one column pair and a group of rows; a warp reads 128 contiguous bytes of one row per instruction
+          constexpr int CP = BN / 2, RG = 256 / CP, RPT = kBM / RG;
+          const int cp = etid % CP, rg = etid / CP;
+          const int col = cp * 2;
+          const uint8_t* cbase = stile + (col >> 6) * (kBM * 128) + (col & 7) * 2;
+          const int unit = (col & 63) >> 3;
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+          for (int r = rg * RPT; r < (rg + 1) * RPT; ++r) {
+            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(cbase + sw128_offset(r, unit)));
+            s0 += v.x; s1 += v.y;
+            q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1);
+          }
+          atomicAdd(&s_csum[col], (double)s0);       // fp64: the accumulation order cannot change the statistics
+          atomicAdd(&s_csum[col + 1], (double)s1);
+          atomicAdd(&s_csq[col], (double)q0);
+          atomicAdd(&s_csq[col + 1], (double)q1);
+        }
       }
     }
     if (do_stats) {
       asm volatile("bar.sync 3, 256;" ::: "memory");
       if (acc_n_blk >= 0 && etid < BN && acc_n_blk * BN + etid < p.N) {
-        atomicAdd(p.stats + acc_n_blk * BN + etid, (double)s_csum[etid]);
-        atomicAdd(p.stats + p.N + acc_n_blk * BN + etid, (double)s_csq[etid]);
+        atomicAdd(p.stats + acc_n_blk * BN + etid, s_csum[etid]);
+        atomicAdd(p.stats + p.N + acc_n_blk * BN + etid, s_csq[etid]);
       }
     }
     if (p.tma_out && issuer) tma_store_wait<0>();

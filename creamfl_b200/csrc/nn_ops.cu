@@ -359,9 +359,7 @@ static int bn_check(const char* who, long long P, int C) {
 
 static int bn_reduce_grid(long long P, int C) {
   const int rows = kBnThreads / (C >> 3) > 0 ? kBnThreads / (C >> 3) : 1;
-  // >= 4 pixels per thread: the small late-stage maps (25088 or 6272 pixels) are latency-bound, they need the
-  // parallelism more than they need long per-thread loops
-  long long want = (P + (long long)rows * 4 - 1) / ((long long)rows * 4);
+  long long want = (P + (long long)rows * 16 - 1) / ((long long)rows * 16);  // >= 16 pixels per thread
   const long long cap = (long long)sm_count() * 8;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
