@@ -78,8 +78,9 @@ class ServerEngine:
                                         no_clip=list(self.criterion.parameters())).attach_stores(self.model)
         self.kd_weight = kd_weight
         self.data_parallel = data_parallel and dist.is_initialized() and dist.get_world_size() > 1
-        # the data-parallel step stays eager: capturing the NCCL all-reduce inside the step graph deadlocked on 2 GPUs
-        self.use_graphs = use_graphs and not self.data_parallel
+        # data-parallel: forward+backward is one captured graph, the NCCL all-reduce of the flat gradient buffer and the
+        # 4-launch optimizer step run eagerly after it (capturing the collective inside the graph deadlocked on 2 GPUs)
+        self.use_graphs = use_graphs
 
     def _graphed(self, name, fn, **tensors):
         key = (name, tuple((k, tuple(t.shape)) for k, t in tensors.items()))
@@ -98,20 +99,29 @@ class ServerEngine:
 
     def train_step(self, images, tokens) -> torch.Tensor:
         if self.use_graphs and isinstance(tokens, dict):
-            return self._graphed('train', lambda images, ids, mask: self._train_step(
+            fn = self._train_fwd_bwd if self.data_parallel else self._train_step
+            loss = self._graphed('train', lambda images, ids, mask: fn(
                 images, {'input_ids': ids, 'attention_mask': mask}), images=images, ids=tokens['input_ids'],
                 mask=tokens['attention_mask'])
+            if self.data_parallel:
+                self._sync_grads()
+                self.optimizer.step()
+            return loss
         return self._train_step(images, tokens)
 
-    def _train_step(self, images, tokens) -> torch.Tensor:
+    def _train_fwd_bwd(self, images, tokens) -> torch.Tensor:
         self.model.train()
         output = self.model(images, None, tokens, None)
         loss, _ = self.criterion(**output)
         self.optimizer.zero_grad()
         loss.backward()
+        return loss.detach()
+
+    def _train_step(self, images, tokens) -> torch.Tensor:
+        loss = self._train_fwd_bwd(images, tokens)
         self._sync_grads()
         self.optimizer.step()
-        return loss.detach()
+        return loss
 
     def extract(self, images, tokens) -> Tuple[torch.Tensor, torch.Tensor]:
         if self.use_graphs and isinstance(tokens, dict):
@@ -130,15 +140,26 @@ class ServerEngine:
         that carries the modality (MMFL.py:361-378; 2 each when image, text and multimodal clients all exist)."""
         if self.use_graphs and isinstance(tokens, dict) and agg_img is not None and agg_txt is not None:
             # aggregated targets are passed as graph inputs (they are re-created every round)
-            return self._graphed(('distill', img_terms, txt_terms),
-                                 lambda images, ids, mask, d_idx, agg_img, agg_txt: self._distill_step(
+            fn = self._distill_fwd_bwd if self.data_parallel else self._distill_step
+            loss = self._graphed(('distill', img_terms, txt_terms),
+                                 lambda images, ids, mask, d_idx, agg_img, agg_txt: fn(
                                      images, {'input_ids': ids, 'attention_mask': mask}, d_idx, agg_img, agg_txt,
                                      img_terms, txt_terms),
                                  images=images, ids=tokens['input_ids'], mask=tokens['attention_mask'], d_idx=d_idx,
                                  agg_img=agg_img, agg_txt=agg_txt)
+            if self.data_parallel:
+                self._sync_grads()
+                self.optimizer.step()
+            return loss
         return self._distill_step(images, tokens, d_idx, agg_img, agg_txt, img_terms, txt_terms)
 
     def _distill_step(self, images, tokens, d_idx, agg_img, agg_txt, img_terms: int = 1, txt_terms: int = 1):
+        loss = self._distill_fwd_bwd(images, tokens, d_idx, agg_img, agg_txt, img_terms, txt_terms)
+        self._sync_grads()
+        self.optimizer.step()
+        return loss
+
+    def _distill_fwd_bwd(self, images, tokens, d_idx, agg_img, agg_txt, img_terms: int = 1, txt_terms: int = 1):
         self.model.train()
         out_img, out_txt = _features(self.model(images, None, tokens, None))
         loss = 0
@@ -148,8 +169,6 @@ class ServerEngine:
             loss = loss + (self.kd_weight * txt_terms) * ops.mse_gather_loss(out_txt, agg_txt, d_idx)
         self.optimizer.zero_grad()
         loss.backward()
-        self._sync_grads()
-        self.optimizer.step()
         return loss.detach()
 
 
