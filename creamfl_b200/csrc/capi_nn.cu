@@ -175,6 +175,14 @@ int creamfl_bn_train_fwd(const void* x, int64_t P, int C, const float* gamma, co
                       res, relu, stats_ready, y, S(stream));
 }
 
+int creamfl_bn_stats(const void* x, int64_t P, int C, double* sums, void* stream) {
+  if (!x || !sums) {
+    set_error("bn_stats: null pointer");
+    return CFL_EINVAL;
+  }
+  return bn_stats_only(x, P, C, sums, S(stream));
+}
+
 int creamfl_bn_eval_fwd(const void* x, int64_t P, int C, const float* gamma, const float* beta, float eps,
                         const float* running_mean, const float* running_var, float* scale, float* shift,
                         const void* res, int relu, void* y, void* stream) {

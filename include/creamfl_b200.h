@@ -152,6 +152,8 @@ int creamfl_bn_train_fwd(const void* x_bf16, int64_t P, int C, const float* gamm
                          float momentum, float* running_mean, float* running_var, double* sums, float* mean,
                          float* rstd, float* scale, float* shift, const void* res_bf16, int relu, int stats_ready,
                          void* y_bf16, void* stream);
+/* stand-alone statistics pass: sums[0..C) += sum_p x, sums[C..2C) += sum_p x^2 */
+int creamfl_bn_stats(const void* x_bf16, int64_t P, int C, double* sums, void* stream);
 int creamfl_bn_eval_fwd(const void* x_bf16, int64_t P, int C, const float* gamma, const float* beta, float eps,
                         const float* running_mean, const float* running_var, float* scale, float* shift,
                         const void* res_bf16, int relu, void* y_bf16, void* stream);
