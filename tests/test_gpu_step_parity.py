@@ -1,0 +1,76 @@
+"""End-to-end parity of one server train step at the shape of BASELINE.json configs[0] (ResNet101+BERT server, 16
+synthetic COCO-shape pairs): creamfl_b200.engine.ServerEngine.train_step against the torch restatement of the
+reference step (RefPCME forward -> MCSoftContrastiveLoss -> backward -> clip_grad_norm_(2) -> AdamP) on identical
+weights and inputs.
+
+Tolerances: loss rel 2e-2 (bf16 towers); clipped-gradient norm rel 5e-2; parameter updates of the head tensors
+(well-conditioned gradients) cosine >= 0.98 against the oracle AdamP update; every parameter moved by at most
+lr / (1 - beta1) * (1 + 1e-3) per element (Adam's first-step bound) and stays finite."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def cos(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return (a @ b / (a.norm() * b.norm()).clamp_min(1e-300)).item()
+
+
+def test_server_train_step_matches_reference_step():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    from creamfl_b200 import engine
+    from oracle import creamfl_oracle as O, torch_towers as RT
+    B, L, lr = 16, 32, 2e-4
+    ref = RT.RefPCME('resnet101', 256)
+    RT.fill_deterministic(ref, seed=41)
+    with torch.no_grad():
+        for name, p in ref.named_parameters():
+            if name.endswith('bn3.weight'):
+                p.mul_(0.2)
+    ref = ref.cuda().train()
+    server = engine.ServerEngine(256, 'resnet101', lr=lr, grad_clip=2.0)
+    server.model.load_state_dict(ref.state_dict(), strict=True)
+    server.model.sync_shadow()
+    g = torch.Generator().manual_seed(42)
+    images = torch.randn(B, 3, 224, 224, generator=g).cuda()
+    lens = torch.sort(torch.randint(8, L + 1, (B,), generator=g), descending=True).values
+    mask = (torch.arange(L)[None] < lens[:, None]).long()
+    ids = torch.randint(1000, 30522, (B, L), generator=g)
+    ids[:, 0] = 101
+    ids, mask = (ids * mask).cuda(), mask.cuda()
+    # ---- reference step (fp32 torch)
+    shift = torch.tensor(15.0, device='cuda', requires_grad=True)
+    scale = torch.tensor(15.0, device='cuda', requires_grad=True)
+    out = ref(images, ids, mask, torch.zeros_like(ids))
+    loss_ref, _ = O.pcme_loss(out['image_features'], out['caption_features'], shift, scale)
+    loss_ref.backward()
+    names = ['img_enc.fc.weight', 'img_enc.pie_net.fc.weight', 'linear.weight', 'linear.bias',
+             'img_enc.pie_net.layer_norm.weight', 'txt_enc.encoder.layer.11.output.dense.weight']
+    ref_params = dict(ref.named_parameters())
+    model_grads = [p.grad for p in ref.parameters() if p.grad is not None]
+    norm_ref = O.clip_grad_norm(model_grads, 2.0)
+    before = {n: ref_params[n].detach().clone() for n in names}
+    ps = [ref_params[n].detach().double().clone() for n in names]
+    gs = [ref_params[n].grad.double() for n in names]
+    O.adamp_step(ps, gs, [torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps], 1, lr)
+    # ---- CUDA step
+    mine_params = dict(server.model.named_parameters())
+    all_before = server.model.store().flat.clone()
+    loss = server.train_step(images, {'input_ids': ids, 'attention_mask': mask})
+    torch.cuda.synchronize()
+    assert loss.item() == pytest.approx(loss_ref.item(), rel=2e-2)
+    assert server.optimizer.grad_norm.item() == pytest.approx(norm_ref, rel=5e-2)
+    for n, p_new in zip(names, ps):
+        d_ref = p_new.float().cuda() - before[n]
+        d_mine = mine_params[n].detach() - before[n]
+        assert cos(d_mine, d_ref) >= 0.98, (n, cos(d_mine, d_ref))
+    moved = (server.model.store().flat - all_before).abs()
+    assert torch.isfinite(server.model.store().flat).all()
+    assert moved.max().item() <= lr / (1 - 0.9) * (1 + 1e-3) * 1.0 + 1e-9      # |update| <= lr * |m_hat| / (sqrt(v_hat)+eps) <= lr/(1-b1)... first step: exactly lr
+    assert moved.max().item() <= lr * (1 + 1e-3)
+    # criterion parameters are optimised too (retrieval_trainer.py:62-63) but not clipped
+    assert server.criterion.shift.item() != 15.0 and abs(server.criterion.shift.item() - 15.0) <= lr * 1.001
