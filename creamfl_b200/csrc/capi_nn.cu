@@ -233,12 +233,13 @@ int creamfl_layernorm_fwd(const void* x, const void* res, const float* gamma, co
 
 int creamfl_layernorm_bwd(const void* dy, const void* x, const void* res, const float* gamma, const float* mean,
                           const float* rstd, int R, int D, int is_bf16, void* dx, float* dgamma, float* dbeta,
-                          void* ws, size_t ws_bytes, void* stream) {
+                          float* dx_colsum, void* ws, size_t ws_bytes, void* stream) {
   if (!dy || !x || !gamma || !mean || !rstd || !dx || !ws) {
     set_error("layernorm_bwd: null pointer");
     return CFL_EINVAL;
   }
-  return layernorm_bwd(dy, x, res, gamma, mean, rstd, R, D, is_bf16, dx, dgamma, dbeta, ws, ws_bytes, S(stream));
+  return layernorm_bwd(dy, x, res, gamma, mean, rstd, R, D, is_bf16, dx, dgamma, dbeta, dx_colsum, ws, ws_bytes,
+                       S(stream));
 }
 
 int creamfl_colsum_bf16(const void* x, int M, int N, int64_t ld, float* out, void* stream) {
@@ -287,12 +288,12 @@ int creamfl_attn_fwd(const void* qkv, const float* mask, int B, int L, int H, in
 }
 
 int creamfl_attn_bwd(const void* qkv, const void* probs, const void* dctx, int B, int L, int H, int head_dim,
-                     void* dqkv, void* stream) {
+                     void* dqkv, float* dbias, void* stream) {
   if (!qkv || !probs || !dctx || !dqkv) {
     set_error("attn_bwd: null pointer");
     return CFL_EINVAL;
   }
-  return attn_bwd(qkv, probs, dctx, B, L, H, head_dim, dqkv, S(stream));
+  return attn_bwd(qkv, probs, dctx, B, L, H, head_dim, dqkv, dbias, S(stream));
 }
 
 int creamfl_pie_pool_fwd(const void* x, const void* h, const float* w2, int B, int P, int C, int Hd, float* attn,

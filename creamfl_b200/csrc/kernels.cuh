@@ -77,14 +77,14 @@ size_t layernorm_bwd_workspace_bytes(int);
 int layernorm_fwd(const void*, const void*, const float*, const float*, float, int, int, int, void*, float*, float*,
                   cudaStream_t);
 int layernorm_bwd(const void*, const void*, const void*, const float*, const float*, const float*, int, int, int,
-                  void*, float*, float*, void*, size_t, cudaStream_t);
+                  void*, float*, float*, float*, void*, size_t, cudaStream_t);
 int colsum_bf16(const void*, int, int, long long, float*, cudaStream_t);
 int add_bf16(const void*, const void*, long long, void*, cudaStream_t);
 int embed_fwd(const long long*, const long long*, const float*, const float*, const float*, int, int, int, void*,
               cudaStream_t);
 int embed_bwd(const long long*, const long long*, const void*, int, int, int, float*, float*, float*, cudaStream_t);
 int attn_fwd(const void*, const float*, int, int, int, int, void*, void*, cudaStream_t);
-int attn_bwd(const void*, const void*, const void*, int, int, int, int, void*, cudaStream_t);
+int attn_bwd(const void*, const void*, const void*, int, int, int, int, void*, float*, cudaStream_t);
 int pie_pool_fwd(const void*, const void*, const float*, int, int, int, int, float*, void*, void*, cudaStream_t);
 int pie_pool_bwd(const void*, const void*, const float*, const float*, const void*, const void*, int, int, int, int,
                  void*, void*, float*, cudaStream_t);

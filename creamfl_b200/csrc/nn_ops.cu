@@ -784,15 +784,15 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ xin, const T* __restrict__ res_in,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
-                     int R, int D, T* __restrict__ dx, float* __restrict__ part /* [gridDim.x, 2, D] */) {
-  extern __shared__ float sh[];  // [warps][2][D]
+                     int R, int D, T* __restrict__ dx, float* __restrict__ part /* [gridDim.x, 3, D] */) {
+  extern __shared__ float sh[];  // [warps][3][D]
   const int warps = blockDim.x >> 5;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float ag[kLnMaxChunks][8], ab[kLnMaxChunks][8];
+  float ag[kLnMaxChunks][8], ab[kLnMaxChunks][8], ax[kLnMaxChunks][8];
 #pragma unroll
   for (int c = 0; c < kLnMaxChunks; ++c)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ag[c][i] = ab[c][i] = 0.0f;
+    for (int i = 0; i < 8; ++i) ag[c][i] = ab[c][i] = ax[c][i] = 0.0f;
   for (int row = blockIdx.x * warps + w; row < R; row += gridDim.x * warps) {
     const float mu = mean[row], rs = rstd[row];
     float g[kLnMaxChunks][8], xh[kLnMaxChunks][8];
@@ -830,7 +830,10 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ xin, const 
       if (k < D) {
         float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = rs * (g[c][i] - s1 - xh[c][i] * s2);
+        for (int i = 0; i < 8; ++i) {
+          o[i] = rs * (g[c][i] - s1 - xh[c][i] * s2);
+          ax[c][i] += o[i];          // column sums of dx: the bias gradient of the linear layer feeding this LayerNorm
+        }
         store8<T>(dx + (long long)row * D + k, o);
       }
     }
@@ -841,38 +844,37 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ xin, const 
     if (k < D) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        sh[(w * 2 + 0) * D + k + i] = ag[c][i];
-        sh[(w * 2 + 1) * D + k + i] = ab[c][i];
+        sh[(w * 3 + 0) * D + k + i] = ag[c][i];
+        sh[(w * 3 + 1) * D + k + i] = ab[c][i];
+        sh[(w * 3 + 2) * D + k + i] = ax[c][i];
       }
     }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 2 * D; e += blockDim.x) {
+  for (int e = threadIdx.x; e < 3 * D; e += blockDim.x) {
     const int which = e / D, k = e % D;
     float acc = 0.0f;
-    for (int ww = 0; ww < warps; ++ww) acc += sh[(ww * 2 + which) * D + k];
-    part[((long long)blockIdx.x * 2 + which) * D + k] = acc;
+    for (int ww = 0; ww < warps; ++ww) acc += sh[(ww * 3 + which) * D + k];
+    part[((long long)blockIdx.x * 3 + which) * D + k] = acc;
   }
 }
 
-// dgamma[k] += sum_b part[b,0,k]; dbeta[k] += sum_b part[b,1,k]   (fixed order)
+// dgamma[k] += sum_b part[b,0,k]; dbeta[k] += sum_b part[b,1,k]; dxsum[k] += sum_b part[b,2,k]   (fixed order)
 __global__ void ln_param_reduce_kernel(const float* __restrict__ part, int blocks, int D, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
+                                       float* __restrict__ dbeta, float* __restrict__ dxsum) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= 2 * D) return;
+  if (e >= 3 * D) return;
   const int which = e / D, k = e % D;
+  float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dxsum);
+  if (dst == nullptr) return;
   float acc = 0.0f;
-  for (int b = 0; b < blocks; ++b) acc += part[((long long)b * 2 + which) * D + k];
-  if (which == 0) {
-    if (dgamma) dgamma[k] += acc;
-  } else {
-    if (dbeta) dbeta[k] += acc;
-  }
+  for (int b = 0; b < blocks; ++b) acc += part[((long long)b * 3 + which) * D + k];
+  dst[k] += acc;
 }
 
 constexpr int kLnBwdBlocks = 148;
 
-size_t layernorm_bwd_workspace_bytes(int D) { return (size_t)kLnBwdBlocks * 2 * D * sizeof(float); }
+size_t layernorm_bwd_workspace_bytes(int D) { return (size_t)kLnBwdBlocks * 3 * D * sizeof(float); }
 
 int layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, float eps, int R, int D,
                   int is_bf16, void* y, float* mean, float* rstd, cudaStream_t st) {
@@ -893,8 +895,8 @@ int layernorm_fwd(const void* x, const void* res, const float* gamma, const floa
 }
 
 int layernorm_bwd(const void* dy, const void* xin, const void* res_in, const float* gamma, const float* mean,
-                  const float* rstd, int R, int D, int is_bf16, void* dx, float* dgamma, float* dbeta, void* ws,
-                  size_t ws_bytes, cudaStream_t st) {
+                  const float* rstd, int R, int D, int is_bf16, void* dx, float* dgamma, float* dbeta, float* dx_colsum,
+                  void* ws, size_t ws_bytes, cudaStream_t st) {
   if (R <= 0 || D <= 0 || (D & 7) || D > kLnMaxChunks * 256) {
     set_error("layernorm_bwd: bad shape R=%d D=%d", R, D);
     return CFL_EINVAL;
@@ -905,7 +907,7 @@ int layernorm_bwd(const void* dy, const void* xin, const void* res_in, const flo
   }
   int blocks = (R + 7) / 8;
   if (blocks > kLnBwdBlocks) blocks = kLnBwdBlocks;
-  const size_t smem = (size_t)8 * 2 * D * sizeof(float);
+  const size_t smem = (size_t)8 * 3 * D * sizeof(float);
   float* part = reinterpret_cast<float*>(ws);
   if (is_bf16) {
     if (smem > 48 * 1024)
@@ -921,7 +923,7 @@ int layernorm_bwd(const void* dy, const void* xin, const void* res_in, const flo
         reinterpret_cast<const float*>(dy), reinterpret_cast<const float*>(xin), reinterpret_cast<const float*>(res_in),
         gamma, mean, rstd, R, D, reinterpret_cast<float*>(dx), part);
   }
-  ln_param_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, st>>>(part, blocks, D, dgamma, dbeta);
+  ln_param_reduce_kernel<<<(3 * D + 255) / 256, 256, 0, st>>>(part, blocks, D, dgamma, dbeta, dx_colsum);
   return check_launch("layernorm_bwd");
 }
 
@@ -1172,8 +1174,11 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__
 // dqkv [B*L, 3*H*64] bf16 from dctx [B*L, H*64], the saved probabilities and qkv.
 __global__ void __launch_bounds__(128)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ probs,
-                const __nv_bfloat16* __restrict__ dctx, int L, int H, float scale, __nv_bfloat16* __restrict__ dqkv) {
+                const __nv_bfloat16* __restrict__ dctx, int L, int H, float scale, __nv_bfloat16* __restrict__ dqkv,
+                float* __restrict__ dbias /* [3*H*64] += column sums of dqkv, or null */) {
   extern __shared__ __align__(16) float att_sm[];
+  __shared__ float s_bias[3 * kAttD];
+  for (int e = threadIdx.x; e < 3 * kAttD; e += blockDim.x) s_bias[e] = 0.0f;
   const int Lp = (L + 3) & ~3;
   const int lp = Lp + 4;
   float* sq = att_sm;
@@ -1233,14 +1238,26 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
     if (which == 0) tile_nn(sds, lp, sk, Lp, i0, d0, acc);
     else if (which == 1) tile_nn(sdst, lp, sq, Lp, i0, d0, acc);
     else tile_nn(spt, lp, sdo, Lp, i0, d0, acc);
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
       if (i0 + x < L) {
         __nv_bfloat16* o = obase + (long long)(i0 + x) * ld + which * H * kAttD + d0;
         *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(acc[x][0], acc[x][1]);
         *reinterpret_cast<__nv_bfloat162*>(o + 2) = __floats2bfloat162_rn(acc[x][2], acc[x][3]);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) cs[y] += acc[x][y];
       }
     }
+    if (dbias) {
+#pragma unroll
+      for (int y = 0; y < 4; ++y) atomicAdd(&s_bias[which * kAttD + d0 + y], cs[y]);
+    }
+  }
+  if (dbias) {   // bias gradient of the fused q/k/v projection: column sums of dqkv, one global atomic per column per CTA
+    __syncthreads();
+    for (int e = threadIdx.x; e < 3 * kAttD; e += blockDim.x)
+      atomicAdd(dbias + (e / kAttD) * H * kAttD + h * kAttD + (e % kAttD), s_bias[e]);
   }
 }
 
@@ -1266,7 +1283,7 @@ int attn_fwd(const void* qkv, const float* mask, int B, int L, int H, int dh, vo
 }
 
 int attn_bwd(const void* qkv, const void* probs, const void* dctx, int B, int L, int H, int dh, void* dqkv,
-             cudaStream_t st) {
+             float* dbias, cudaStream_t st) {
   if (B <= 0 || L <= 0 || L > kAttMaxL || dh != kAttD || H <= 0) {
     set_error("attn_bwd: unsupported shape");
     return CFL_EINVAL;
@@ -1279,7 +1296,7 @@ int attn_bwd(const void* qkv, const void* probs, const void* dctx, int B, int L,
   attn_bwd_kernel<<<B * H, 128, attn_smem(L, 4, 4), st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                           reinterpret_cast<const __nv_bfloat16*>(probs),
                                                           reinterpret_cast<const __nv_bfloat16*>(dctx), L, H, 0.125f,
-                                                          reinterpret_cast<__nv_bfloat16*>(dqkv));
+                                                          reinterpret_cast<__nv_bfloat16*>(dqkv), dbias);
   return check_launch("attn_bwd");
 }
 

@@ -174,14 +174,15 @@ def layernorm_fwd(x, gamma, beta, eps, res=None):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, res=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, res=None, dx_colsum=None):
     r, d = x.shape
     lib = _lib.load()
     dx = torch.empty_like(x)
     nb = lib.creamfl_layernorm_bwd_workspace_bytes(d)
     ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
     _chk(lib.creamfl_layernorm_bwd(_p(dy), _p(x), _p(res), _p(gamma), _p(mean), _p(rstd), r, d, int(x.dtype == BF16),
-                                   _p(dx), _p(dgamma), _p(dbeta), _p(ws), nb, _stream()), "layernorm_bwd", 2)
+                                   _p(dx), _p(dgamma), _p(dbeta), _p(dx_colsum), _p(ws), nb, _stream()),
+         "layernorm_bwd", 2)
     return dx
 
 
@@ -225,9 +226,10 @@ def attn_fwd(qkv, mask, b, l, heads):
     return ctx, probs
 
 
-def attn_bwd(qkv, probs, dctx, b, l, heads):
+def attn_bwd(qkv, probs, dctx, b, l, heads, dbias=None):
     dqkv = torch.empty_like(qkv)
-    _chk(_lib.load().creamfl_attn_bwd(_p(qkv), _p(probs), _p(dctx), b, l, heads, 64, _p(dqkv), _stream()), "attn_bwd")
+    _chk(_lib.load().creamfl_attn_bwd(_p(qkv), _p(probs), _p(dctx), b, l, heads, 64, _p(dqkv), _p(dbias), _stream()),
+         "attn_bwd")
     return dqkv
 
 

@@ -671,28 +671,27 @@ class _BertFn(torch.autograd.Function):
         for lyr, sv in zip(reversed(bert.encoder.layer), reversed(saved_layers)):
             h_in, qkv, probs, ctxv, ao, m1, r1, h1, pre, ff, fo, m2, r2 = sv
             ln2, ln1 = lyr.output.LayerNorm, lyr.attention.output.LayerNorm
-            d_fo = T.layernorm_bwd(dh, fo, ln2.weight, m2, r2, grad_target(ln2.weight), grad_target(ln2.bias))
+            d_fo = T.layernorm_bwd(dh, fo, ln2.weight, m2, r2, grad_target(ln2.weight), grad_target(ln2.bias),
+                                   dx_colsum=grad_target(lyr.output.dense.bias))
             ops.gemm_bf16(d_fo, ff, a_mn=True, b_mn=True, out=grad_target(lyr.output.dense.weight), split_k=0,
                           accumulate=True)
-            T.colsum_into(d_fo, grad_target(lyr.output.dense.bias))
             d_pre = ops.gemm_bf16(d_fo, lyr.output.dense.weight._w16, b_mn=True, act=ops.ACT_DGELU, aux=pre)
             ops.gemm_bf16(d_pre, h1, a_mn=True, b_mn=True, out=grad_target(lyr.intermediate.dense.weight), split_k=0,
                           accumulate=True)
             T.colsum_into(d_pre, grad_target(lyr.intermediate.dense.bias))
             d_h1 = ops.gemm_bf16(d_pre, lyr.intermediate.dense.weight._w16, b_mn=True, add=d_fo)
-            d_ao = T.layernorm_bwd(d_h1, ao, ln1.weight, m1, r1, grad_target(ln1.weight), grad_target(ln1.bias))
+            d_ao = T.layernorm_bwd(d_h1, ao, ln1.weight, m1, r1, grad_target(ln1.weight), grad_target(ln1.bias),
+                                   dx_colsum=grad_target(lyr.attention.output.dense.bias))
             ops.gemm_bf16(d_ao, ctxv, a_mn=True, b_mn=True, out=grad_target(lyr.attention.output.dense.weight),
                           split_k=0, accumulate=True)
-            T.colsum_into(d_ao, grad_target(lyr.attention.output.dense.bias))
             d_ctx = ops.gemm_bf16(d_ao, lyr.attention.output.dense.weight._w16, b_mn=True)
-            d_qkv = T.attn_bwd(qkv, probs, d_ctx, b, l, heads)
             s = lyr.attention.self
             for p_ in (s.query.weight, s.key.weight, s.value.weight, s.query.bias, s.key.bias, s.value.bias):
                 grad_target(p_)
             wqkv, gqkv = store.fused([s.query.weight, s.key.weight, s.value.weight], 3 * d, d)
             _, gbqkv = store.fused([s.query.bias, s.key.bias, s.value.bias], 3 * d)
+            d_qkv = T.attn_bwd(qkv, probs, d_ctx, b, l, heads, dbias=gbqkv)
             ops.gemm_bf16(d_qkv, h_in, a_mn=True, b_mn=True, out=gqkv, split_k=0, accumulate=True)
-            T.colsum_into(d_qkv, gbqkv)
             dh = ops.gemm_bf16(d_qkv, wqkv, b_mn=True, add=d_ao)
         emb = bert.embeddings
         de = T.layernorm_bwd(dh, e, emb.LayerNorm.weight, m0, r0, grad_target(emb.LayerNorm.weight),

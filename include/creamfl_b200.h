@@ -175,9 +175,11 @@ int creamfl_maxpool_bwd(const void* dy_bf16, const void* idx_u8, int N, int H, i
 size_t creamfl_layernorm_bwd_workspace_bytes(int D);
 int creamfl_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, float eps, int R,
                           int D, int is_bf16, void* y, float* mean, float* rstd, void* stream);
+/* dx_colsum (optional, D floats, accumulated): column sums of dx = bias gradient of the linear layer whose output
+ * (plus residual) this LayerNorm normalises - saves a separate pass over dx */
 int creamfl_layernorm_bwd(const void* dy, const void* x, const void* res, const float* gamma, const float* mean,
                           const float* rstd, int R, int D, int is_bf16, void* dx, float* dgamma, float* dbeta,
-                          void* workspace, size_t workspace_bytes, void* stream);
+                          float* dx_colsum, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- out[n] += sum_m x[m, n]  (bias gradients) */
 int creamfl_colsum_bf16(const void* x_bf16, int M, int N, int64_t ld, float* out, void* stream);
@@ -193,8 +195,9 @@ int creamfl_embed_bwd(const int64_t* ids, const int64_t* token_type, const void*
  * ctx [B*L, H*64] bf16, probs [B, H, L, L] bf16 */
 int creamfl_attn_fwd(const void* qkv_bf16, const float* mask, int B, int L, int H, int head_dim, void* ctx_bf16,
                      void* probs_bf16, void* stream);
+/* dbias (optional, 3*H*64 floats, accumulated): column sums of dqkv = bias gradient of the fused q/k/v projection */
 int creamfl_attn_bwd(const void* qkv_bf16, const void* probs_bf16, const void* dctx_bf16, int B, int L, int H,
-                     int head_dim, void* dqkv_bf16, void* stream);
+                     int head_dim, void* dqkv_bf16, float* dbias, void* stream);
 
 /* ---- PIENet attention pooling over the P (= 49) positions of the final feature map (pie_model.py:28-40,61-67)
  * and global average pooling (image_encoder.py:56): x [B, P, C] bf16, h = tanh(x W1^T) [B, P, Hd] bf16 */

@@ -47,9 +47,9 @@ def pcme_direction_loss(anchors, candidates, shift, negative_scale) -> Dict[str,
     n = len(anchors)
     dist = pcme_pair_distance(anchors, candidates)
     logits = -negative_scale * dist + shift
-    matched = 2.0 * torch.eye(n, dtype=logits.dtype) - 1.0
+    matched = 2.0 * torch.eye(n, dtype=logits.dtype, device=logits.device) - 1.0
     nll = -(logits * matched - torch.logaddexp(logits, -logits))
-    eye = torch.eye(n, dtype=torch.bool)
+    eye = torch.eye(n, dtype=torch.bool, device=logits.device)
     pos = nll[eye].sum()
     neg = nll[~eye].sum()
     return {'loss': pos + neg, 'pos_loss': pos, 'neg_loss': neg}

@@ -188,7 +188,10 @@ def test_layernorm(T, r, d, dtype, with_res):
     tol = 4e-3 if dtype == torch.bfloat16 else 1e-5
     assert rel_l2(y, y64) < tol
     dg, db = torch.ones(d, device='cuda'), torch.ones(d, device='cuda')
-    dx = T.layernorm_bwd(dy.cuda(), x.cuda(), gamma.cuda(), mean, rstd, dg, db, res=res.cuda() if with_res else None)
+    dxs = torch.full((d,), 2.0, device='cuda')
+    dx = T.layernorm_bwd(dy.cuda(), x.cuda(), gamma.cuda(), mean, rstd, dg, db, res=res.cuda() if with_res else None,
+                         dx_colsum=dxs)
+    assert rel_l2(dxs - 2, xin.grad.sum(0)) < (2e-3 if dtype == torch.bfloat16 else 1e-4)
     assert rel_l2(dx, xin.grad) < (6e-3 if dtype == torch.bfloat16 else 1e-4)
     assert rel_l2(dg - 1, g64.grad) < 1e-4 and rel_l2(db - 1, b64.grad) < 1e-4
 
@@ -223,8 +226,10 @@ def test_attention(T, b, l, h):
     ctx, probs = T.attn_fwd(qkv.cuda(), mask.cuda(), b, l, h)
     assert rel_l2(ctx, ctx64) < 6e-3
     assert rel_l2(probs, p) < 4e-3
-    dqkv = T.attn_bwd(qkv.cuda(), probs, dctx.cuda(), b, l, h)
+    dbias = torch.ones(3 * h * 64, device='cuda')
+    dqkv = T.attn_bwd(qkv.cuda(), probs, dctx.cuda(), b, l, h, dbias=dbias)
     assert rel_l2(dqkv, q64.grad) < 1e-2
+    assert rel_l2(dbias - 1, q64.grad.sum(0)) < 1e-2
 
 
 def test_embeddings(T):
