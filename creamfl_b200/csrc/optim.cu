@@ -201,33 +201,31 @@ opt_update_kernel(const OptRow* __restrict__ rows, const OptTensor* __restrict__
   }
 }
 
-// K4: layer-view tensors only (rare): one block per tensor walks its rows; block 0 clears the gradient-norm
-// accumulator for the next step.
+// K4: rows of layer-view tensors (the layer view fires for a sizeable share of the large matrices, so this runs over
+// the row table like K3); block 0 clears the gradient-norm accumulator for the next step.
 __global__ void __launch_bounds__(kOptThreads)
-opt_layer_fix_kernel(const OptRow* __restrict__ rows, const OptTensor* __restrict__ tensors, int n_tensors,
-                     const float* __restrict__ hyper, const float* __restrict__ state, const int* __restrict__ flag,
-                     const float* __restrict__ tnorm, const float* __restrict__ layer_acc,
-                     double* __restrict__ total_gg) {
-  const int t = blockIdx.x;
-  if (t == 0 && threadIdx.x == 0) *total_gg = 0.0;
-  if (t >= n_tensors || flag[t] != 2) return;
+opt_layer_fix_kernel(const OptRow* __restrict__ rows, int n_rows, const float* __restrict__ hyper,
+                     const float* __restrict__ state, const int* __restrict__ flag, const float* __restrict__ tnorm,
+                     const float* __restrict__ layer_acc, double* __restrict__ total_gg) {
+  const int r = blockIdx.x;
+  if (r == 0 && threadIdx.x == 0) *total_gg = 0.0;
+  if (r >= n_rows) return;
+  const OptRow row = rows[r];
+  if (flag[row.tensor] != 2) return;
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], wd_ratio = hyper[6];
   const float step = state[0];
   const float bc1 = 1.0f - powf(b1, step), bc2 = 1.0f - powf(b2, step);
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   const float step_size = lr / bc1;
-  const float inv = 1.0f / (tnorm[t] + eps);
-  const float s = layer_acc[t] * inv * inv;
-  for (int r = tensors[t].row_begin; r < tensors[t].row_end; ++r) {
-    const OptRow row = rows[r];
-    for (int i = threadIdx.x; i < row.len; i += kOptThreads) {
-      float p = row.p[i];
-      const float u = row.m[i] / (sqrtf(row.v[i]) * inv_sqrt_bc2 + eps) - p * s;
-      if (wd > 0.f) p *= 1.0f - lr * wd * wd_ratio;
-      p = fmaf(-step_size, u, p);
-      row.p[i] = p;
-      if (row.shadow) row.shadow[i] = __float2bfloat16(p);
-    }
+  const float inv = 1.0f / (tnorm[row.tensor] + eps);
+  const float s = layer_acc[row.tensor] * inv * inv;
+  for (int i = threadIdx.x; i < row.len; i += kOptThreads) {
+    float p = row.p[i];
+    const float u = row.m[i] / (sqrtf(row.v[i]) * inv_sqrt_bc2 + eps) - p * s;
+    if (wd > 0.f) p *= 1.0f - lr * wd * wd_ratio;
+    p = fmaf(-step_size, u, p);
+    row.p[i] = p;
+    if (row.shadow) row.shadow[i] = __float2bfloat16(p);
   }
 }
 
@@ -242,7 +240,7 @@ int optimizer_step(const void* rows, int n_rows, const void* tensors, int n_tens
   opt_row_stats_kernel<<<n_rows, kOptThreads, 0, st>>>(r, t, n_rows, stats, total_gg);
   opt_decide_kernel<<<n_tensors, 256, 0, st>>>(t, n_tensors, stats, hyper, state, total_gg, flag, tnorm, layer_acc);
   opt_update_kernel<<<n_rows, kOptThreads, 0, st>>>(r, t, n_rows, stats, hyper, state, flag, tnorm, layer_acc);
-  opt_layer_fix_kernel<<<n_tensors, kOptThreads, 0, st>>>(r, t, n_tensors, hyper, state, flag, tnorm, layer_acc, total_gg);
+  opt_layer_fix_kernel<<<n_rows, kOptThreads, 0, st>>>(r, n_rows, hyper, state, flag, tnorm, layer_acc, total_gg);
   return check_launch("optimizer_step");
 }
 
