@@ -73,4 +73,4 @@ def test_server_train_step_matches_reference_step():
     # first Adam step moves every element by ~lr; the AdamP projection can add a component along the weight
     assert moved.max().item() <= 50 * lr
     # criterion parameters are optimised too (retrieval_trainer.py:62-63) but not clipped
-    assert server.criterion.shift.item() != 15.0 and abs(server.criterion.shift.item() - 15.0) <= lr * 1.001
+    assert server.criterion.shift.item() != 15.0 and abs(server.criterion.shift.item() - 15.0) <= lr + 2e-6  # 1 ulp at 15
