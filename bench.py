@@ -377,11 +377,10 @@ def cpu_mini_round(B, n_conw, seed=0):
     """The reference's per-round path on the host (fp32 torch, restated in oracle/): returns a closure running one
     mini-round with S = 1 at batch B, con_w at n_conw rows, and the number of public pairs it processes."""
     from oracle import torch_towers as RT, creamfl_oracle as O
-    from creamfl_b200.clients import GRUEncoderText
     torch.manual_seed(seed)
     server = RT.RefPCME('resnet101', D)
     client_img = RT.RefEncoderImage('resnet18', D)
-    client_txt = GRUEncoderText(VOCAB, 300, D)
+    client_txt = RT.RefGRUEncoderText(VOCAB, 300, D)
     shift = torch.nn.Parameter(torch.tensor(15.0))
     scale = torch.nn.Parameter(torch.tensor(15.0))
     s_params = list(server.parameters()) + [shift, scale]

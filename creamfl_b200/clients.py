@@ -1,95 +1,19 @@
 """Client-side models of the hot path.
 
 ClientPCME mirrors the multimodal client's PCME(ResNet18 + GRU) (src/networks/models/pcme.py with
-`config.not_bert = True`, forced at MMFL.py:163): the image tower runs on the creamfl_b200 kernels
-(towers.EncoderImage), the text tower (Embedding -> packed bi-GRU -> PIENet, caption_encoder.py:29-116) stays on
-torch / cuDNN for now - SURVEY.md 8f ranks the GRU kernel as next row f2.
+`config.not_bert = True`, forced at MMFL.py:163): the image tower (towers.EncoderImage) and the GRU text tower
+(text_towers.GRUEncoderText: Embedding -> packed bi-GRU -> PIENet, caption_encoder.py:29-116) both run on the
+creamfl_b200 kernels and share one flat parameter store.  ImageClient / TextClient mirror the unimodal clients
+(src/networks/resnet_client.py, src/networks/language_model.py).
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 import torch.nn as nn
-from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
 
 from . import ops, tower_ops as T
-from .towers import EncoderImage, ResNet, StoreMixin, ParamStore, _Linear, grad_target
-
-
-def get_pad_mask(max_length, lengths, set_pad_to_one=True):
-    """caption_encoder.py:19-26."""
-    ind = torch.arange(0, max_length).unsqueeze(0)
-    mask = (ind >= lengths.unsqueeze(1)) if set_pad_to_one else (ind < lengths.unsqueeze(1))
-    return mask
-
-
-class _TorchPIENet(nn.Module):
-    """pie_model.PIENet with the pad-mask path (text variant: d_in = 300, d_h = 150), plain torch."""
-
-    def __init__(self, d_in, d_out, d_h):
-        super().__init__()
-        self.attention = nn.Module()
-        self.attention.w_1 = nn.Linear(d_in, d_h, bias=False)
-        self.attention.w_2 = nn.Linear(d_h, 1, bias=False)
-        self.fc = nn.Linear(d_in, d_out)
-        self.layer_norm = nn.LayerNorm(d_out)
-        nn.init.xavier_uniform_(self.attention.w_1.weight)
-        nn.init.xavier_uniform_(self.attention.w_2.weight)
-        nn.init.xavier_uniform_(self.fc.weight)
-        nn.init.constant_(self.fc.bias, 0.0)
-
-    def forward(self, out, x, pad_mask):
-        attn = self.attention.w_2(torch.tanh(self.attention.w_1(x)))            # pie_model.py:30
-        attn = attn.masked_fill(pad_mask.unsqueeze(-1), float('-inf'))            # :31-34
-        attn = torch.softmax(attn, dim=1)
-        residual = torch.bmm(attn.transpose(1, 2), x).squeeze(1)                  # :37-39
-        residual = torch.sigmoid(self.fc(residual))                               # :63
-        return self.layer_norm(out + residual), attn, residual                    # :66
-
-
-class GRUEncoderText(nn.Module):
-    """caption_encoder.EncoderText (wemb_type None -> xavier init; GloVe vectors are data, not on the box)."""
-
-    def __init__(self, vocab_size, word_dim, embed_dim):
-        super().__init__()
-        self.embed_dim = embed_dim
-        self.embed = nn.Embedding(vocab_size, word_dim)
-        self.rnn = nn.GRU(word_dim, embed_dim // 2, bidirectional=True, batch_first=True)
-        self.pie_net = _TorchPIENet(word_dim, embed_dim, word_dim // 2)
-        nn.init.xavier_uniform_(self.embed.weight)
-        self._len_cache = {}
-
-    def _length_tensors(self, lengths_cpu, seq_len, device):
-        """Device-side gather index and pad mask for one length profile (cached: built once per profile, so a
-        CUDA-graph capture of the step contains no host-to-device copy)."""
-        key = (tuple(lengths_cpu.tolist()), seq_len, str(device))
-        hit = self._len_cache.get(key)
-        if hit is None:
-            idx = (lengths_cpu - 1).to(device).view(-1, 1, 1).expand(-1, 1, self.embed_dim).contiguous()
-            hit = (idx, get_pad_mask(seq_len, lengths_cpu, True).to(device))
-            if len(self._len_cache) > 64:
-                self._len_cache.clear()
-            self._len_cache[key] = hit
-        return hit
-
-    def __deepcopy__(self, memo):
-        import copy
-        new = self.__class__.__new__(self.__class__)
-        memo[id(self)] = new
-        for k, v in self.__dict__.items():
-            new.__dict__[k] = {} if k == '_len_cache' else copy.deepcopy(v, memo)
-        return new
-
-    def forward(self, x, lengths):
-        lengths_cpu = lengths.cpu() if torch.is_tensor(lengths) else torch.as_tensor(lengths)
-        wemb_out = self.embed(x)
-        packed = pack_padded_sequence(wemb_out, lengths_cpu, batch_first=True)
-        rnn_out, _ = self.rnn(packed)
-        padded, _ = pad_packed_sequence(rnn_out, batch_first=True, total_length=wemb_out.shape[1])
-        idx, pad_mask = self._length_tensors(lengths_cpu, wemb_out.shape[1], x.device)
-        out = torch.gather(padded, 1, idx).squeeze(1)                             # caption_encoder.py:99-101
-        out, attn, residual = self.pie_net(out, wemb_out, pad_mask)
-        return {'embedding': torch.nn.functional.normalize(out, p=2, dim=-1)}     # :109
+from .text_towers import GRUEncoderText, TextClient  # noqa: F401  (re-exported: src/networks/language_model.py)
+from .towers import EncoderImage, ResNet, StoreMixin, _Linear, grad_target
 
 
 class ClientPCME(StoreMixin, nn.Module):
@@ -102,13 +26,11 @@ class ClientPCME(StoreMixin, nn.Module):
         self.img_enc = EncoderImage({'embed_dim': embed_dim, 'cnn_type': cnn_type})
         self.txt_enc = GRUEncoderText(vocab_size, word_dim, embed_dim)
 
-    def store(self) -> ParamStore:       # only the CUDA image tower lives in the flat store
-        st = self.__dict__.get('_store')
-        first = next(self.img_enc.parameters())
-        if st is None or not st.intact() or st.params[0] is not first:
-            st = ParamStore(self.img_enc)
-            self.__dict__['_store'] = st
-        return st
+    def _adjacent_groups(self):
+        return self.txt_enc.adjacent_groups()
+
+    def _after_store_build(self, st):
+        self.txt_enc.bind(st)
 
     def image_forward(self, images):
         self.store()
@@ -123,8 +45,6 @@ class ClientPCME(StoreMixin, nn.Module):
         a.shadow.copy_(b.shadow)
         for (dst, _), (src, _) in zip(a.padded, b.padded):
             dst.copy_(src)
-        for p, q in zip(self.txt_enc.parameters(), other.txt_enc.parameters()):
-            p.copy_(q)
         for p, q in zip(self.buffers(), other.buffers()):
             p.copy_(q)
 
@@ -283,47 +203,9 @@ def unimodal_supervised_loss(model: ImageClient, inputs, labels, inter_distance:
 
 
 # ===================================================================================================== unimodal text client
-class TextClient(nn.Module):
-    """Mirror of src/networks/language_model.py EncoderText (:28-130): Embedding -> packed bi-GRU -> PIENet ->
-    `* scale` -> ReLU -> classifier heads (training) or L2-normalised embedding.  Runs on torch / cuDNN (SURVEY 8f-f2:
-    the GRU kernel is the next row); the losses on top of it use the creamfl_b200 kernels."""
-
-    def __init__(self, vocab_size=11755, word_dim=300, embed_dim=256, num_class=4, scale=128):
-        super().__init__()
-        self.embed_dim = embed_dim
-        self.embed = nn.Embedding(vocab_size, word_dim)
-        self.rnn = nn.GRU(word_dim, embed_dim // 2, bidirectional=True, batch_first=True)
-        self.pie_net = _TorchPIENet(word_dim, embed_dim, word_dim // 2)
-        self.class_fc = nn.Linear(embed_dim, num_class)
-        self.class_fc_2 = nn.Linear(embed_dim, 80)
-        nn.init.xavier_uniform_(self.embed.weight)
-        self.is_train, self.phase, self.scale = True, '', scale
-        self._len_cache = {}
-
-    _length_tensors = GRUEncoderText._length_tensors
-
-    def forward(self, x, lengths):
-        lengths_cpu = lengths.cpu() if torch.is_tensor(lengths) else torch.as_tensor(lengths)
-        wemb_out = self.embed(x)
-        packed = pack_padded_sequence(wemb_out, lengths_cpu, batch_first=True)
-        rnn_out, _ = self.rnn(packed)
-        padded, _ = pad_packed_sequence(rnn_out, batch_first=True, total_length=wemb_out.shape[1])
-        idx, pad_mask = self._length_tensors(lengths_cpu, wemb_out.shape[1], x.device)
-        out = torch.gather(padded, 1, idx).squeeze(1)
-        out, _, _ = self.pie_net(out, wemb_out, pad_mask)
-        out = torch.relu(out * self.scale)                                     # language_model.py:111-112
-        if self.is_train:
-            w1 = torch.relu(self.class_fc.weight)                              # :115-121
-            self.class_fc.weight.data.clamp_(min=0)      # same values as `.data = relu(w)`, address kept (optimizer table)
-            w2 = torch.relu(self.class_fc_2.weight)
-            self.class_fc_2.weight.data.clamp_(min=0)
-            return self.class_fc(out), self.class_fc_2(out), w1, w2
-        return torch.nn.functional.normalize(out, p=2, dim=1)                  # :128
-
-
 def text_supervised_loss(model: TextClient, captions, lengths, labels, inter_distance: float = 4.0):
     """ClientTrainer.tra supervised pass for the text clients (ClientTrainer.py:335-356)."""
     fvec, _, class_weight, _ = model(captions, lengths)
     loss = ops.cross_entropy(fvec, labels, inter_distance)
-    center = ops.cross_entropy(torch.mm(class_weight, class_weight.t()), None, 0.0)
+    center = ops.cross_entropy(_GramFn.apply(class_weight), None, 0.0)
     return 0.5 * center + loss, fvec

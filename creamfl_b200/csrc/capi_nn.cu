@@ -359,4 +359,79 @@ int creamfl_optimizer_step(const void* rows, int n_rows, const void* tensors, in
                         S(stream));
 }
 
+// ---- GRU text towers (text_ops.cu)
+int creamfl_wemb_gather_fwd(const int64_t* ids, const float* table, int T, int V, int Dw, int pitch, void* out_bf16,
+                            void* stream) {
+  if (!ids || !table || !out_bf16) {
+    set_error("wemb_gather_fwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return wemb_gather_fwd(reinterpret_cast<const long long*>(ids), table, T, V, Dw, pitch, out_bf16, S(stream));
+}
+
+int creamfl_wemb_scatter_bwd(const int64_t* ids, const void* dx_bf16, int T, int V, int Dw, int pitch, float* dtable,
+                             void* stream) {
+  const void* dx = dx_bf16;
+  if (!ids || !dx || !dtable) {
+    set_error("wemb_scatter_bwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return wemb_scatter_bwd(reinterpret_cast<const long long*>(ids), dx, T, V, Dw, pitch, dtable, S(stream));
+}
+
+int creamfl_gru_fwd(const float* xproj, const float* w_hh, const float* b_hh, const int32_t* lengths, int B, int L,
+                    int H, int rev_steps, float* hseq, float* hlast, float* gates, void* stream) {
+  if (!xproj || !w_hh || !b_hh || !lengths || (!hseq && !hlast)) {
+    set_error("gru_fwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return gru_fwd(xproj, w_hh, b_hh, lengths, B, L, H, rev_steps, hseq, hlast, gates, S(stream));
+}
+
+int creamfl_gru_bwd(const float* gates, const float* hseq, const float* w_hh, const int32_t* lengths,
+                    const float* dhseq, const float* dhlast, int B, int L, int H, int rev_steps, void* dxp_bf16,
+                    void* dgh_bf16, void* hprev_bf16, void* stream) {
+  if (!gates || !hseq || !w_hh || !lengths || (!dhseq && !dhlast) || !dxp_bf16 || !dgh_bf16 || !hprev_bf16) {
+    set_error("gru_bwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return gru_bwd(gates, hseq, w_hh, lengths, dhseq, dhlast, B, L, H, rev_steps, dxp_bf16, dgh_bf16, hprev_bf16,
+                 S(stream));
+}
+
+int creamfl_seq_pool_fwd(const void* x, const void* h, const float* w2, const int32_t* lengths, int B, int L, int C,
+                         int pitch, int Hd, int hpitch, float* attn, void* r_bf16, void* stream) {
+  if (!x || !h || !w2 || !lengths || !attn || !r_bf16) {
+    set_error("seq_pool_fwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return seq_pool_fwd(x, h, w2, lengths, B, L, C, pitch, Hd, hpitch, attn, r_bf16, S(stream));
+}
+
+int creamfl_seq_pool_bwd(const void* x, const void* h, const float* w2, const float* attn, const void* d_r,
+                         const int32_t* lengths, int B, int L, int C, int pitch, int Hd, int hpitch, void* dx_bf16,
+                         void* dpre_bf16, float* dw2, void* stream) {
+  if (!x || !h || !w2 || !attn || !d_r || !lengths || !dx_bf16 || !dpre_bf16 || !dw2) {
+    set_error("seq_pool_bwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return seq_pool_bwd(x, h, w2, attn, d_r, lengths, B, L, C, pitch, Hd, hpitch, dx_bf16, dpre_bf16, dw2, S(stream));
+}
+
+int creamfl_scale_relu_fwd(const float* x, int64_t n, float scale, float* y, void* stream) {
+  if (!x || !y) {
+    set_error("scale_relu_fwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return scale_relu_fwd(x, n, scale, y, S(stream));
+}
+
+int creamfl_scale_relu_bwd(const float* dy, const float* y, int64_t n, float scale, float* dx, void* stream) {
+  if (!dy || !y || !dx) {
+    set_error("scale_relu_bwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return scale_relu_bwd(dy, y, n, scale, dx, S(stream));
+}
+
 }  // extern "C"

@@ -95,4 +95,17 @@ int avgpool_fwd(const void*, int, int, int, float, float*, void*, cudaStream_t);
 int avgpool_bwd(const void*, int, int, int, float, void*, cudaStream_t);
 int ce_fwd(const float*, long long, const long long*, int, int, float, float*, float*, float*, cudaStream_t);
 int relu_inplace(float*, void*, long long, cudaStream_t);
+// text_ops.cu
+int wemb_gather_fwd(const long long*, const float*, int, int, int, int, void*, cudaStream_t);
+int wemb_scatter_bwd(const long long*, const void*, int, int, int, int, float*, cudaStream_t);
+int gru_fwd(const float*, const float*, const float*, const int*, int, int, int, int, float*, float*, float*,
+            cudaStream_t);
+int gru_bwd(const float*, const float*, const float*, const int*, const float*, const float*, int, int, int, int, void*,
+            void*, void*, cudaStream_t);
+int seq_pool_fwd(const void*, const void*, const float*, const int*, int, int, int, int, int, int, float*, void*,
+                 cudaStream_t);
+int seq_pool_bwd(const void*, const void*, const float*, const float*, const void*, const int*, int, int, int, int, int,
+                 int, void*, void*, float*, cudaStream_t);
+int scale_relu_fwd(const float*, long long, float, float*, cudaStream_t);
+int scale_relu_bwd(const float*, const float*, long long, float, float*, cudaStream_t);
 }  // namespace cfl

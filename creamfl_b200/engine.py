@@ -179,7 +179,6 @@ class MMClient:
         self.use_graphs = use_graphs
         self._graphs = {}
         self.model = ClientPCME(vocab_size, embed_dim).to(self.device)
-        self.model.txt_enc.rnn.flatten_parameters()      # one contiguous cuDNN weight buffer; updated in place below
         self.criterion = get_criterion('pcme', PCME_CRITERION_CFG).to(self.device)
         self.model.store()
         params = [p for p in self.model.parameters() if p.requires_grad] + list(self.criterion.parameters())
@@ -193,7 +192,6 @@ class MMClient:
         place so that its addresses - and any captured graph - stay valid."""
         if self.old_model is None:
             self.old_model = copy.deepcopy(self.model).eval()
-            self.old_model.txt_enc.rnn.flatten_parameters()
             self.old_model.store()
         else:
             self.old_model.copy_weights_from(self.model)

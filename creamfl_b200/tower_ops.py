@@ -274,3 +274,83 @@ def avgpool_bwd(dy16, shape, scale=1.0):
 
 def relu_inplace(master, shadow):
     _chk(_lib.load().creamfl_relu_inplace(_p(master), _p(shadow), master.numel(), _stream()), "relu_inplace")
+
+
+# --------------------------------------------------------------------------------------------------- GRU text towers
+def pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def wemb_gather(ids, table, pitch):
+    """ids int64 [T] -> bf16 [T, pitch]: rows of the fp32 table, zero tail (pitch % 8 == 0 for TMA)."""
+    _need_cuda(ids, table)
+    t = ids.numel()
+    v, dw = table.shape
+    out = torch.empty((t, pitch), dtype=BF16, device=ids.device)
+    _chk(_lib.load().creamfl_wemb_gather_fwd(_p(ids), _p(table), t, v, dw, pitch, _p(out), _stream()),
+         "wemb_gather_fwd")
+    return out
+
+
+def wemb_scatter(ids, dx16, dtable):
+    """dtable[ids[t], :] += dx16[t, :Dw]  (dx16 bf16 [T, pitch])."""
+    if dx16.dtype != BF16:
+        raise TypeError('wemb_scatter: dx must be bf16')
+    t = ids.numel()
+    v, dw = dtable.shape
+    _chk(_lib.load().creamfl_wemb_scatter_bwd(_p(ids), _p(dx16), t, v, dw, dx16.stride(0), _p(dtable), _stream()),
+         "wemb_scatter_bwd")
+
+
+def gru_fwd(xproj, w_hh, b_hh, lengths32, b, l, h, rev_steps=0, want_seq=True, want_last=True, want_gates=True):
+    """xproj fp32 [B*L, 6H]; w_hh fp32 [2, 3H, H] (contiguous), b_hh fp32 [2*3H]; lengths int32 [B]."""
+    _need_cuda(xproj, w_hh, b_hh, lengths32)
+    dev = xproj.device
+    hseq = torch.empty((b, l, 2 * h), dtype=torch.float32, device=dev) if want_seq else None
+    hlast = torch.empty((b, 2 * h), dtype=torch.float32, device=dev) if want_last else None
+    gates = torch.empty((b, l, 2, 4, h), dtype=torch.float32, device=dev) if want_gates else None
+    _chk(_lib.load().creamfl_gru_fwd(_p(xproj), _p(w_hh), _p(b_hh), _p(lengths32), b, l, h, int(rev_steps), _p(hseq),
+                                     _p(hlast), _p(gates), _stream()), "gru_fwd")
+    return hseq, hlast, gates
+
+
+def gru_bwd(gates, hseq, w_hh, lengths32, dhseq, dhlast, b, l, h, rev_steps=0):
+    dev = gates.device
+    dxp = torch.empty((b * l, 6 * h), dtype=BF16, device=dev)
+    dgh = torch.empty((b * l, 6 * h), dtype=BF16, device=dev)
+    hprev = torch.empty((b * l, 2 * h), dtype=BF16, device=dev)
+    _chk(_lib.load().creamfl_gru_bwd(_p(gates), _p(hseq), _p(w_hh), _p(lengths32), _p(dhseq), _p(dhlast), b, l, h,
+                                     int(rev_steps), _p(dxp), _p(dgh), _p(hprev), _stream()), "gru_bwd")
+    return dxp, dgh, hprev
+
+
+def seq_pool_fwd(x, hid, w2, lengths32, c, hd):
+    """x bf16 [B, L, pitch] (c valid columns), hid bf16 [B, L, hpitch] (hd valid), w2 fp32 [hd]."""
+    b, l, pitch = x.shape
+    attn = torch.empty((b, l), dtype=torch.float32, device=x.device)
+    r = torch.empty((b, pitch), dtype=BF16, device=x.device)
+    _chk(_lib.load().creamfl_seq_pool_fwd(_p(x), _p(hid), _p(w2), _p(lengths32), b, l, c, pitch, hd, hid.shape[-1],
+                                          _p(attn), _p(r), _stream()), "seq_pool_fwd")
+    return attn, r
+
+
+def seq_pool_bwd(x, hid, w2, attn, d_r, lengths32, c, hd, dw2):
+    b, l, pitch = x.shape
+    dx = torch.empty_like(x)
+    dpre = torch.empty_like(hid)
+    _chk(_lib.load().creamfl_seq_pool_bwd(_p(x), _p(hid), _p(w2), _p(attn), _p(d_r), _p(lengths32), b, l, c, pitch, hd,
+                                          hid.shape[-1], _p(dx), _p(dpre), _p(dw2), _stream()), "seq_pool_bwd")
+    return dx, dpre
+
+
+def scale_relu_fwd(x, scale):
+    y = torch.empty_like(x)
+    _chk(_lib.load().creamfl_scale_relu_fwd(_p(x), x.numel(), float(scale), _p(y), _stream()), "scale_relu_fwd")
+    return y
+
+
+def scale_relu_bwd(dy, y, scale):
+    dx = torch.empty_like(y)
+    _chk(_lib.load().creamfl_scale_relu_bwd(_p(dy), _p(y), y.numel(), float(scale), _p(dx), _stream()),
+         "scale_relu_bwd")
+    return dx

@@ -28,6 +28,15 @@ BF16 = torch.bfloat16
 
 
 # ===================================================================================================== parameters
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _require_cuda(dev: torch.device) -> None:
+    if dev.type != 'cuda':
+        raise RuntimeError('creamfl_b200 towers run on CUDA only (no CPU fallback exists); call .cuda() first')
+
+
 class ParamStore:
     """All parameters of a model in one flat fp32 buffer, with a flat fp32 gradient buffer and a flat bf16 shadow.
 
@@ -50,8 +59,7 @@ class ParamStore:
         if not params:
             raise ValueError('ParamStore: module has no parameters')
         dev = params[0].device
-        if dev.type != 'cuda':
-            raise RuntimeError('creamfl_b200 towers run on CUDA only (no CPU fallback exists); call .cuda() first')
+        _require_cuda(dev)
         in_group = {id(p) for grp in adjacent for p in grp}
         offs, total = [], 0
         for p in params:
@@ -84,11 +92,30 @@ class ParamStore:
                 view = self.flat[off:off + n].view(p.shape)
                 gview = self.grad[off:off + n].view(p.shape)
                 p._w16 = self.shadow[off:off + n].view(p.shape)
+                if p.dim() == 2 and p.shape[1] % 8 and id(p) not in in_group:
+                    # K = 300 operands of the GRU text towers: row pitch padded to 16 bytes (TMA), rows to 8
+                    buf = torch.zeros((_pad8(p.shape[0]), _pad8(p.shape[1])), dtype=BF16, device=dev)
+                    self.padded.append((buf[:p.shape[0]], p._w16))
+                    p._w16, p._w16p = buf[:p.shape[0]], buf
                 p._g2d = gview
             view.copy_(p.data)
             p.data = view
             p._gview = gview
             p.grad = gview if p.requires_grad else None
+        # adjacent 2-D groups with an unaligned inner dimension share one padded operand (both directions of the
+        # GRU input projection -> one [6H, 304] matrix)
+        self.group_pad = {}
+        for grp in adjacent:
+            if all(p.dim() == 2 for p in grp) and len({p.shape[1] for p in grp}) == 1 and grp[0].shape[1] % 8:
+                rows, cols = sum(p.shape[0] for p in grp), grp[0].shape[1]
+                buf = torch.zeros((_pad8(rows), _pad8(cols)), dtype=BF16, device=dev)
+                r0 = 0
+                for p in grp:
+                    off = self.offsets[id(p)]
+                    self.padded.append((buf[r0:r0 + p.shape[0]], self.shadow[off:off + p.numel()].view(p.shape)))
+                    p._w16, p._w16p = buf[r0:r0 + p.shape[0]], buf
+                    r0 += p.shape[0]
+                self.group_pad[id(grp[0])] = buf[:rows]
         self.first_ptr = params[0].data_ptr()
         self.sync_shadow()
 
@@ -716,7 +743,7 @@ class PCME(StoreMixin, nn.Module):
         self.embed_dim = get('embed_dim')
         self.n_embeddings = get('n_samples_inference', 0) or 1
         if get('not_bert', False):
-            raise NotImplementedError('GRU text tower is served by creamfl_b200.clients (cuDNN GRU, SURVEY 8f-f2)')
+            raise NotImplementedError('the GRU text tower (config.not_bert) is served by creamfl_b200.clients.ClientPCME')
         self.img_enc = EncoderImage(config, mlp_local)
         self.txt_enc = BertEncoder()
         self.linear = _Linear(768, self.embed_dim)

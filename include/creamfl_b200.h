@@ -218,6 +218,45 @@ int creamfl_ce_fwd(const float* x, int64_t ldx, const int64_t* labels, int R, in
 /* in-place ReLU clamp of a parameter and its bf16 shadow (class_fc weights, resnet_client.py:193-197) */
 int creamfl_relu_inplace(float* x, void* shadow_bf16, int64_t n, void* stream);
 
+/* ---- GRU text towers of the clients (src/networks/models/caption_encoder.py:87-116 - the multimodal client's
+ * EncoderText; src/networks/language_model.py:93-130 - the unimodal text client).  The dense parts (x W_ih^T, PIENet
+ * w_1 / fc, all weight gradients) go through creamfl_gemm_bf16; these entry points are the rest.
+ * word embedding: out[t, 0:Dw] = bf16(table[ids[t]]), out[t, Dw:pitch] = 0 (pitch % 8 == 0: TMA row pitch);
+ * backward: dtable[ids[t], :] += dx[t, 0:Dw] (dx bf16 with row pitch `pitch`).  Replaces nn.Embedding
+ * (caption_encoder.py:41,90; language_model.py:40,96). */
+int creamfl_wemb_gather_fwd(const int64_t* ids, const float* table, int T, int V, int Dw, int pitch, void* out_bf16,
+                            void* stream);
+int creamfl_wemb_scatter_bwd(const int64_t* ids, const void* dx_bf16, int T, int V, int Dw, int pitch, float* dtable,
+                             void* stream);
+/* recurrent part of nn.GRU(bidirectional=True, batch_first=True) over pack_padded_sequence input
+ * (caption_encoder.py:93-97; language_model.py:99-103).  xproj [B, L, 2, 3H] fp32 = x W_ih^T + b_ih of both
+ * directions (gate order r, z, n); w_hh [2, 3H, H], b_hh [2, 3H] fp32; lengths int32 [B]; H in {32, 64, 128}.
+ * hseq [B, L, 2H] (optional) = pad_packed_sequence output (zeros past each length); hlast [B, 2H] (optional) =
+ * hseq[b, len_b - 1, :] (the gather of caption_encoder.py:99-101); gates [B, L, 2, 4, H] (optional) = r, z, n and
+ * W_hn h + b_hn kept for the backward.  rev_steps > 0 runs only the first rev_steps steps of the reverse
+ * direction (1 is all the hlast consumer needs); 0 = the full sequence. */
+int creamfl_gru_fwd(const float* xproj, const float* w_hh, const float* b_hh, const int32_t* lengths, int B, int L,
+                    int H, int rev_steps, float* hseq, float* hlast, float* gates, void* stream);
+/* backward through time given d(hseq) and / or d(hlast).  Outputs (bf16, zero where no step ran):
+ * dxp [B*L, 2, 3H] = gradient at xproj; dgh [B*L, 2, 3H] = gradient at W_hh h + b_hh; hprev [B*L, 2, H] = the state
+ * each step started from.  dW_ih = dxp^T x, dW_hh = dgh^T hprev, dx = dxp W_ih follow as creamfl_gemm_bf16 calls,
+ * db_ih / db_hh as creamfl_colsum_bf16. */
+int creamfl_gru_bwd(const float* gates, const float* hseq, const float* w_hh, const int32_t* lengths,
+                    const float* dhseq, const float* dhlast, int B, int L, int H, int rev_steps, void* dxp_bf16,
+                    void* dgh_bf16, void* hprev_bf16, void* stream);
+/* PIENet attention pooling over the words of a caption with the pad mask (pie_model.py:28-40 with mask):
+ * x [B, L, pitch] bf16 (C valid columns), h = tanh(x W1^T) [B, L, hpitch] bf16 (Hd valid columns), w2 [Hd];
+ * attn [B, L] fp32 = softmax over p < len_b (0 at pad positions), r [B, pitch] bf16 = sum_p attn[p] x[p, :]. */
+int creamfl_seq_pool_fwd(const void* x_bf16, const void* h_bf16, const float* w2, const int32_t* lengths, int B, int L,
+                         int C, int pitch, int Hd, int hpitch, float* attn, void* r_bf16, void* stream);
+/* dx [B, L, pitch] = attn[p] d_r;  dpre [B, L, hpitch] = gradient at the tanh pre-activation;  dw2 [Hd] accumulated */
+int creamfl_seq_pool_bwd(const void* x_bf16, const void* h_bf16, const float* w2, const float* attn,
+                         const void* d_r_bf16, const int32_t* lengths, int B, int L, int C, int pitch, int Hd,
+                         int hpitch, void* dx_bf16, void* dpre_bf16, float* dw2, void* stream);
+/* y = relu(x * scale) (language_model.py:111-112) and dx = dy * scale * (y > 0) */
+int creamfl_scale_relu_fwd(const float* x, int64_t n, float scale, float* y, void* stream);
+int creamfl_scale_relu_bwd(const float* dy, const float* y, int64_t n, float scale, float* dx, void* stream);
+
 /* ---- fused optimizer step: global-norm clipping + AdamP / Adam / SGD-momentum + bf16 shadow refresh in four
  * launches for any number of tensors.  Replaces adamp.AdamP.step (third-party adamp==0.3.0, call site
  * src/algorithms/optimizers.py:24-28), clip_grad_norm_ (retrieval_trainer.py:211-214) and torch.optim.SGD

@@ -176,3 +176,94 @@ def ref_unimodal_supervised_loss(model, inputs, labels, num_class, inter_distanc
     loss = F.cross_entropy(fvec, labels)
     center = F.cross_entropy(class_weight @ class_weight.t(), torch.arange(num_class, device=fvec.device))
     return 0.5 * center + loss, fvec
+
+
+# ===================================================================================================== GRU text towers
+def get_pad_mask(max_length, lengths, set_pad_to_one=True):
+    """reference src/networks/models/caption_encoder.py:19-26."""
+    ind = torch.arange(0, max_length).unsqueeze(0)
+    mask = (ind >= lengths.unsqueeze(1)) if set_pad_to_one else (ind < lengths.unsqueeze(1))
+    return mask
+
+
+class RefMaskedPIENet(nn.Module):
+    """reference pie_model.PIENet with the pad-mask path (text variant: d_in = 300, d_h = 150; pie_model.py:28-40,
+    61-67, dropout 0)."""
+
+    def __init__(self, d_in, d_out, d_h):
+        super().__init__()
+        self.attention = nn.Module()
+        self.attention.w_1 = nn.Linear(d_in, d_h, bias=False)
+        self.attention.w_2 = nn.Linear(d_h, 1, bias=False)
+        self.fc = nn.Linear(d_in, d_out)
+        self.layer_norm = nn.LayerNorm(d_out)
+        nn.init.xavier_uniform_(self.attention.w_1.weight)
+        nn.init.xavier_uniform_(self.attention.w_2.weight)
+        nn.init.xavier_uniform_(self.fc.weight)
+        nn.init.constant_(self.fc.bias, 0.0)
+
+    def forward(self, out, x, pad_mask):
+        attn = self.attention.w_2(torch.tanh(self.attention.w_1(x)))            # pie_model.py:30
+        attn = attn.masked_fill(pad_mask.unsqueeze(-1), float('-inf'))            # :31-34
+        attn = torch.softmax(attn, dim=1)                                         # :35
+        residual = torch.bmm(attn.transpose(1, 2), x).squeeze(1)                  # :37-39
+        residual = torch.sigmoid(self.fc(residual))                               # :63
+        return self.layer_norm(out + residual), attn, residual                    # :66
+
+
+class RefGRUEncoderText(nn.Module):
+    """reference src/networks/models/caption_encoder.py:29-116 (wemb_type None -> xavier init; mlp_local False)."""
+
+    def __init__(self, vocab_size, word_dim, embed_dim):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.embed = nn.Embedding(vocab_size, word_dim)
+        self.rnn = nn.GRU(word_dim, embed_dim // 2, bidirectional=True, batch_first=True)
+        self.pie_net = RefMaskedPIENet(word_dim, embed_dim, word_dim // 2)
+        nn.init.xavier_uniform_(self.embed.weight)
+
+    def trunk(self, x, lengths):
+        from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+        lengths = lengths.cpu() if torch.is_tensor(lengths) else torch.as_tensor(lengths)
+        wemb_out = self.embed(x)                                                  # caption_encoder.py:90
+        packed = pack_padded_sequence(wemb_out, lengths, batch_first=True)        # :93
+        rnn_out, _ = self.rnn(packed)                                             # :96
+        padded, _ = pad_packed_sequence(rnn_out, batch_first=True, total_length=wemb_out.shape[1])   # :97
+        idx = (lengths - 1).to(x.device).view(-1, 1, 1).expand(-1, 1, self.embed_dim)
+        out = torch.gather(padded, 1, idx).squeeze(1)                             # :99-101
+        pad_mask = get_pad_mask(wemb_out.shape[1], lengths, True).to(x.device)    # :105
+        out, attn, residual = self.pie_net(out, wemb_out, pad_mask)               # :107
+        return out
+
+    def forward(self, x, lengths):
+        return {'embedding': l2_normalize(self.trunk(x, lengths))}                # :109
+
+
+class RefTextClient(RefGRUEncoderText):
+    """reference src/networks/language_model.py:28-130 (vocabulary size passed in instead of the pickled vocab)."""
+
+    def __init__(self, vocab_size=11755, word_dim=300, embed_dim=256, num_class=4, scale=128):
+        super().__init__(vocab_size, word_dim, embed_dim)
+        self.class_fc = nn.Linear(embed_dim, num_class)
+        self.class_fc_2 = nn.Linear(embed_dim, 80)
+        self.is_train, self.phase, self.scale = True, '', scale
+
+    def forward(self, x, lengths):
+        out = torch.relu(self.trunk(x, lengths) * self.scale)                     # language_model.py:111-112
+        if self.is_train:
+            w1 = torch.relu(self.class_fc.weight)                                 # :115-121
+            self.class_fc.weight.data = w1.detach().clone()
+            w2 = torch.relu(self.class_fc_2.weight)
+            self.class_fc_2.weight.data = w2.detach().clone()
+            return self.class_fc(out), self.class_fc_2(out), w1, w2
+        return F.normalize(out, p=2, dim=1)                                       # :128
+
+
+def ref_text_supervised_loss(model, captions, lengths, labels, num_class, inter_distance=4.0):
+    """reference src/algorithms/ClientTrainer.py:335-355 for the text clients."""
+    fvec, _, class_weight, _ = model(captions, lengths)
+    onehot = F.one_hot(labels, num_class).to(fvec.dtype)
+    fvec = fvec - inter_distance * onehot
+    loss = F.cross_entropy(fvec, labels)
+    center = F.cross_entropy(class_weight @ class_weight.t(), torch.arange(num_class, device=fvec.device))
+    return 0.5 * center + loss, fvec

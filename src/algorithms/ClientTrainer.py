@@ -37,15 +37,13 @@ class ClientTrainer:
         else:
             self.model = TextClient(embed_dim=self.args.feature_dim, num_class=self.classSize,
                                     scale=self.scale).to(self.device)
-            self.model.rnn.flatten_parameters()
+            self.model.store()
             self.optimizer = FusedOptimizer(self.model.parameters(), lr=self.init_lr, momentum=0.9, weight_decay=5e-5,
-                                            mode='sgd')
+                                            mode='sgd').attach_stores(self.model)
 
     def run(self, global_img_feature, global_txt_feature, distill_index, global_train_loader):
         self.old_model = copy.deepcopy(self.model)
         self.old_model.eval()
-        if not self.is_image:
-            self.old_model.rnn.flatten_parameters()
         for _ in range(self.local_epochs):
             self.local_epoch += 1
             self.tra(global_img_feature, global_txt_feature, distill_index, global_train_loader)

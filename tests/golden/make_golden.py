@@ -456,7 +456,65 @@ def case_towers():
     np.savez_compressed(OUT / 'towers.npz', **out)
 
 
-CASES = {'towers': case_towers, 'pcme': case_pcme, 'mm_contrast': case_mm_contrast, 'uni_contrast': case_uni_contrast,
+def case_text_towers():
+    """The reference's own GRU text towers - caption_encoder.EncoderText (multimodal client) and
+    language_model.EncoderText (unimodal text client) - on deterministic weights and ragged, length-sorted captions:
+    pins RefGRUEncoderText / RefTextClient of oracle/torch_towers.py (forward values and parameter gradients)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('oracle_torch_towers', OUT.parent.parent / 'oracle' / 'torch_towers.py')
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    fill_deterministic = mod.fill_deterministic
+    import src.networks.models.caption_encoder as ce
+    vocab = 500
+    word2idx = {f'w{i}': i for i in range(vocab)}
+    opt = Munch(wemb_type=None, word_dim=300, embed_dim=64, cache_dir='')
+    enc = ce.EncoderText(word2idx, opt, False)
+    fill_deterministic(enc, seed=41)
+    g = torch.Generator().manual_seed(42)
+    lengths = torch.tensor([9, 9, 7, 4, 2, 1])
+    x = torch.randint(4, vocab, (6, 9), generator=g)
+    for i, n in enumerate(lengths.tolist()):
+        x[i, n:] = 0
+    coef = torch.randn(6, 64, generator=g)
+    enc.train()
+    emb = enc(x, lengths)['embedding']
+    (emb * coef).sum().backward()
+    names = ['embed.weight', 'rnn.weight_ih_l0', 'rnn.weight_hh_l0', 'rnn.bias_ih_l0', 'rnn.bias_hh_l0',
+             'rnn.weight_ih_l0_reverse', 'rnn.weight_hh_l0_reverse', 'rnn.bias_ih_l0_reverse', 'rnn.bias_hh_l0_reverse',
+             'pie_net.attention.w_1.weight', 'pie_net.attention.w_2.weight', 'pie_net.fc.weight', 'pie_net.fc.bias',
+             'pie_net.layer_norm.weight', 'pie_net.layer_norm.bias']
+    params = dict(enc.named_parameters())
+    out = {'x': x.numpy(), 'lengths': lengths.numpy(), 'coef': coef.numpy(), 'mm_embedding': emb.detach().numpy()}
+    for nme in names:
+        gr = params[nme].grad
+        out['mm_grad.' + nme] = (gr if gr is not None else torch.zeros_like(params[nme])).numpy()
+    # unimodal text client (opens src/datasets/vocabs/coco_vocab.pkl relative to the reference root: 11755 words)
+    import src.networks.language_model as lm
+    client = lm.EncoderText(wemb_type=None, word_dim=300, embed_dim=64, num_class=4, scale=128)
+    fill_deterministic(client, seed=43)
+    xv = x.clone()
+    client.train()
+    x1, x2, w1, w2 = client(xv, lengths)
+    labels = torch.tensor([0, 3, 1, 2, 2, 0])
+    onehot = torch.nn.functional.one_hot(labels, 4).float()
+    loss = torch.nn.functional.cross_entropy(x1 - 4.0 * onehot, labels) + \
+        0.5 * torch.nn.functional.cross_entropy(w1 @ w1.t(), torch.arange(4))        # ClientTrainer.py:344-355
+    loss.backward()
+    cparams = dict(client.named_parameters())
+    out.update({'uni_x1': x1.detach().numpy(), 'uni_x2': x2.detach().numpy(), 'uni_loss': np.float64(loss.item()),
+                'uni_labels': labels.numpy(), 'uni_vocab': np.int64(client.embed.weight.shape[0]),
+                'uni_w_min': np.float64(min(w1.min().item(), w2.min().item()))})
+    for nme in ['rnn.weight_hh_l0', 'rnn.weight_ih_l0_reverse', 'pie_net.fc.weight', 'class_fc.weight', 'class_fc.bias']:
+        out['uni_grad.' + nme] = cparams[nme].grad.numpy()
+    out['uni_grad_embed_rows'] = cparams['embed.weight'].grad[:vocab].numpy()
+    client.is_train = False
+    with torch.no_grad():
+        out['uni_embedding'] = client(xv, lengths).numpy()
+    np.savez_compressed(OUT / 'text_towers.npz', **out)
+
+
+CASES = {'towers': case_towers, 'text_towers': case_text_towers, 'pcme': case_pcme, 'mm_contrast': case_mm_contrast, 'uni_contrast': case_uni_contrast,
          'recall': case_recall, 'partition': case_partition, 'conw': case_conw}
 
 if __name__ == '__main__':

@@ -1,0 +1,353 @@
+"""GPU parity tests of the GRU text towers (csrc/text_ops.cu + creamfl_b200/text_towers.py) through the C ABI.
+
+Oracles: torch nn.GRU / the restated towers of oracle/torch_towers.py (pinned against the reference's own
+caption_encoder.EncoderText and language_model.EncoderText by tests/golden/text_towers.npz), run on the CPU in fp32/64.
+
+Tolerances
+  * recurrent kernel, fp32 in / fp32 out, same operands on both sides: max abs 2e-5 over <= 40 steps
+  * backward kernel outputs are bf16 (operands of the weight-gradient GEMMs): rel-L2 <= 6e-3 (2^-9 rounding + fp32 chain)
+  * embedding gather: exact bf16 rounding; scatter: fp32 atomics, rel 1e-5
+  * towers (bf16 operands, fp32 accumulation): embeddings cos >= 0.9995, gradients rel-L2 <= 3e-2; unimodal client
+    (logits in the hundreds through `* 128`): gradients rel-L2 <= 1e-1, see tests/test_cpu_text_tower_host.py
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF16 = torch.bfloat16
+
+
+@pytest.fixture(scope='module')
+def env():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from creamfl_b200 import clients, ops, optim, text_towers, tower_ops
+    from oracle import torch_towers
+    return clients, ops, optim, text_towers, tower_ops, torch_towers
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def gru_reference(xproj, w_hh, b_hh, lengths, rev_steps=0):
+    """Packed bidirectional GRU given the input projections, plain torch (autograd-capable), PyTorch gate order.
+    xproj [B, L, 2, 3H]; returns hseq [B, L, 2H] (zeros past each length)."""
+    b, l, _, h3 = xproj.shape
+    h = h3 // 3
+    rows = []
+    for bi in range(b):
+        ln = int(lengths[bi])
+        outs = [[None] * l, [None] * l]
+        for d in range(2):
+            nst = rev_steps if (d == 1 and 0 < rev_steps < ln) else ln
+            hs = torch.zeros(h, dtype=xproj.dtype)
+            for s in range(nst):
+                t = s if d == 0 else ln - 1 - s
+                gh = w_hh[d] @ hs + b_hh[d]
+                x = xproj[bi, t, d]
+                r = torch.sigmoid(x[:h] + gh[:h])
+                z = torch.sigmoid(x[h:2 * h] + gh[h:2 * h])
+                n = torch.tanh(x[2 * h:] + r * gh[2 * h:])
+                hs = (1 - z) * n + z * hs
+                outs[d][t] = hs
+        zero = torch.zeros(h, dtype=xproj.dtype)
+        rows.append(torch.stack([torch.cat([outs[0][t] if outs[0][t] is not None else zero,
+                                            outs[1][t] if outs[1][t] is not None else zero]) for t in range(l)]))
+    return torch.stack(rows)
+
+
+def _gru_case(b, l, h, seed):
+    g = torch.Generator().manual_seed(seed)
+    lengths = torch.sort(torch.randint(1, l + 1, (b,), generator=g), descending=True).values
+    lengths[0] = l
+    xproj = torch.randn(b, l, 2, 3 * h, generator=g)
+    w_hh = torch.randn(2, 3 * h, h, generator=g) / h ** 0.5
+    b_hh = 0.1 * torch.randn(2, 3 * h, generator=g)
+    return lengths, xproj, w_hh, b_hh
+
+
+@pytest.mark.parametrize('b,l,h', [(6, 9, 32), (13, 17, 64), (128, 32, 128), (5, 40, 128)])
+def test_gru_fwd_matches_torch_gru(env, b, l, h):
+    """Full bidirectional recurrence (rev_steps = 0) against torch.nn.GRU on a packed batch."""
+    *_, T, _ = env
+    from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+    lengths, xproj, w_hh, b_hh = _gru_case(b, l, h, 100 + b)
+    g = torch.Generator().manual_seed(7)
+    din = 20
+    x = torch.randn(b, l, din, generator=g)
+    gru = torch.nn.GRU(din, h, bidirectional=True, batch_first=True)
+    with torch.no_grad():
+        gru.weight_hh_l0.copy_(w_hh[0]); gru.weight_hh_l0_reverse.copy_(w_hh[1])
+        gru.bias_hh_l0.copy_(b_hh[0]); gru.bias_hh_l0_reverse.copy_(b_hh[1])
+        xp = torch.stack([x @ gru.weight_ih_l0.t() + gru.bias_ih_l0,
+                          x @ gru.weight_ih_l0_reverse.t() + gru.bias_ih_l0_reverse], dim=2)      # [B, L, 2, 3H]
+        out, _ = gru(pack_padded_sequence(x, lengths, batch_first=True))
+        want, _ = pad_packed_sequence(out, batch_first=True, total_length=l)
+    hseq, hlast, gates = T.gru_fwd(xp.reshape(b * l, 6 * h).contiguous().cuda(), w_hh.cuda().contiguous(),
+                                   b_hh.reshape(-1).cuda(), lengths.to(torch.int32).cuda(), b, l, h)
+    torch.cuda.synchronize()
+    assert (hseq.cpu() - want).abs().max().item() < 2e-5
+    idx = (lengths - 1).view(-1, 1, 1).expand(-1, 1, 2 * h)
+    assert (hlast.cpu() - want.gather(1, idx).squeeze(1)).abs().max().item() < 2e-5
+    # rev_steps = 1: forward direction unchanged, reverse direction only at t = len - 1; same hlast
+    hseq1, hlast1, _ = T.gru_fwd(xp.reshape(b * l, 6 * h).contiguous().cuda(), w_hh.cuda().contiguous(),
+                                 b_hh.reshape(-1).cuda(), lengths.to(torch.int32).cuda(), b, l, h, rev_steps=1)
+    assert torch.equal(hlast1, hlast) and torch.equal(hseq1[:, :, :h], hseq[:, :, :h])
+    only_last = torch.zeros_like(want[:, :, h:])
+    for i, n in enumerate(lengths.tolist()):
+        only_last[i, n - 1] = want[i, n - 1, h:]
+    assert (hseq1[:, :, h:].cpu() - only_last).abs().max().item() < 2e-5
+    # the saved gate tensor holds r, z, n in (0,1) / (-1,1)
+    assert gates.shape == (b, l, 2, 4, h)
+
+
+@pytest.mark.parametrize('b,l,h,rev_steps,use_last', [(6, 9, 32, 0, False), (13, 17, 64, 0, True), (64, 24, 128, 1, True),
+                                                      (7, 30, 128, 0, False)])
+def test_gru_bwd_matches_autograd(env, b, l, h, rev_steps, use_last):
+    *_, T, _ = env
+    lengths, xproj, w_hh, b_hh = _gru_case(b, l, h, 200 + b)
+    g = torch.Generator().manual_seed(8)
+    dhseq = torch.randn(b, l, 2 * h, generator=g)
+    dhlast = torch.randn(b, 2 * h, generator=g) if use_last else None
+    xo, wo, bo = (t.double().requires_grad_(True) for t in (xproj, w_hh, b_hh))
+    hs = gru_reference(xo, wo, bo, lengths, rev_steps)
+    loss = (hs * dhseq.double()).sum()
+    if use_last:
+        idx = (lengths - 1).view(-1, 1, 1).expand(-1, 1, 2 * h)
+        loss = loss + (hs.gather(1, idx).squeeze(1) * dhlast.double()).sum()
+    loss.backward()
+    len32 = lengths.to(torch.int32).cuda()
+    xp_d = xproj.reshape(b * l, 6 * h).contiguous().cuda()
+    hseq, _, gates = T.gru_fwd(xp_d, w_hh.cuda().contiguous(), b_hh.reshape(-1).cuda(), len32, b, l, h,
+                               rev_steps=rev_steps)
+    assert (hseq.cpu().double() - hs.detach()).abs().max().item() < 2e-5
+    dxp, dgh, hprev = T.gru_bwd(gates, hseq, w_hh.cuda().contiguous(), len32, dhseq.cuda(),
+                                dhlast.cuda() if use_last else None, b, l, h, rev_steps=rev_steps)
+    torch.cuda.synchronize()
+    assert dxp.dtype == BF16 and dxp.shape == (b * l, 6 * h)
+    assert rel(dxp.view(b, l, 2, 3 * h), xo.grad) < 6e-3
+    # dW_hh = dgh^T hprev and db_hh = colsum(dgh), formed in fp64 from the kernel's bf16 outputs
+    dgh_v, hp_v = dgh.view(b * l, 2, 3 * h).double().cpu(), hprev.view(b * l, 2, h).double().cpu()
+    for d in range(2):
+        dw = dgh_v[:, d].t() @ hp_v[:, d]
+        if wo.grad[d].abs().max() == 0:
+            assert dw.abs().max() == 0
+        else:
+            assert rel(dw, wo.grad[d]) < 8e-3
+        assert rel(dgh_v[:, d].sum(0), bo.grad[d]) < 8e-3
+
+
+def test_gru_rejects_unsupported_hidden_size(env):
+    *_, T, _ = env
+    with pytest.raises(RuntimeError, match='hidden size'):
+        T.gru_fwd(torch.zeros(4, 6 * 256, device='cuda'), torch.zeros(2, 768, 256, device='cuda'),
+                  torch.zeros(1536, device='cuda'), torch.ones(2, dtype=torch.int32, device='cuda'), 2, 2, 256)
+
+
+def test_word_embedding_gather_and_scatter(env):
+    *_, T, _ = env
+    g = torch.Generator().manual_seed(3)
+    table = torch.randn(97, 300, generator=g)
+    ids = torch.randint(0, 97, (53,), generator=g)
+    out = T.wemb_gather(ids.cuda(), table.cuda(), 304)
+    assert torch.equal(out[:, :300].cpu(), table[ids].to(BF16)) and float(out[:, 300:].abs().max()) == 0.0
+    dx = torch.randn(53, 304, generator=g).to(BF16)
+    dtab = torch.zeros(97, 300, device='cuda')
+    T.wemb_scatter(ids.cuda(), dx.cuda(), dtab)
+    want = torch.zeros(97, 300, dtype=torch.float64).index_add_(0, ids, dx[:, :300].double())
+    assert rel(dtab, want) < 1e-5
+
+
+@pytest.mark.parametrize('b,l', [(6, 9), (128, 32), (3, 130)])
+def test_masked_sequence_pooling(env, b, l):
+    *_, T, _ = env
+    g = torch.Generator().manual_seed(b * l)
+    c, hd = 300, 150
+    lengths = torch.sort(torch.randint(1, l + 1, (b,), generator=g), descending=True).values
+    x = torch.zeros(b, l, 304); x[:, :, :c] = torch.randn(b, l, c, generator=g)
+    hid = torch.zeros(b, l, 152); hid[:, :, :hd] = torch.tanh(torch.randn(b, l, hd, generator=g))
+    w2 = torch.randn(hd, generator=g) * 0.3
+    x16, h16 = x.to(BF16), hid.to(BF16)
+    xo, ho, wo = x16.double().requires_grad_(True), h16.double().requires_grad_(True), w2.double().requires_grad_(True)
+    a = ho[:, :, :hd] @ wo
+    mask = torch.arange(l).unsqueeze(0) >= lengths.unsqueeze(1)
+    a = torch.softmax(a.masked_fill(mask, float('-inf')), dim=1)              # pie_model.py:31-35
+    r = torch.bmm(a.unsqueeze(1), xo).squeeze(1)
+    d_r = torch.zeros(b, 304); d_r[:, :c] = torch.randn(b, c, generator=g)
+    d_r16 = d_r.to(BF16)
+    (r * d_r16.double()).sum().backward()
+    len32 = lengths.to(torch.int32).cuda()
+    attn, r16 = T.seq_pool_fwd(x16.cuda(), h16.cuda(), w2.cuda(), len32, c, hd)
+    assert (attn.cpu().double() - a.detach()).abs().max().item() < 1e-5
+    assert rel(r16, r.detach()) < 4e-3 and float(r16[:, c:].abs().max()) == 0.0
+    dw2 = torch.zeros(hd, device='cuda')
+    dx, dpre = T.seq_pool_bwd(x16.cuda(), h16.cuda(), w2.cuda(), attn, d_r16.cuda(), len32, c, hd, dw2)
+    torch.cuda.synchronize()
+    # dx here is the pooling path only (attn * d_r); the score path reaches x through dpre and the w_1 GEMM
+    want_dx = a.detach().unsqueeze(-1) * d_r16.double().unsqueeze(1)
+    assert rel(dx, want_dx) < 4e-3
+    # dpre = d(loss)/d(pre-tanh) = d(loss)/d(hid) * (1 - hid^2)
+    want_dpre = ho.grad * (1 - h16.double() ** 2)
+    assert rel(dpre, want_dpre) < 6e-3
+    assert rel(dw2, wo.grad) < 1e-4
+
+
+def test_gemm_shapes_of_the_text_tower(env):
+    """The K = 300 (pitch 304) / N = 150 (pitch 152) operand shapes of the tower through creamfl_gemm_bf16."""
+    _, ops, *_ = env
+    g = torch.Generator().manual_seed(5)
+    t = 200
+    x = torch.zeros(t, 304); x[:, :300] = torch.randn(t, 300, generator=g) / 4
+    w1 = torch.zeros(152, 304); w1[:150, :300] = torch.randn(150, 300, generator=g) / 4
+    x16, w16 = x.to(BF16).cuda(), w1.to(BF16).cuda()
+    hid = ops.gemm_bf16(x16, w16, act=ops.ACT_TANH)
+    want = torch.tanh(x16.double().cpu() @ w16.double().cpu().t())
+    assert hid.shape == (t, 152) and rel(hid, want) < 4e-3 and float(hid[:, 150:].abs().max()) == 0.0
+    dpre = (torch.randn(t, 152, generator=g) / 4).to(BF16).cuda()
+    dpre[:, 150:] = 0
+    add = (torch.randn(t, 304, generator=g) / 4).to(BF16).cuda()
+    dx = ops.gemm_bf16(dpre, w16, b_mn=True, add=add)
+    assert rel(dx, dpre.double().cpu() @ w16.double().cpu() + add.double().cpu()) < 4e-3
+    gw = torch.zeros(150, 300, device='cuda')
+    ops.gemm_bf16(dpre[:, :150], x16, a_mn=True, b_mn=True, out=gw, split_k=0, accumulate=True, n_cols=300)
+    ops.gemm_bf16(dpre[:, :150], x16, a_mn=True, b_mn=True, out=gw, split_k=0, accumulate=True, n_cols=300)
+    assert rel(gw, 2 * (dpre[:, :150].double().cpu().t() @ x16[:, :300].double().cpu())) < 1e-5
+
+
+def _golden():
+    from pathlib import Path
+    return np.load(Path(__file__).resolve().parent / 'golden' / 'text_towers.npz', allow_pickle=False)
+
+
+def test_mm_text_tower_against_reference_golden(env):
+    """The committed golden vectors of the REFERENCE's caption_encoder.EncoderText (values and all parameter
+    gradients) against the CUDA tower."""
+    _, _, _, TT, _, RT = env
+    g = _golden()
+    x, lengths, coef = torch.from_numpy(g['x']), torch.from_numpy(g['lengths']), torch.from_numpy(g['coef'])
+    model = TT.TextModel(500, 300, 64)
+    RT.fill_deterministic(model.txt_enc, seed=41)
+    model = model.cuda().train()
+    st = model.store()
+    emb = model(x.cuda(), lengths)
+    cosv = F.cosine_similarity(emb.detach().double().cpu(), torch.from_numpy(g['mm_embedding']).double(), dim=-1)
+    assert float(cosv.min()) > 0.9995, cosv
+    st.zero_grad()
+    (emb * coef.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    for name, p in model.txt_enc.named_parameters():
+        ref = g['mm_grad.' + name]
+        if np.abs(ref).max() == 0.0:
+            assert float(p.grad.abs().max()) == 0.0, name
+        else:
+            assert rel(p.grad, ref) < 3e-2, (name, rel(p.grad, ref))
+
+
+def test_mm_text_tower_full_size_against_oracle(env):
+    """B = 128, L = 32, D = 256 (configs[1] client batch) against the torch restatement on the CPU."""
+    _, _, optim, TT, _, RT = env
+    g = torch.Generator().manual_seed(11)
+    b, l, vocab = 128, 32, 11755
+    lengths = torch.sort(torch.randint(5, 31, (b,), generator=g), descending=True).values
+    x = torch.randint(4, vocab, (b, l), generator=g)
+    for i, n in enumerate(lengths.tolist()):
+        x[i, n:] = 0
+    ref = RT.RefGRUEncoderText(vocab, 300, 256)
+    RT.fill_deterministic(ref, seed=12)
+    model = TT.TextModel(vocab, 300, 256)
+    missing = model.txt_enc.load_state_dict(ref.state_dict(), strict=True)
+    model = model.cuda().train()
+    st = model.store()
+    coef = torch.randn(b, 256, generator=g)
+    e_ref = ref(x, lengths)['embedding']
+    (e_ref * coef).sum().backward()
+    emb = model(x.cuda(), lengths)
+    st.zero_grad()
+    (emb * coef.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    cosv = F.cosine_similarity(emb.detach().double().cpu(), e_ref.detach().double(), dim=-1)
+    assert float(cosv.min()) > 0.9995
+    rp = dict(ref.named_parameters())
+    for name, p in model.txt_enc.named_parameters():
+        if rp[name].grad is None or rp[name].grad.abs().max() == 0:
+            assert float(p.grad.abs().max()) == 0.0, name
+        else:
+            assert rel(p.grad, rp[name].grad) < 3e-2, (name, rel(p.grad, rp[name].grad))
+    # eval / no-grad path and a fused AdamP step over the padded K = 300 shadows
+    with torch.no_grad():
+        e2 = model(x.cuda(), lengths)
+    assert torch.allclose(e2, emb.detach(), atol=1e-6)
+    opt = optim.FusedOptimizer(model.parameters(), lr=1e-3, max_norm=2.0, mode='adamp').attach_stores(model)
+    w_before = model.txt_enc.rnn.weight_ih_l0.data.clone()
+    opt.step()
+    torch.cuda.synchronize()
+    tw = model.txt_enc
+    assert not torch.equal(tw.rnn.weight_ih_l0.data, w_before)
+    assert torch.equal(tw._wih16[:384, :300], tw.rnn.weight_ih_l0.data.to(BF16))
+    assert torch.equal(tw._wih16[384:, :300], tw.rnn.weight_ih_l0_reverse.data.to(BF16))
+    assert float(tw._wih16[:, 300:].abs().max()) == 0.0
+    w1 = tw.pie_net.attention.w_1.weight
+    assert torch.equal(w1._w16p[:150, :300], w1.data.to(BF16)) and float(w1._w16p[150:].abs().max()) == 0.0
+
+
+def test_unimodal_text_client_against_reference_golden(env):
+    clients, ops, optim, TT, _, RT = env
+    g = _golden()
+    x, lengths, labels = torch.from_numpy(g['x']), torch.from_numpy(g['lengths']), torch.from_numpy(g['uni_labels'])
+    client = clients.TextClient(int(g['uni_vocab']), 300, 64, num_class=4, scale=128)
+    RT.fill_deterministic(client, seed=43)
+    client = client.cuda().train()
+    st = client.store()
+    st.zero_grad()
+    loss, fvec = clients.text_supervised_loss(client, x.cuda(), lengths, labels.cuda(), 4.0)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert rel(fvec.detach(), g['uni_x1']) < 2e-2
+    assert loss.item() == pytest.approx(float(g['uni_loss']), rel=2e-2)
+    assert (client.class_fc.weight.data >= 0).all() and (client.class_fc_2.weight.data >= 0).all()
+    params = dict(client.named_parameters())
+    for name in ['rnn.weight_hh_l0', 'rnn.weight_ih_l0_reverse', 'pie_net.fc.weight', 'class_fc.weight', 'class_fc.bias']:
+        assert rel(params[name].grad, g['uni_grad.' + name]) < 1e-1, (name, rel(params[name].grad, g['uni_grad.' + name]))
+    assert rel(params['embed.weight'].grad[:500], g['uni_grad_embed_rows']) < 1e-1
+    client.is_train = False
+    with torch.no_grad():
+        emb = client(x.cuda(), lengths)
+    cosv = F.cosine_similarity(emb.double().cpu(), torch.from_numpy(g['uni_embedding']).double(), dim=-1)
+    assert float(cosv.min()) > 0.9995
+    # deepcopy (the trainer's old_model) owns its own store and reproduces the embedding
+    old = copy.deepcopy(client).eval()
+    with torch.no_grad():
+        assert torch.equal(old(x.cuda(), lengths), emb)
+
+
+def test_client_pcme_shares_one_store_and_refreshes_old_model(env):
+    clients, ops, optim, TT, _, RT = env
+    model = clients.ClientPCME(vocab_size=300, embed_dim=256).cuda()
+    st = model.store()
+    assert model.txt_enc._bound is st
+    old = copy.deepcopy(model).eval()
+    old.store()
+    g = torch.Generator().manual_seed(1)
+    images = torch.randn(4, 3, 64, 64, generator=g).cuda()
+    caps = torch.randint(1, 300, (4, 7), generator=g).cuda()
+    lengths = torch.tensor([7, 6, 3, 1])
+    with torch.no_grad():
+        model.eval()
+        a = model(images, caps, None, lengths)
+        b = old(images, caps, None, lengths)
+    assert torch.equal(a['caption_features'], b['caption_features'])
+    with torch.no_grad():
+        model.txt_enc.rnn.weight_ih_l0.data.mul_(1.5)
+        model.sync_shadow()
+        old.copy_weights_from(model)
+        a = model(images, caps, None, lengths)
+        b = old(images, caps, None, lengths)
+    assert torch.equal(a['caption_features'], b['caption_features'])
+    assert torch.equal(a['image_features'], b['image_features'])

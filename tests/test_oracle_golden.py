@@ -202,3 +202,42 @@ def test_tower_restatement_matches_reference_modules(golden):
     with torch.no_grad():
         emb = client(small)
     np.testing.assert_allclose(emb.numpy(), g['client_embedding'], rtol=1e-4, atol=1e-6)
+
+
+def test_text_tower_restatement_matches_reference_modules(golden):
+    """oracle/torch_towers.py RefGRUEncoderText / RefTextClient against the reference's own
+    caption_encoder.EncoderText and language_model.EncoderText (tests/golden/make_golden.py::case_text_towers, same
+    deterministic weights, ragged length-sorted captions): forward values and parameter gradients, fp32, rel 1e-5."""
+    from oracle import torch_towers as RT
+    g = golden('text_towers')
+    x, lengths, coef = T(g['x']), T(g['lengths']), T(g['coef'])
+    enc = RT.RefGRUEncoderText(500, 300, 64)
+    RT.fill_deterministic(enc, seed=41)
+    enc.train()
+    emb = enc(x, lengths)['embedding']
+    np.testing.assert_allclose(emb.detach().numpy(), g['mm_embedding'], rtol=1e-5, atol=1e-6)
+    (emb * coef).sum().backward()
+    for name, p in enc.named_parameters():
+        ref = g['mm_grad.' + name]
+        got = p.grad.numpy() if p.grad is not None else np.zeros_like(ref)
+        np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-7, err_msg=name)
+    # the reverse direction contributes one step only: its recurrent matrix receives no gradient
+    assert np.abs(g['mm_grad.rnn.weight_hh_l0_reverse']).max() == 0.0
+    client = RT.RefTextClient(int(g['uni_vocab']), 300, 64, num_class=4, scale=128)
+    RT.fill_deterministic(client, seed=43)
+    client.train()
+    labels = T(g['uni_labels'])
+    loss, _ = RT.ref_text_supervised_loss(client, x, lengths, labels, 4)
+    x1, x2, w1, w2 = client(x, lengths)          # second forward: weights already clamped, same values
+    np.testing.assert_allclose(x1.detach().numpy(), g['uni_x1'], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(x2.detach().numpy(), g['uni_x2'], rtol=1e-4, atol=1e-4)
+    assert abs(float(loss) - float(g['uni_loss'])) <= 1e-5 * abs(float(g['uni_loss']))
+    assert min(float(w1.min()), float(w2.min())) == float(g['uni_w_min']) == 0.0
+    loss.backward()
+    params = dict(client.named_parameters())
+    for name in ['rnn.weight_hh_l0', 'rnn.weight_ih_l0_reverse', 'pie_net.fc.weight', 'class_fc.weight', 'class_fc.bias']:
+        np.testing.assert_allclose(params[name].grad.numpy(), g['uni_grad.' + name], rtol=2e-4, atol=1e-6, err_msg=name)
+    np.testing.assert_allclose(params['embed.weight'].grad[:500].numpy(), g['uni_grad_embed_rows'], rtol=2e-4, atol=1e-7)
+    client.is_train = False
+    with torch.no_grad():
+        np.testing.assert_allclose(client(x, lengths).numpy(), g['uni_embedding'], rtol=1e-5, atol=1e-6)
