@@ -222,7 +222,13 @@ def run_ours(args):
     ktimer = KernelTimer(T, ((B, 14, 14, 256), 256, 3, 1))
     ktimer.install()
 
-    def step(src, copy_in):
+    def step(src, copy_in, marks=None):
+        def mark(name):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+        mark('start')
         if copy_in:
             cur = {k: (v.to(dev, non_blocking=True) if k != 'cap_lens' else v) for k, v in src.items()}
         else:
@@ -233,6 +239,7 @@ def run_ours(args):
         if 'A' in phases:
             for s in range(S):
                 losses.append(server.train_step(cur['images'][s], tok(s)))
+        mark('A_server_train')
         if 'B' in phases:
             for s in range(S):
                 fi, ft = server.extract(cur['images'][s], tok(s))
@@ -240,26 +247,31 @@ def run_ours(args):
                 g_txt.index_copy_(0, cur['d_idx'][s], ft)
         ops.cast_into(g_img.view(-1), g_img16.view(-1))
         ops.cast_into(g_txt.view(-1), g_txt16.view(-1))
+        mark('B_server_extract')
         if 'C' in phases:
             client.begin_round()
             losses.append(client.private_step(cur['priv_images'], cur['priv_caps'], lens))
             for s in range(S):
                 losses.append(client.contrast_step(cur['images'][s], cur['caps'][s], lens, cur['d_idx'][s], g_img, g_txt,
                                                    g_img16, g_txt16))
+        mark('C_client_private_contrast')
         if 'D' in phases:
             for s in range(S):
                 ci, ct = client.generate(cur['images'][s], cur['caps'][s], lens)
                 c_img.index_copy_(0, cur['d_idx'][s], ci)
                 c_txt.index_copy_(0, cur['d_idx'][s], ct)
+        mark('D_client_generate')
         agg_img = agg_txt = None
         if 'E' in phases:
             agg_img = engine.exchange_and_aggregate(c_img, g_txt16)
             agg_txt = engine.exchange_and_aggregate(c_txt, g_img16)
+        mark('E_conw_aggregate')
         if 'F' in phases:
             if agg_img is None:
                 agg_img, agg_txt = c_img, c_txt
             for s in range(S):
                 losses.append(server.distill_step(cur['images'][s], tok(s), cur['d_idx'][s], agg_img, agg_txt))
+        mark('F_server_distill')
         return torch.stack([l.reshape(()) for l in losses]) if losses else torch.zeros(1, device=dev)
 
     def timed(src, copy_in, n):
@@ -292,6 +304,11 @@ def run_ours(args):
     time.sleep(0.3)
     ms_res, launches, out = timed(resident, False, args.steps)
     clocks = sampler.stop()
+    # where the step's time goes: one more resident step with CUDA events at the phase boundaries
+    marks = []
+    step(resident, False, marks)
+    torch.cuda.synchronize()
+    phase_ms = {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 2) for i in range(1, len(marks))}
     # roofline of the dominant convolution shape: one eager (un-graphed) server step with CUDA events recorded on
     # the launching stream around each of its launches, right after the timed region (same process, warm)
     tok0 = {'input_ids': resident['ids'][0], 'attention_mask': resident['mask'][0]}
@@ -359,7 +376,7 @@ def run_ours(args):
                    'with flat-gradient all-reduce' if world > 1 else 'single gpu'},
         'e2e': {'value': round(e2e, 1), 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d_bytes(host),
                 'd2h_bytes_per_step': int(out_e2e.numel() * 4), 'ms_per_step': round(ms_e2e / args.steps, 2)},
-        'gpu_launches': int(launches), 'clocks': clocks, 'losses_finite': finite,
+        'gpu_launches': int(launches), 'clocks': clocks, 'losses_finite': finite, 'phase_ms': phase_ms,
     }
     if roofline:
         line['roofline'] = roofline

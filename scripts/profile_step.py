@@ -52,7 +52,7 @@ for name in which:
     total = sum(v for _, v in agg.values())
     n = sum(c for c, _ in agg.values())
     print(f'== {name}: wall {wall:.2f} ms | kernels {n} | summed kernel time {total:.2f} ms')
-    top = sorted(agg.items(), key=lambda x: -x[1][1])[:14]
+    top = sorted(agg.items(), key=lambda x: -x[1][1])[:24]
     for k, (c, v) in top:
         print(f'   {v:8.3f} ms {100 * v / total:5.1f}% {c:5d}  {k}')
     report[name] = {'wall_ms': wall, 'kernels': n, 'kernel_ms': total, 'top': [(k, c, v) for k, (c, v) in top]}
