@@ -177,15 +177,15 @@ class KernelTimer:
         return sum(ts) / len(ts), len(ts)
 
 
-def ncu_traffic_bytes(csv_path):
-    """dram read + write bytes of the first launch in a profiles/r01_ncu_*.csv summary (None if absent)."""
+def ncu_traffic_bytes(csv_path, column=0):
+    """dram read + write bytes of launch `column` in a profiles/r01_ncu_*.csv summary (None if absent)."""
     try:
         tot = 0.0
         for ln in Path(csv_path).read_text().splitlines():
             k = ln.split(',')
             if k[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
                 scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[k[1]]
-                tot += float(k[2]) * scale
+                tot += float(k[2 + column]) * scale
         return int(tot) if tot else None
     except (OSError, KeyError, ValueError, IndexError):
         return None
@@ -364,6 +364,29 @@ def run_ours(args):
                     'avg_launch_ms': round(sim_ms, 4), 'ncu_tensor_pipe_pct': 47.1,
                     'note': 'ncu sm__pipe_tensor_cycles_active_realtime 47.1 % of the 1.72 GHz un-capped pipe peak; '
                             'the kernel reaches 92 % of the measured cuBLAS sustained rate'}
+    # the HBM-bound half of the con_w aggregation: softmax over clients + weighted sum at C = 8 clients (the 8-GPU
+    # configuration; SURVEY 8d: C*N*D*4 + C*N*4 + N*D*4 = 461 MB algorithmic), timed live with the L2 flushed
+    hbm_ms = []
+    vecs8 = [c_img, c_txt, g_img, g_txt] + [torch.empty_like(c_img).copy_(c_img) for _ in range(4)]
+    scores8 = torch.randn(8, N_PUB, device=dev)
+    for _ in range(5):
+        a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        server.model.store().grad.zero_()
+        a_ev.record()
+        ops.conw_reduce(vecs8, scores8)
+        b_ev.record()
+        torch.cuda.synchronize()
+        hbm_ms.append(a_ev.elapsed_time(b_ev))
+    del vecs8
+    hbm_ms = sorted(hbm_ms)[len(hbm_ms) // 2]
+    hbm_bytes = 8 * N_PUB * D * 4 + 8 * N_PUB * 4 + N_PUB * D * 4
+    peak_gbs = peaks.get('hbm_gbs', 6400.0)
+    hbm_gbs = hbm_bytes / (hbm_ms * 1e-3) / 1e9
+    roofline_hbm = {'bound': 'hbm', 'kernel': 'conw_reduce_kernel (softmax over C = 8 clients + weighted sum, N_pub=50000, D=256)',
+                    'achieved': round(hbm_gbs, 1), 'peak': peak_gbs, 'unit': 'GB/s', 'frac': round(hbm_gbs / peak_gbs, 4),
+                    'traffic': ncu_traffic_bytes(ROOT / 'profiles' / 'r01_ncu_hbm_kernels.csv', column=2),
+                    'avg_launch_ms': round(hbm_ms, 4), 'algorithmic_bytes': hbm_bytes,
+                    'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback'}
     line = {
         'metric': 'image-text pairs/sec per FL round', 'value': round(value, 1), 'unit': 'pairs/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms_res / args.steps, 2),
@@ -381,6 +404,7 @@ def run_ours(args):
     if roofline:
         line['roofline'] = roofline
     line['roofline_sim'] = roofline_sim
+    line['roofline_hbm'] = roofline_hbm
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline(steps=1, warmup=0)
     if rank == 0:

@@ -24,13 +24,7 @@ int creamfl_gemm_bf16(const void* a, int64_t lda, int a_mn, const void* b, int64
   }
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
-  if (split_k == 0) {
-    const long long tiles = ((M + 127LL) / 128) * ((N + 127LL) / 128);
-    long long split = (2LL * sm_count() + tiles - 1) / tiles;
-    const long long nkb = (K + 63LL) / 64;
-    if (split > nkb / 4) split = nkb / 4;
-    split_k = (accumulate && split > 1) ? (int)split : 1;
-  }
+  if (split_k == 0) split_k = accumulate ? gemm_plan_split(M, N, K) : 1;
   p.split_k = split_k;
   p.atomic_out = accumulate ? 1 : 0;
   p.out = out; p.ldo = ldo; p.out_bf16 = out_bf16;
@@ -39,6 +33,11 @@ int creamfl_gemm_bf16(const void* a, int64_t lda, int a_mn, const void* b, int64
   p.add = add; p.ld_add = ld_add; p.add_bf16 = add_bf16;
   p.aux = reinterpret_cast<const __nv_bfloat16*>(aux_bf16); p.ld_aux = ld_aux;
   return gemm_bf16(a, lda, a_mn, b, ldb, b_mn, p, S(stream));
+}
+
+int creamfl_plan_split_k(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 1;
+  return gemm_plan_split(M, N, K);
 }
 
 size_t creamfl_rowlse_workspace_bytes(int M, int N) {

@@ -40,14 +40,7 @@ int check_shape(const char* who, const ConvShape& c) {
   }
   return CFL_OK;
 }
-int split_for(long long M, long long N, long long K) {
-  const long long tiles = ((M + 127) / 128) * ((N + 127) / 128);
-  long long split = (2LL * sm_count() + tiles - 1) / tiles;
-  const long long nkb = (K + 63) / 64;
-  if (split > nkb / 4) split = nkb / 4;
-  if (split < 1) split = 1;
-  return (int)split;
-}
+int split_for(long long M, long long N, long long K) { return gemm_plan_split((int)M, (int)N, (int)K); }
 }  // namespace
 
 extern "C" {
@@ -165,14 +158,14 @@ int creamfl_im2col_nchw_f32(const float* images, int N, int C, int H, int W, int
 
 int creamfl_bn_train_fwd(const void* x, int64_t P, int C, const float* gamma, const float* beta, float eps,
                          float momentum, float* running_mean, float* running_var, double* sums, float* mean,
-                         float* rstd, float* scale, float* shift, const void* res, int relu, int stats_ready, void* y,
-                         void* stream) {
+                         float* rstd, float* scale, float* shift, const void* res, int relu, int stats_ready,
+                         int64_t* num_batches_tracked, void* y, void* stream) {
   if (!x || !gamma || !beta || !sums || !mean || !rstd || !scale || !shift || !y) {
     set_error("bn_train_fwd: null pointer");
     return CFL_EINVAL;
   }
   return bn_train_fwd(x, P, C, gamma, beta, eps, momentum, running_mean, running_var, sums, mean, rstd, scale, shift,
-                      res, relu, stats_ready, y, S(stream));
+                      res, relu, stats_ready, reinterpret_cast<long long*>(num_batches_tracked), y, S(stream));
 }
 
 int creamfl_bn_stats(const void* x, int64_t P, int C, double* sums, void* stream) {

@@ -410,14 +410,8 @@ int conv_same_wgrad(const void* dy, const void* x, int N, int H, int W, int Cin,
   const int num_m = (Cout + kCBM - 1) / kCBM, num_n = (Cin + BN - 1) / BN;
   const int base_units = num_m * num_n * R * S;
   const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  // two waves of units when the reduction is long enough to split (>= 8 pixel tiles per split)
-  int split = (2 * sm_count() + base_units - 1) / base_units;
-  if (split > pix_tiles / 8) split = pix_tiles / 8;
-  if (split < 1) split = 1;
-  {
-    const int per = (pix_tiles + split - 1) / split;
-    split = (pix_tiles + per - 1) / per;
-  }
+  // whole waves of units (see plan_split_k in gemm_tc.cu); at least 8 pixel tiles per split
+  const int split = plan_split_k(base_units, pix_tiles, 8, 4.0);
   p.split_k = split;
   CUtensorMap ta, tb;
   if ((rc = make_tmap_nhwc(&ta, dy, N, H, W, Cout, 64, p.bw, p.bh, p.bn, 1))) return rc;

@@ -528,6 +528,42 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return check_launch("gemm_tc_kernel");
 }
 
+// Tile width the launcher picks for an [M, N, K] problem (see gemm_bf16 below).
+int gemm_tile_n(int N, int K) {
+  return (N <= 64) ? 64 : ((((N >= 256 && N % 256 == 0) || N >= 1024) && K >= 512) ? 256 : 128);
+}
+
+// Split-K planner of the accumulating (weight-gradient) GEMMs.  A launch runs `tiles * split` units on sm_count()
+// persistent CTAs, i.e. ceil(units / SMs) waves, each costing the unit's k-blocks plus its atomic epilogue
+// (~4 k-block times, calibrated on the ResNet101 / BERT shapes with scripts/sweep_wgrad.py): pick the split with the
+// smallest waves * (k-blocks per unit + epilogue).  The earlier "two waves of 128-wide tiles" rule produced e.g.
+// 152 units on 148 SMs for the 23 + 22 1x1 convolutions of ResNet101's layer 3 (a second wave for 4 units).
+int plan_split_k(long long tiles, long long nkb, long long min_per, double epi_kb) {
+  const long long sms = sm_count();
+  long long max_split = nkb / (min_per > 0 ? min_per : 1);
+  if (max_split < 1) max_split = 1;
+  if (max_split > 4 * sms) max_split = 4 * sms;
+  int best = 1;
+  double best_cost = 1e300;
+  for (long long s = 1; s <= max_split; ++s) {
+    const long long per = (nkb + s - 1) / s;
+    if ((nkb + per - 1) / per != s) continue;          // not a distinct partition
+    const long long waves = (tiles * s + sms - 1) / sms;
+    const double cost = (double)waves * ((double)per + epi_kb);
+    if (cost < best_cost * (1.0 - 1e-9)) {
+      best_cost = cost;
+      best = (int)s;
+    }
+  }
+  return best;
+}
+
+int gemm_plan_split(int M, int N, int K) {
+  const int BN = gemm_tile_n(N, K);
+  const long long tiles = ((M + kBM - 1LL) / kBM) * ((N + BN - 1LL) / BN);
+  return plan_split_k(tiles, (K + kBK - 1LL) / kBK, 4, 4.0);
+}
+
 // Host entry shared by the C ABI wrappers.  a/b are bf16.  a_mn / b_mn select the storage order (see top).
 int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, GemmParams p,
               cudaStream_t stream) {
@@ -554,7 +590,7 @@ int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long l
   // Narrow outputs waste MMA columns: pick the tile width from N.  128x256 tiles read 96 B/clk of operands from
   // shared memory per SM (128x128: 128 B/clk, the port limit), so wide outputs use them whenever N fills them.
   // (short-K problems are HBM-bound: they keep the 128-wide configuration with double-buffered output staging)
-  int BN = (p.N <= 64) ? 64 : ((((p.N >= 256 && p.N % 256 == 0) || p.N >= 1024) && p.K >= 512) ? 256 : 128);
+  int BN = gemm_tile_n(p.N, p.K);
   // residual operand through TMA: needs the 128-wide configuration (two residual + two output staging buffers)
   const bool add_tma = p.add != nullptr && p.add_bf16 && p.split_k == 1 && !a_mn && p.N > 64 &&
                        (reinterpret_cast<uintptr_t>(p.add) & 15) == 0 && ((p.ld_add * 2) & 15) == 0;

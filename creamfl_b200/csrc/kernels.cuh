@@ -26,6 +26,9 @@ struct GemmParams {
 };
 int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, GemmParams p,
               cudaStream_t stream);
+int gemm_tile_n(int N, int K);
+int plan_split_k(long long tiles, long long nkb, long long min_per, double epi_kb);
+int gemm_plan_split(int M, int N, int K);
 // sim_tc.cu
 size_t rowlse_workspace_bytes(int M, int N);
 int rowlse_bf16(const void* Q, const void* G, const long long* labels, int M, int N, int D, float scale,
@@ -62,7 +65,7 @@ int conv_same_dgrad(const void*, const void*, int, int, int, int, int, int, int,
 int conv_same_wgrad(const void*, const void*, int, int, int, int, int, int, int, float*, cudaStream_t);
 // nn_ops.cu
 int bn_train_fwd(const void*, long long, int, const float*, const float*, float, float, float*, float*, double*,
-                 float*, float*, float*, float*, const void*, int, int, void*, cudaStream_t);
+                 float*, float*, float*, float*, const void*, int, int, long long*, void*, cudaStream_t);
 int bn_stats_only(const void*, long long, int, double*, cudaStream_t);
 int bn_eval_fwd(const void*, long long, int, const float*, const float*, float, const float*, const float*, float*,
                 float*, const void*, int, void*, cudaStream_t);

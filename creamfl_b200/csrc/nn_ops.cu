@@ -102,9 +102,11 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, long long P, int C
                                    const float* __restrict__ beta, float eps, float momentum,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                   float* __restrict__ scale, float* __restrict__ shift) {
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   long long* __restrict__ num_batches_tracked) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;   // nn.BatchNorm2d's counter, no extra launch
   const double m = sums[c] / (double)P;
   double var = sums[C + c] / (double)P - m * m;
   if (var < 0.0) var = 0.0;
@@ -211,10 +213,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       be[i] = relu_from_x ? beta[g * 8 + i] : 0.0f;
     }
     const long long stride = (long long)gridDim.x * rows;
-    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += 2 * stride) {
-      bf16x8 rd[2], rx[2], ry[2];
+    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += 4 * stride) {
+      bf16x8 rd[4], rx[4], ry[4];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < 4; ++u) {        // 8-12 independent 16-byte loads in flight per thread
         if (p + u * stride < P) {
           const long long o = (p + u * stride) * C + g * 8;
           rd[u] = *reinterpret_cast<const bf16x8*>(dy + o);
@@ -223,7 +225,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < 4; ++u) {
         if (p + u * stride < P) {
           float d[8], xv[8];
           unpack8(rd[u], d);
@@ -357,9 +359,15 @@ static int bn_check(const char* who, long long P, int C) {
   return CFL_OK;
 }
 
+// Blocks of the reduction kernels.  Every block ends with 2*C fp64 atomics, so wide layers (C >= 512: 2-4 K atomics
+// per block) take fatter blocks (64 pixels per thread instead of 16).  Swept on the ResNet101 shapes at batch 128
+// with scripts/bench_bn.py: 16/64 is within 1 % of every other setting tried - the large maps already run at
+// 75-90 % of the HBM roofline, the 14x14 / 7x7 maps are bound by the three dependent launches.
+static int bn_ppt(int C) { return C >= 512 ? 64 : 16; }
 static int bn_reduce_grid(long long P, int C) {
   const int rows = kBnThreads / (C >> 3) > 0 ? kBnThreads / (C >> 3) : 1;
-  long long want = (P + (long long)rows * 16 - 1) / ((long long)rows * 16);  // >= 16 pixels per thread
+  const long long ppt = bn_ppt(C);
+  long long want = (P + (long long)rows * ppt - 1) / ((long long)rows * ppt);
   const long long cap = (long long)sm_count() * 8;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
@@ -377,12 +385,13 @@ int bn_stats_only(const void* x, long long P, int C, double* sums, cudaStream_t 
 
 int bn_train_fwd(const void* x, long long P, int C, const float* gamma, const float* beta, float eps, float momentum,
                  float* running_mean, float* running_var, double* sums, float* mean, float* rstd, float* scale,
-                 float* shift, const void* res, int relu, int stats_ready, void* y, cudaStream_t st) {
+                 float* shift, const void* res, int relu, int stats_ready, long long* num_batches_tracked, void* y,
+                 cudaStream_t st) {
   int rc = bn_check("bn_train_fwd", P, C);
   if (rc) return rc;
   if (!stats_ready && (rc = bn_stats_only(x, P, C, sums, st))) return rc;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, beta, eps, momentum, running_mean,
-                                                       running_var, mean, rstd, scale, shift);
+                                                       running_var, mean, rstd, scale, shift, num_batches_tracked);
   const long long total8 = P * C / 8;
   bn_apply_kernel<<<ew_grid(total8, kEwVec), kEwThreads, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(res), relu,

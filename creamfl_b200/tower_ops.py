@@ -108,7 +108,7 @@ class BNScratch:
 
 
 def bn_train_fwd(x, gamma, beta, running_mean, running_var, sc: BNScratch, eps, momentum, res=None, relu=True,
-                 stats_ready=False):
+                 stats_ready=False, num_batches_tracked=None):
     c = x.shape[-1]
     p = x.numel() // c
     mean = torch.empty(c, dtype=torch.float32, device=x.device)
@@ -116,7 +116,8 @@ def bn_train_fwd(x, gamma, beta, running_mean, running_var, sc: BNScratch, eps, 
     y = torch.empty_like(x)
     _chk(_lib.load().creamfl_bn_train_fwd(_p(x), p, c, _p(gamma), _p(beta), eps, momentum, _p(running_mean),
                                           _p(running_var), _p(sc.sums), _p(mean), _p(rstd), _p(sc.scale), _p(sc.shift),
-                                          _p(res), int(relu), int(stats_ready), _p(y), _stream()), "bn_train_fwd",
+                                          _p(res), int(relu), int(stats_ready), _p(num_batches_tracked), _p(y),
+                                          _stream()), "bn_train_fwd",
          2 if stats_ready else 3)
     return y, mean, rstd
 

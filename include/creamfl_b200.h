@@ -50,6 +50,9 @@ int creamfl_gemm_bf16(const void* a, int64_t lda, int a_mn, const void* b, int64
                       int K, void* out, int64_t ldo, int out_bf16, void* out_preact_bf16, const float* bias,
                       int act, float alpha, const void* add, int64_t ld_add, int add_bf16, const void* aux_bf16,
                       int64_t ld_aux, int split_k, int accumulate, void* stream);
+/* the split the library chooses for an accumulating [M, N, K] product when split_k == 0 (host-only introspection:
+ * whole waves of tiles * split units on the device's SMs; 148 is assumed when no device is present) */
+int creamfl_plan_split_k(int M, int N, int K);
 /* elementwise derivative of an activation from its OUTPUT y: kind CREAMFL_ACT_SIGMOID -> dy*y*(1-y),
  * CREAMFL_ACT_TANH -> dy*(1-y^2); fp32 in, bf16 out (the result feeds a dgrad/wgrad GEMM) */
 int creamfl_act_bwd_f32(const float* dy, const float* y, int64_t n, int kind, void* out_bf16, void* stream);
@@ -147,11 +150,12 @@ int creamfl_im2col_nchw_f32(const float* images, int N, int C, int H, int W, int
 
 /* ---- BatchNorm2d over NHWC bf16 (P = N*H*W pixels), fused with the residual add and ReLU of the ResNet blocks.
  * train: batch statistics (fp64 accumulation in `sums`, 2*C doubles, zero on entry and on exit), running stats
- * updated with `momentum`; keeps mean/rstd for the backward.  scale/shift: C-float scratch each. */
+ * updated with `momentum`; keeps mean/rstd for the backward.  scale/shift: C-float scratch each.
+ * num_batches_tracked (optional, device int64 scalar) is incremented (nn.BatchNorm2d's buffer). */
 int creamfl_bn_train_fwd(const void* x_bf16, int64_t P, int C, const float* gamma, const float* beta, float eps,
                          float momentum, float* running_mean, float* running_var, double* sums, float* mean,
                          float* rstd, float* scale, float* shift, const void* res_bf16, int relu, int stats_ready,
-                         void* y_bf16, void* stream);
+                         int64_t* num_batches_tracked, void* y_bf16, void* stream);
 /* stand-alone statistics pass: sums[0..C) += sum_p x, sums[C..2C) += sum_p x^2 */
 int creamfl_bn_stats(const void* x_bf16, int64_t P, int C, double* sums, void* stream);
 int creamfl_bn_eval_fwd(const void* x_bf16, int64_t P, int C, const float* gamma, const float* beta, float eps,

@@ -117,3 +117,26 @@ def test_exchange_gloo_world2_matches_single_process_oracle():
         assert s_shape == (world, n) and v_shape == (world, n, d)
         np.testing.assert_allclose(agg, want.numpy(), rtol=1e-5, atol=1e-7)     # every rank holds the full ensemble (fp32 scores on the wire)
         np.testing.assert_allclose(grad, np.full(5, 1.5))                       # mean of the rank gradients
+
+
+def test_split_k_planner_fills_whole_waves():
+    """Host logic of the accumulating (weight-gradient) GEMMs: `creamfl_plan_split_k` must return a distinct
+    partition of the k-blocks (>= 4 per unit) whose tiles * split units fill whole waves of the 148 SMs on the shapes
+    the server step issues most (ResNet101 layer 3 / 4 1x1 convolutions at batch 128, BERT-base at 4096 tokens)."""
+    import math
+    from creamfl_b200 import _lib
+    lib = _lib.load()
+    shapes = [(1024, 256, 25088), (256, 1024, 25088), (2048, 512, 6272), (512, 2048, 6272), (768, 768, 4096),
+              (3072, 768, 4096), (768, 3072, 4096), (2304, 768, 4096), (512, 128, 100352), (128, 512, 100352),
+              (256, 64, 401408), (64, 256, 401408)]
+    for m, n, k in shapes:
+        s = lib.creamfl_plan_split_k(m, n, k)
+        bn = 64 if n <= 64 else (256 if ((n >= 256 and n % 256 == 0) or n >= 1024) and k >= 512 else 128)
+        nkb = math.ceil(k / 64)
+        per = math.ceil(nkb / s)
+        assert s >= 1 and per >= 4 and math.ceil(nkb / per) == s, (m, n, k, s)
+        units = math.ceil(m / 128) * math.ceil(n / bn) * s
+        waves = math.ceil(units / 148)
+        assert units / (waves * 148) >= 0.85, (m, n, k, s, units)
+    assert lib.creamfl_plan_split_k(256, 768, 128) == 1          # two k-blocks: nothing to split
+    assert lib.creamfl_plan_split_k(0, 5, 5) == 1

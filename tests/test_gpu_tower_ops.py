@@ -122,8 +122,10 @@ def test_batchnorm_train(T, shape, relu, with_res):
         y64 = torch.relu(y64)
     sc = T.BNScratch(c, 'cuda')
     rmg, rvg = rm.cuda(), rv.cuda()
+    nbt = torch.tensor(41, dtype=torch.long, device='cuda')
     y, mean, rstd = T.bn_train_fwd(x.cuda(), gamma.cuda(), beta.cuda(), rmg, rvg, sc, 1e-5, 0.1,
-                                   res=res.cuda() if with_res else None, relu=relu)
+                                   res=res.cuda() if with_res else None, relu=relu, num_batches_tracked=nbt)
+    assert nbt.item() == 42                      # nn.BatchNorm2d's counter rides in the finalize kernel
     assert rel_l2(y, y64.permute(0, 2, 3, 1)) < 4e-3
     assert rel_l2(rmg, rm64) < 1e-5 and rel_l2(rvg, rv64) < 1e-5
     dy = rnd(*shape, seed=11)
