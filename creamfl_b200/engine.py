@@ -294,8 +294,11 @@ def gather_client_rows(score: torch.Tensor, vec: torch.Tensor) -> Tuple[torch.Te
 def average_gradients(flat_grad: torch.Tensor) -> None:
     """Replicated server with the public batches sharded over ranks: mean of the flat gradient buffer."""
     if dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
-        flat_grad.mul_(1.0 / dist.get_world_size())
+        if flat_grad.is_cuda and dist.get_backend() == 'nccl':
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)         # one pass: NCCL divides inside the collective
+        else:                                                         # gloo (CPU tests) has no AVG
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+            flat_grad.mul_(1.0 / dist.get_world_size())
 
 
 def exchange_and_aggregate(own_vec: torch.Tensor, global_other16: torch.Tensor) -> torch.Tensor:

@@ -351,3 +351,38 @@ def test_client_pcme_shares_one_store_and_refreshes_old_model(env):
         b = old(images, caps, None, lengths)
     assert torch.equal(a['caption_features'], b['caption_features'])
     assert torch.equal(a['image_features'], b['image_features'])
+
+
+def test_text_tower_rows_are_independent_agnews_shape(env):
+    """Size-independent property at the AG_NEWS-shape client batch (B = 509 captions of 10..120 words, not a multiple
+    of the 4-sequence tile, unsorted lengths): every caption's embedding depends on that caption only, so a sub-batch
+    and a permuted batch reproduce the rows of the full batch; words past a caption's length do not matter."""
+    _, _, _, TT, T, RT = env
+    g = torch.Generator().manual_seed(21)
+    b, l, vocab = 509, 120, 11755
+    lengths = torch.randint(10, l + 1, (b,), generator=g)
+    lengths[3], lengths[77] = 1, l
+    x = torch.randint(4, vocab, (b, l), generator=g)
+    model = TT.TextModel(vocab, 300, 256)
+    RT.fill_deterministic(model.txt_enc, seed=22)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        full = model(x.cuda(), lengths)
+        assert torch.isfinite(full).all() and torch.allclose(full.norm(dim=1), torch.ones(b, device='cuda'), atol=1e-5)
+        sub = model(x[::7].contiguous().cuda(), lengths[::7])
+        assert torch.allclose(sub, full[::7], atol=2e-6)
+        perm = torch.randperm(b, generator=g)
+        shuffled = model(x[perm].cuda(), lengths[perm])
+        assert torch.allclose(shuffled, full[perm.cuda()], atol=2e-6)
+        x2 = x.clone()
+        for i, n in enumerate(lengths.tolist()):
+            x2[i, n:] = 7                              # different padding words
+        assert torch.allclose(model(x2.cuda(), lengths), full, atol=2e-6)
+    # against the CPU oracle on a slice (the oracle needs length-sorted batches)
+    order = torch.argsort(lengths[:64], descending=True)
+    ref = RT.RefGRUEncoderText(vocab, 300, 256)
+    ref.load_state_dict({k: v.cpu() for k, v in model.txt_enc.state_dict().items()})
+    with torch.no_grad():
+        want = ref(x[:64][order], lengths[:64][order])['embedding']
+    cosv = F.cosine_similarity(full[:64][order.cuda()].double().cpu(), want.double(), dim=-1)
+    assert float(cosv.min()) > 0.9995
