@@ -61,6 +61,28 @@ def unit(x):
     return x / x.norm(dim=-1, keepdim=True)
 
 
+class stdout_to_stderr:
+    """File-descriptor level redirect of stdout to stderr (catches C-level printf of libraries, e.g. the
+    `NCCL version ...` banner NCCL writes to stdout when NCCL_DEBUG=VERSION)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)                       # flush C stdio buffers before restoring the fd
+        except OSError:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 # ===================================================================================================== synthetic data
 def make_host_batches(S, B, seed):
     """SURVEY.md 8d recipe: N(0,1) images, BERT ids U[1000, 30522) with CLS/SEP, lengths U{8..32} sorted descending,
@@ -200,9 +222,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=dev)
+        with stdout_to_stderr():     # stdout carries exactly one JSON line: NCCL's version banner goes to stderr
+            dist.init_process_group('nccl', device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))          # forces communicator creation inside the redirect
+            torch.cuda.synchronize()
     S, B = args.sub_batches, args.batch
     torch.manual_seed(1234 + rank)
     server = engine.ServerEngine(D, 'resnet101', device=dev, data_parallel=world > 1, use_graphs=not args.no_graphs)
