@@ -12,13 +12,18 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-BF16 = torch.bfloat16
+BF16 = torch.bfloat16        # storage type of the "bf16" tensors; install(exact=True) switches it to fp32
+EXACT = False
 
 
 def gemm_bf16(a, b, *, a_mn=False, b_mn=False, bias=None, act=0, alpha=1.0, add=None, aux=None,
-              out_dtype=BF16, want_preact=False, split_k=1, out=None, accumulate=False, n_cols=None):
+              out_dtype=None, want_preact=False, split_k=1, out=None, accumulate=False, n_cols=None):
+    if out_dtype is None or out_dtype == torch.bfloat16:
+        out_dtype = BF16
     assert a.dtype == BF16 and b.dtype == BF16 and a.stride(1) == 1 and b.stride(1) == 1
-    assert a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0 and (a.stride(0) * 2) % 16 == 0 and (b.stride(0) * 2) % 16 == 0
+    if not EXACT:      # TMA operand rules: 16-byte aligned base and row pitch
+        assert a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0
+        assert (a.stride(0) * 2) % 16 == 0 and (b.stride(0) * 2) % 16 == 0
     A = a.float().t() if a_mn else a.float()
     Bm = b.float() if b_mn else b.float().t()
     assert A.shape[1] == Bm.shape[0], (A.shape, Bm.shape)
@@ -32,12 +37,19 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, bias=None, act=0, alpha=1.0, add=
         assert add.shape == acc.shape
         acc = acc + add.float()
     pre = acc.to(BF16) if want_preact else None
-    if act == 3:
-        acc = torch.tanh(acc)
-    elif act == 6:
-        acc = torch.sigmoid(acc)
+    if act == 1:
+        acc = F.gelu(acc)                                   # erf GELU
     elif act == 2:
         acc = torch.relu(acc)
+    elif act == 3:
+        acc = torch.tanh(acc)
+    elif act == 4:                                          # acc * gelu'(aux)
+        xa = aux.float()
+        acc = acc * (0.5 * (1 + torch.erf(xa / 2 ** 0.5)) + xa * torch.exp(-0.5 * xa * xa) / (2 * torch.pi) ** 0.5)
+    elif act == 5:                                          # acc * (aux > 0)
+        acc = acc * (aux.float() > 0)
+    elif act == 6:
+        acc = torch.sigmoid(acc)
     elif act != 0:
         raise NotImplementedError(act)
     if out is None:
@@ -220,13 +232,233 @@ def relu_inplace(master, shadow):
         shadow.copy_(master.to(BF16))
 
 
-def install(monkeypatch):
-    """Swap the ctypes wrappers used by creamfl_b200.text_towers / clients._LinearFn for the emulations above and
-    lift the CUDA-only guard of the ParamStore (tests only)."""
-    from creamfl_b200 import ops, tower_ops, towers
+
+
+# ---- image tower / BERT entry points (tower_ops)
+def _nchw(x):
+    return x.float().permute(0, 3, 1, 2)
+
+
+def _filters(w2d, cout, r, s_, cin):
+    return w2d[:, :r * s_ * cin].float().reshape(cout, r, s_, cin).permute(0, 3, 1, 2)
+
+
+def conv_out_hw(h, w, r, s_, stride, pad):
+    return (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s_) // stride + 1
+
+
+def conv_fprop(x, w2d, r, s_, stride, pad, bn_sums=None):
+    n, h, w, cin = x.shape
+    cout = w2d.shape[0]
+    y = F.conv2d(_nchw(x), _filters(w2d, cout, r, s_, cin), stride=stride, padding=pad).permute(0, 2, 3, 1)
+    y = y.contiguous().to(BF16)
+    if bn_sums is not None:                     # statistics of the bf16 output, accumulated
+        y2 = y.double().reshape(-1, cout)
+        bn_sums[:cout] += y2.sum(0)
+        bn_sums[cout:] += (y2 * y2).sum(0)
+    return y
+
+
+def conv_dgrad(dy, w2d, x_shape, r, s_, stride, pad, add=None):
+    n, h, w, cin = x_shape
+    cout = w2d.shape[0]
+    dx = torch.nn.grad.conv2d_input((n, cin, h, w), _filters(w2d, cout, r, s_, cin), _nchw(dy), stride=stride,
+                                    padding=pad).permute(0, 2, 3, 1)
+    if add is not None:
+        dx = dx + add.float()
+    return dx.contiguous().to(BF16)
+
+
+def conv_wgrad(dy, x, dw, r, s_, stride, pad):
+    n, h, w, cin = x.shape
+    cout = dy.shape[-1]
+    gw = torch.nn.grad.conv2d_weight(_nchw(x), (cout, cin, r, s_), _nchw(dy), stride=stride, padding=pad)
+    dw += gw.permute(0, 2, 3, 1).reshape(cout, r * s_ * cin)
+
+
+def im2col_images(images, r, s_, stride, pad, pitch):
+    n, c, h, w = images.shape
+    cols = F.unfold(images.float(), (r, s_), padding=pad, stride=stride)           # [N, C*r*s, L], (c, r, s) order
+    l = cols.shape[-1]
+    cols = cols.view(n, c, r * s_, l).permute(0, 3, 2, 1).reshape(n * l, r * s_ * c)
+    out = torch.zeros((n * l, pitch), dtype=BF16)
+    out[:, :r * s_ * c] = cols.to(BF16)
+    return out
+
+
+def bn_train_fwd(x, gamma, beta, running_mean, running_var, sc, eps, momentum, res=None, relu=True, stats_ready=False,
+                 num_batches_tracked=None):
+    c = x.shape[-1]
+    x2 = x.double().reshape(-1, c)
+    p = x2.shape[0]
+    if not stats_ready:
+        sc.sums[:c] += x2.sum(0)
+        sc.sums[c:] += (x2 * x2).sum(0)
+    m = sc.sums[:c] / p
+    var = (sc.sums[c:] / p - m * m).clamp_min(0)
+    sc.sums.zero_()
+    rstd = (1.0 / torch.sqrt(var + eps)).float()
+    mean = m.float()
+    running_mean.mul_(1 - momentum).add_(momentum * mean)
+    running_var.mul_(1 - momentum).add_(momentum * (var * p / max(p - 1, 1)).float())
+    if num_batches_tracked is not None:
+        num_batches_tracked += 1
+    scale = gamma * rstd
+    y = x.float() * scale + (beta - mean * scale)
+    if res is not None:
+        y = y + res.float()
+    if relu:
+        y = torch.relu(y)
+    return y.to(BF16), mean, rstd
+
+
+def bn_eval_fwd(x, gamma, beta, running_mean, running_var, sc, eps, res=None, relu=True):
+    scale = gamma * torch.rsqrt(running_var + eps)
+    y = x.float() * scale + (beta - running_mean * scale)
+    if res is not None:
+        y = y + res.float()
+    if relu:
+        y = torch.relu(y)
+    return y.to(BF16)
+
+
+def bn_train_bwd(dy, y_mask, x, gamma, mean, rstd, sc, dgamma, dbeta, want_g=False, beta=None, relu_from_x=False):
+    c = x.shape[-1]
+    xhat = (x.float() - mean) * rstd
+    g = dy.float()
+    if y_mask is not None:
+        g = g * (y_mask.float() > 0)
+    elif relu_from_x and beta is not None:
+        g = g * ((gamma * xhat + beta) > 0)
+    g2, xh2 = g.reshape(-1, c), xhat.reshape(-1, c)
+    p = g2.shape[0]
+    s1, s2 = g2.sum(0), (g2 * xh2).sum(0)
+    dbeta += s1
+    dgamma += s2
+    dx = gamma * rstd * (g - s1 / p - xhat * (s2 / p))
+    return dx.to(BF16), (g.to(BF16) if want_g else None)
+
+
+def maxpool_fwd(x, want_idx=True):
+    y, idx = F.max_pool2d(_nchw(x), 3, 2, 1, return_indices=True)
+    return y.permute(0, 2, 3, 1).contiguous().to(BF16), (idx if want_idx else None)     # idx: opaque to the caller
+
+
+def maxpool_bwd(dy, idx, x_shape):
+    n, h, w, c = x_shape
+    dx = torch.zeros(n, c, h * w)
+    dx.scatter_add_(2, idx.flatten(2), _nchw(dy).flatten(2))          # overlapping windows: contributions add up
+    return dx.view(n, c, h, w).permute(0, 2, 3, 1).contiguous().to(BF16)
+
+
+def embed_fwd(ids, token_type, word, pos, typ, seq_len):
+    t = ids.numel()
+    posidx = torch.arange(t) % seq_len
+    tt = token_type.reshape(-1) if token_type is not None else torch.zeros(t, dtype=torch.long)
+    return (word[ids.reshape(-1)] + pos[posidx] + typ[tt]).to(BF16)
+
+
+def embed_bwd(ids, token_type, dh, seq_len, dword, dpos, dtyp):
+    t = dh.shape[0]
+    d = dh.float()
+    dword.index_add_(0, ids.reshape(-1), d)
+    dpos.index_add_(0, torch.arange(t) % seq_len, d)
+    tt = token_type.reshape(-1) if token_type is not None else torch.zeros(t, dtype=torch.long)
+    dtyp.index_add_(0, tt, d)
+
+
+def _split_heads(qkv, b, l, heads):
+    q, k, v = qkv.float().view(b, l, 3, heads, 64).permute(2, 0, 3, 1, 4)                # each [B, H, L, 64]
+    return q, k, v
+
+
+def attn_fwd(qkv, mask, b, l, heads):
+    q, k, v = _split_heads(qkv, b, l, heads)
+    s = q @ k.transpose(-1, -2) * 0.125
+    s = s + torch.where(mask > 0.5, 0.0, -3.0e38)[:, None, None, :]                     # HF extended mask
+    p = torch.softmax(s, dim=-1)
+    ctx = (p @ v).permute(0, 2, 1, 3).reshape(b * l, heads * 64)
+    return ctx.to(BF16), p.to(BF16)
+
+
+def attn_bwd(qkv, probs, dctx, b, l, heads, dbias=None):
+    q, k, v = _split_heads(qkv, b, l, heads)
+    p = probs.float()
+    do = dctx.float().view(b, l, heads, 64).permute(0, 2, 1, 3)
+    dp = do @ v.transpose(-1, -2)
+    ds = p * (dp - (dp * p).sum(-1, keepdim=True)) * 0.125
+    dq, dk, dv = ds @ k, ds.transpose(-1, -2) @ q, p.transpose(-1, -2) @ do
+    dqkv = torch.stack([dq, dk, dv], 0).permute(1, 3, 0, 2, 4).reshape(b * l, 3 * heads * 64)
+    if dbias is not None:
+        dbias += dqkv.sum(0)
+    return dqkv.to(BF16)
+
+
+def pie_pool_fwd(x, h, w2):
+    a = torch.softmax(h.float() @ w2, dim=1)                                            # [B, P]
+    r = torch.einsum('bp,bpc->bc', a, x.float())
+    return a, r.to(BF16), x.float().mean(1).to(BF16)
+
+
+def pie_pool_bwd(x, h, w2, attn, d_r, d_pooled, dw2):
+    xf, hf, dr = x.float(), h.float(), d_r.float()
+    p = x.shape[1]
+    dx = attn[:, :, None] * dr[:, None, :] + d_pooled.float()[:, None, :] / p
+    dattn = torch.einsum('bpc,bc->bp', xf, dr)
+    da = attn * (dattn - (attn * dattn).sum(1, keepdim=True))
+    dpre = da[:, :, None] * w2[None, None, :] * (1 - hf * hf)
+    dw2 += torch.einsum('bp,bph->h', da, hf)
+    return dx.to(BF16), dpre.to(BF16)
+
+
+def avgpool_fwd(x, scale=1.0):
+    n, h, w, c = x.shape
+    y = x.float().reshape(n, h * w, c).mean(1) * scale
+    return y, y.to(BF16)
+
+
+def avgpool_bwd(dy16, shape, scale=1.0):
+    n, h, w, c = shape
+    return (dy16.float()[:, None, None, :] * (scale / (h * w))).expand(n, h, w, c).contiguous().to(BF16)
+
+
+def l2norm_raw(x32):
+    inv = 1.0 / x32.norm(dim=-1).clamp_min(1e-12)
+    return x32 * inv[:, None], inv
+
+
+def l2norm_bwd_raw(gy, y, inv):
+    return inv[:, None] * (gy - y * (gy * y).sum(-1, keepdim=True))
+
+
+def cross_entropy(x, labels, margin=0.0):
+    lab = torch.arange(x.shape[0]) if labels is None else labels
+    return F.cross_entropy(x - margin * F.one_hot(lab, x.shape[1]).to(x.dtype), lab)
+
+
+_OPS = ('gemm_bf16', 'cast_into', 'to_bf16', 'l2_normalize', 'l2norm_raw', 'l2norm_bwd_raw', 'cross_entropy')
+_TOWER_OPS = ('wemb_gather', 'wemb_scatter', 'gru_fwd', 'gru_bwd', 'seq_pool_fwd', 'seq_pool_bwd', 'scale_relu_fwd',
+              'scale_relu_bwd', 'layernorm_fwd', 'layernorm_bwd', 'act_bwd', 'colsum_into', 'relu_inplace', 'conv_fprop',
+              'conv_dgrad', 'conv_wgrad', 'im2col_images', 'bn_train_fwd', 'bn_eval_fwd', 'bn_train_bwd', 'maxpool_fwd',
+              'maxpool_bwd', 'embed_fwd', 'embed_bwd', 'attn_fwd', 'attn_bwd', 'pie_pool_fwd', 'pie_pool_bwd',
+              'avgpool_fwd', 'avgpool_bwd')
+
+
+def install(monkeypatch, exact=False):
+    """Swap the ctypes wrappers used by creamfl_b200.{towers,text_towers,clients} for the emulations above and lift
+    the CUDA-only guard of the ParamStore (tests only).  exact=True additionally stores every "bf16" tensor in fp32,
+    which turns the comparison with the fp32 oracle into a sharp check of the host-side sequencing (1e-4 instead of
+    the bf16 noise floor)."""
+    import sys
+    from creamfl_b200 import ops, tower_ops, towers, text_towers
+    me = sys.modules[__name__]
+    monkeypatch.setattr(me, 'BF16', torch.float32 if exact else torch.bfloat16)
+    monkeypatch.setattr(me, 'EXACT', bool(exact))
+    if exact:
+        for mod in (towers, tower_ops, text_towers):
+            monkeypatch.setattr(mod, 'BF16', torch.float32)
     monkeypatch.setattr(towers, '_require_cuda', lambda dev: None)
-    for name in ('gemm_bf16', 'cast_into', 'to_bf16', 'l2_normalize'):
-        monkeypatch.setattr(ops, name, globals()[name])
-    for name in ('wemb_gather', 'wemb_scatter', 'gru_fwd', 'gru_bwd', 'seq_pool_fwd', 'seq_pool_bwd', 'scale_relu_fwd',
-                 'scale_relu_bwd', 'layernorm_fwd', 'layernorm_bwd', 'act_bwd', 'colsum_into', 'relu_inplace'):
-        monkeypatch.setattr(tower_ops, name, globals()[name])
+    for name in _OPS:
+        monkeypatch.setattr(ops, name, getattr(me, name))
+    for name in _TOWER_OPS:
+        monkeypatch.setattr(tower_ops, name, getattr(me, name))

@@ -121,3 +121,37 @@ def test_deepcopy_rebinds_to_its_own_store(emu):
     assert torch.equal(a, b)
     assert clone.txt_enc._whh.data_ptr() != model.txt_enc._whh.data_ptr()
     assert clone.txt_enc._whh.data_ptr() == clone.txt_enc.rnn.weight_hh_l0.data_ptr()
+
+
+def test_mm_text_tower_exact_mode(monkeypatch):
+    """Same sequencing with the "bf16" tensors stored in fp32: every parameter gradient of the GRU text tower agrees
+    with the fp64 oracle to 1e-4 (a wrong operand, transpose or accumulation target would be O(1))."""
+    import copy
+    KE.install(monkeypatch, exact=True)
+    from creamfl_b200.text_towers import TextModel
+    from oracle.torch_towers import RefGRUEncoderText, fill_deterministic
+    g = torch.Generator().manual_seed(31)
+    vocab, b, l = 200, 7, 11
+    lengths = torch.tensor([11, 11, 8, 5, 3, 2, 1])
+    x = torch.randint(1, vocab, (b, l), generator=g)
+    coef = torch.randn(b, 128, generator=g)
+    ref = RefGRUEncoderText(vocab, 300, 128)
+    fill_deterministic(ref, seed=32)
+    model = TextModel(vocab, 300, 128)
+    model.txt_enc.load_state_dict(ref.state_dict(), strict=True)
+    ref64 = copy.deepcopy(ref).double()
+    e64 = ref64(x, lengths)['embedding']
+    (e64 * coef.double()).sum().backward()
+    st = model.store()
+    st.zero_grad()
+    model.train()
+    emb = model(x, lengths)
+    assert _rel(emb.detach(), e64.detach()) < 1e-5
+    (emb * coef).sum().backward()
+    p64 = dict(ref64.named_parameters())
+    for name, p in model.txt_enc.named_parameters():
+        r = p64[name].grad
+        if r is None or float(r.abs().max()) == 0.0:
+            assert float(p.grad.abs().max()) == 0.0, name
+        else:
+            assert _rel(p.grad, r) < 1e-4, (name, _rel(p.grad, r))
