@@ -655,14 +655,20 @@ class _BertFn(torch.autograd.Function):
         h, m0, r0 = T.layernorm_fwd(e, emb.LayerNorm.weight, emb.LayerNorm.bias, emb.LayerNorm.eps)
         saved_layers = []
         maskf = mask.to(torch.float32).contiguous()
-        for lyr in bert.encoder.layer:
+        n_layers = len(bert.encoder.layer)
+        for li, lyr in enumerate(bert.encoder.layer):
             s = lyr.attention.self
             wqkv, _ = store.fused([s.query.weight, s.key.weight, s.value.weight], 3 * d, d)
             bqkv_view = store.flat[store.offsets[id(s.query.bias)]:store.offsets[id(s.query.bias)] + 3 * d]
             qkv = ops.gemm_bf16(h, wqkv, bias=bqkv_view)
             ctxv, probs = T.attn_fwd(qkv, maskf, b, l, heads)
-            ao = ops.gemm_bf16(ctxv, lyr.attention.output.dense.weight._w16, bias=lyr.attention.output.dense.bias,
-                               add=h)
+            # pcme.py:44 reads last_hidden_state[:, 0] only: after the attention of the LAST layer every row-wise op
+            # (output projection, LayerNorms, FFN) runs on the B [CLS] rows instead of the B*L tokens
+            last = li == n_layers - 1
+            a_in = ctxv.view(b, l * d)[:, :d] if last else ctxv
+            r_in = h.view(b, l * d)[:, :d] if last else h
+            ao = ops.gemm_bf16(a_in, lyr.attention.output.dense.weight._w16, bias=lyr.attention.output.dense.bias,
+                               add=r_in)
             ln1 = lyr.attention.output.LayerNorm
             h1, m1, r1 = T.layernorm_fwd(ao, ln1.weight, ln1.bias, ln1.eps)
             ff, pre = ops.gemm_bf16(h1, lyr.intermediate.dense.weight._w16, bias=lyr.intermediate.dense.bias,
@@ -673,7 +679,7 @@ class _BertFn(torch.autograd.Function):
             if need:
                 saved_layers.append((h, qkv, probs, ctxv, ao, m1, r1, h1, pre, ff, fo, m2, r2))
             h = h2
-        cls = h.view(b, l * d)[:, :d]                       # rows b*L of the token matrix (pitch L*d)
+        cls = h                                             # [B, d]: the last layer already reduced to the [CLS] rows
         out = ops.gemm_bf16(cls, lin.weight._w16, bias=lin.bias, out_dtype=torch.float32)
         ctx.model = model
         ctx.saved = (ids, token_type, e, m0, r0, saved_layers, h, b, l) if need else None
@@ -688,13 +694,14 @@ class _BertFn(torch.autograd.Function):
         d, heads = bert.hidden, bert.heads
         t = b * l
         dout16 = ops.to_bf16(dout.contiguous().float())
-        cls = h_last.view(b, l * d)[:, :d]
+        cls = h_last                                        # [B, d]
         ops.gemm_bf16(dout16, cls, a_mn=True, b_mn=True, out=grad_target(lin.weight), split_k=0, accumulate=True)
         T.colsum_into(dout16, grad_target(lin.bias))
-        dh = torch.zeros((t, d), dtype=BF16, device=dout.device)
-        ops.gemm_bf16(dout16, lin.weight._w16, b_mn=True, out=dh.view(b, l * d)[:, :d])
-        for lyr, sv in zip(reversed(bert.encoder.layer), reversed(saved_layers)):
+        dh = ops.gemm_bf16(dout16, lin.weight._w16, b_mn=True)          # [B, d] gradient at the last layer's [CLS] rows
+        n_layers = len(bert.encoder.layer)
+        for li, lyr, sv in zip(reversed(range(n_layers)), reversed(bert.encoder.layer), reversed(saved_layers)):
             h_in, qkv, probs, ctxv, ao, m1, r1, h1, pre, ff, fo, m2, r2 = sv
+            last = li == n_layers - 1
             ln2, ln1 = lyr.output.LayerNorm, lyr.attention.output.LayerNorm
             d_fo = T.layernorm_bwd(dh, fo, ln2.weight, m2, r2, grad_target(ln2.weight), grad_target(ln2.bias),
                                    dx_colsum=grad_target(lyr.output.dense.bias))
@@ -707,9 +714,18 @@ class _BertFn(torch.autograd.Function):
             d_h1 = ops.gemm_bf16(d_pre, lyr.intermediate.dense.weight._w16, b_mn=True, add=d_fo)
             d_ao = T.layernorm_bwd(d_h1, ao, ln1.weight, m1, r1, grad_target(ln1.weight), grad_target(ln1.bias),
                                    dx_colsum=grad_target(lyr.attention.output.dense.bias))
-            ops.gemm_bf16(d_ao, ctxv, a_mn=True, b_mn=True, out=grad_target(lyr.attention.output.dense.weight),
+            a_in = ctxv.view(b, l * d)[:, :d] if last else ctxv
+            ops.gemm_bf16(d_ao, a_in, a_mn=True, b_mn=True, out=grad_target(lyr.attention.output.dense.weight),
                           split_k=0, accumulate=True)
-            d_ctx = ops.gemm_bf16(d_ao, lyr.attention.output.dense.weight._w16, b_mn=True)
+            if last:
+                # scatter the [CLS]-row gradients back to token rows: every other row of the last layer is dead
+                d_ctx = torch.zeros((t, d), dtype=BF16, device=dout.device)
+                ops.gemm_bf16(d_ao, lyr.attention.output.dense.weight._w16, b_mn=True, out=d_ctx.view(b, l * d)[:, :d])
+                d_res = torch.zeros((t, d), dtype=BF16, device=dout.device)
+                d_res.view(b, l * d)[:, :d].copy_(d_ao)
+            else:
+                d_ctx = ops.gemm_bf16(d_ao, lyr.attention.output.dense.weight._w16, b_mn=True)
+                d_res = d_ao
             s = lyr.attention.self
             for p_ in (s.query.weight, s.key.weight, s.value.weight, s.query.bias, s.key.bias, s.value.bias):
                 grad_target(p_)
@@ -717,7 +733,7 @@ class _BertFn(torch.autograd.Function):
             _, gbqkv = store.fused([s.query.bias, s.key.bias, s.value.bias], 3 * d)
             d_qkv = T.attn_bwd(qkv, probs, d_ctx, b, l, heads, dbias=gbqkv)
             ops.gemm_bf16(d_qkv, h_in, a_mn=True, b_mn=True, out=gqkv, split_k=0, accumulate=True)
-            dh = ops.gemm_bf16(d_qkv, wqkv, b_mn=True, add=d_ao)
+            dh = ops.gemm_bf16(d_qkv, wqkv, b_mn=True, add=d_res)
         emb = bert.embeddings
         de = T.layernorm_bwd(dh, e, emb.LayerNorm.weight, m0, r0, grad_target(emb.LayerNorm.weight),
                              grad_target(emb.LayerNorm.bias))
