@@ -30,6 +30,14 @@ from .towers import PCME
 PCME_CRITERION_CFG = {'init_shift': 15, 'init_negative_scale': 15, 'num_samples': 7}    # coco.yaml:41-47
 
 
+def default_device(index: Optional[int] = None) -> torch.device:
+    """The CUDA device the engines run on (current device unless an index is given).  There is no CPU path: without a
+    CUDA device this raises instead of handing back a CPU device."""
+    if not torch.cuda.is_available():
+        raise RuntimeError('creamfl_b200 engines need a CUDA device (the hot path has no CPU fallback)')
+    return torch.device('cuda', torch.cuda.current_device() if index is None else index)
+
+
 def _features(output: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
     return output['image_features'], output['caption_features']
 
@@ -68,7 +76,7 @@ class ServerEngine:
     def __init__(self, embed_dim: int = 256, cnn_type: str = 'resnet101', lr: float = 2e-4, grad_clip: float = 2.0,
                  kd_weight: float = 0.3, device: Optional[torch.device] = None, data_parallel: bool = False,
                  use_graphs: bool = False):
-        self.device = device or torch.device('cuda', torch.cuda.current_device())
+        self.device = device or default_device()
         self._graphs = {}
         self.model = PCME(None, {'embed_dim': embed_dim, 'cnn_type': cnn_type, 'not_bert': False}).to(self.device)
         self.criterion = get_criterion('pcme', PCME_CRITERION_CFG).to(self.device)
@@ -175,7 +183,7 @@ class ServerEngine:
 class MMClient:
     def __init__(self, embed_dim: int = 256, lr: float = 2e-4, grad_clip: float = 2.0, interintra_weight: float = 0.5,
                  vocab_size: int = 11755, device: Optional[torch.device] = None, use_graphs: bool = False):
-        self.device = device or torch.device('cuda', torch.cuda.current_device())
+        self.device = device or default_device()
         self.use_graphs = use_graphs
         self._graphs = {}
         self.model = ClientPCME(vocab_size, embed_dim).to(self.device)

@@ -12,7 +12,7 @@ import time
 
 import torch
 
-from creamfl_b200 import ops
+from creamfl_b200 import engine as _engine, ops
 from creamfl_b200.partition import data_partitioner, distill_lookup, shard_partition
 
 from .ClientTrainer import ClientTrainer
@@ -83,7 +83,7 @@ class MMFL:
     def create_model(self, args):
         """MMFL.py:116-178: Dirichlet(0.1) partitions for the unimodal clients, Flickr shards for the multimodal ones."""
         self.logger.log('start creating model and partition datasets')
-        self.device = torch.device('cuda:%d' % args.device)
+        self.device = _engine.default_device(args.device)
         self.img_local_trainers, self.txt_local_trainers, self.mm_local_trainers = [], [], []
         n_priv = args.private_samples
         if args.num_img_clients > 0:
@@ -93,7 +93,7 @@ class MMFL:
             for i in range(args.num_img_clients):
                 loader = SyntheticLabelled('image', part[i], 512, 100, image_size=args.client_image_size, seed=i)
                 self.img_local_trainers.append(ClientTrainer(args, 'Cifar100', 'Cifar100', None, None, loader,
-                                                             self.logger, client_id=i))
+                                                             self.logger, gpuid=str(self.device), client_id=i))
         if args.num_txt_clients > 0:
             import numpy as np
             part = data_partitioner('AG_NEWS', n_priv, 10, 'hetero', 0.1, np.arange(n_priv) % 4, seed=2021,
@@ -101,7 +101,7 @@ class MMFL:
             for i in range(args.num_txt_clients):
                 loader = SyntheticLabelled('text', part[i], 512, 4, seed=100 + i)
                 self.txt_local_trainers.append(ClientTrainer(args, 'AG_NEWS', 'AG_NEWS', None, None, loader,
-                                                             self.logger, client_id=i))
+                                                             self.logger, gpuid=str(self.device), client_id=i))
         if args.num_mm_clients > 0:
             shards = shard_partition(max(150, n_priv), 15, 150, seed=2021)
             for i in range(args.num_mm_clients):

@@ -36,7 +36,7 @@ class TrainerEngine:
         self.evaluator.set_logger(self.logger)
 
     def model_to_device(self):
-        self.model.to(self.device)
+        self.model.to(self._core.device)
 
     def to_half(self):
         """apex O2 in the reference (retrieval_trainer.py:107-111); the CUDA towers already run bf16 storage with

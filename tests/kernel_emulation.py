@@ -462,3 +462,126 @@ def install(monkeypatch, exact=False):
         monkeypatch.setattr(ops, name, getattr(me, name))
     for name in _TOWER_OPS:
         monkeypatch.setattr(tower_ops, name, getattr(me, name))
+
+
+# ================================================================================================ engine level
+# Loss / aggregation / metric / optimizer entry points, emulated with the CPU oracle (oracle/creamfl_oracle.py - the
+# restatement of the reference's arithmetic that the CUDA kernels are tested against on the GPU).  Used by
+# tests/test_cpu_round_plumbing.py to run the product's orchestrator (src/algorithms) for one communication round on
+# the CPU: BASELINE.json configs[0] "plumbing, no GPU".
+def _O():
+    from oracle import creamfl_oracle
+    return creamfl_oracle
+
+
+def _ste_round(x):
+    """bf16 operand rounding with a straight-through gradient (the kernels round the operand, not the gradient)."""
+    return x + (x.detach().to(BF16).to(x.dtype) - x.detach())
+
+
+def pcme_loss(img, txt, shift, neg_scale):
+    O = _O()
+    i2t = O.pcme_direction_loss(img.float(), txt.float(), shift.float().reshape(()), neg_scale.float().reshape(()))
+    t2i = O.pcme_direction_loss(txt.float(), img.float(), shift.float().reshape(()), neg_scale.float().reshape(()))
+    loss = i2t['loss'] + t2i['loss']
+    parts = torch.stack([loss.detach(), i2t['pos_loss'].detach(), i2t['neg_loss'].detach()]).float()
+    return loss, parts
+
+
+def infonce_loss(q, bank_bf16, labels, inv_tau=2.0):
+    return _O().inter_infonce(_ste_round(q.float()), bank_bf16.float(), labels, tau=1.0 / inv_tau)
+
+
+def moon_intra_loss(z, zold, bank, idx, inv_tau=2.0, denom=None):
+    return _O().moon_intra(z.float(), zold.float(), bank[idx].float(), tau=1.0 / inv_tau, denom=denom)
+
+
+def mse_gather_loss(x, bank, idx):
+    return _O().distill_mse(x.float(), bank, idx)
+
+
+def conw_score(v_bf16, g_bf16):
+    return _O().conw_scores(v_bf16.float(), g_bf16.float())
+
+
+def conw_reduce(vecs, scores, want_weights=False):
+    w = torch.softmax(scores.float(), dim=0)
+    out = sum(v.float() * w[c].reshape(-1, 1) for c, v in enumerate(vecs))
+    return (out, w) if want_weights else out
+
+
+def conw_aggregate(vecs, global_other, want_weights=False):
+    g = global_other.to(BF16).float()
+    scores = torch.stack([conw_score(v.to(BF16), g) for v in vecs], dim=0)
+    return conw_reduce(vecs, scores, want_weights)
+
+
+def recall_ranks(q, g, q_labels, g_labels):
+    return torch.from_numpy(_O().recall_ranks_count(q.float(), g.float(), q_labels.numpy(), g_labels.numpy())).to(torch.int32)
+
+
+class _EmuOptimizer:
+    """Drop-in bodies for creamfl_b200.optim.FusedOptimizer's device-table methods: global-norm clipping + AdamP /
+    Adam / SGD-momentum through the oracle's fp64 restatement, then the bf16 shadow refresh."""
+
+    @staticmethod
+    def _build(self):
+        params = [p for g in self.param_groups for p in g['params']]
+        self._loose = []
+        for p in params:
+            if hasattr(p, '_g2d'):
+                if p.grad is None:
+                    p.grad = p._gview
+            else:
+                gbuf = torch.zeros_like(p.data)
+                if p.grad is not None:
+                    gbuf.copy_(p.grad)
+                p.grad = gbuf
+                self._loose.append((p, gbuf))
+        self._emu = {'step': 0, 'm': [torch.zeros(p.shape, dtype=torch.float64) for p in params],
+                     'v': [torch.zeros(p.shape, dtype=torch.float64) for p in params], 'norm': torch.zeros(())}
+        self._built = True
+
+    @staticmethod
+    def _sync_hyper(self):
+        pass
+
+    @staticmethod
+    def step(self, closure=None):
+        O = _O()
+        self.prepare()
+        params = [p for g in self.param_groups for p in g['params']]
+        hp = self.param_groups[0]
+        grads = [(p.grad if p.grad is not None else torch.zeros_like(p.data)).detach().double().clone() for p in params]
+        if hp['max_norm'] > 0:
+            self._emu['norm'] = torch.tensor(O.clip_grad_norm(
+                [g for p, g in zip(params, grads) if id(p) not in self._no_clip], hp['max_norm']))
+        pd = [p.data.double() for p in params]
+        st = self._emu
+        st['step'] += 1
+        if self.mode == 'sgd':
+            O.sgd_momentum_step(pd, grads, st['m'], st['step'], hp['lr'], hp['momentum'], hp['weight_decay'])
+        else:
+            O.adamp_step(pd, grads, st['m'], st['v'], st['step'], hp['lr'], betas=hp['betas'], eps=hp['eps'],
+                         weight_decay=hp['weight_decay'], delta=hp['delta'] if self.mode == 'adamp' else -1.0,
+                         wd_ratio=hp['wd_ratio'])
+        with torch.no_grad():
+            for p, new in zip(params, pd):
+                p.data.copy_(new.float())
+        for store in self._stores():
+            store.sync_shadow()
+
+
+def install_engine(monkeypatch, exact=False):
+    """install() plus the engine-level entry points and a CPU device for the engines (tests only)."""
+    import sys
+    install(monkeypatch, exact=exact)
+    from creamfl_b200 import engine, ops, optim
+    me = sys.modules[__name__]
+    for name in ('pcme_loss', 'infonce_loss', 'moon_intra_loss', 'mse_gather_loss', 'conw_score', 'conw_reduce',
+                 'conw_aggregate', 'recall_ranks'):
+        monkeypatch.setattr(ops, name, getattr(me, name))
+    monkeypatch.setattr(engine, 'default_device', lambda index=None: torch.device('cpu'))
+    for name in ('_build', '_sync_hyper', 'step'):
+        monkeypatch.setattr(optim.FusedOptimizer, name, getattr(_EmuOptimizer, name))
+    monkeypatch.setattr(optim.FusedOptimizer, 'grad_norm', property(lambda self: self._emu['norm']))

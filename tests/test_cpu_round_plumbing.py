@@ -1,0 +1,87 @@
+"""BASELINE.json configs[0]: "1 FL round, 2 clients, ResNet101+BERT server, 16 synthetic COCO-shape pairs, CPU
+(plumbing, no GPU)".
+
+The product's own orchestrator (src/algorithms/MMFL.py: create_model -> load_dataset -> train(round) with public
+training, extraction, client rounds, con_w aggregation, distillation, Recall@K evaluation) runs one communication
+round on the CPU.  Every C-ABI entry point is replaced by the test-only emulation of tests/kernel_emulation.py (kernel
+semantics from include/creamfl_b200.h, losses / aggregation / optimizer through the CPU oracle); everything above the
+ABI - engines, trainers, parameter stores, index plumbing - is the shipped code.  Nothing here is a product CPU path:
+without the emulation the same call raises (last test)."""
+import sys
+import types
+from pathlib import Path
+
+import pytest
+import torch
+
+import kernel_emulation as KE  # tests/ is on sys.path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _args(**over):
+    a = dict(name='plumbing', local_epochs=1, comm_rounds=1, seed=0, device=0, num_img_clients=0, num_txt_clients=0,
+             num_mm_clients=2, client_num_per_round=2, server_lr=1e-5, disable_distill=False, agg_method='con_w',
+             contrast_local_intra=True, contrast_local_inter=True, mlp_local=False, kd_weight=0.3,
+             interintra_weight=0.5, loss_scale=False, save_client=False, pub_data_num=16, feature_dim=256,
+             not_bert=False, private_samples=150, image_size=224, client_image_size=64, test_images=16, test_folds=2,
+             pub_batch_size=16)
+    a.update(over)
+    return types.SimpleNamespace(**a)
+
+
+def _mmfl():
+    for p in (str(ROOT), str(ROOT / 'src')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from src.algorithms.MMFL import MMFL
+    return MMFL
+
+
+def test_one_round_two_clients_on_cpu(monkeypatch):
+    KE.install_engine(monkeypatch)
+    import random
+    random.seed(0)
+    torch.manual_seed(0)
+    MMFL = _mmfl()
+    args = _args()
+    algo = MMFL(args, None)
+    algo.create_model(args)
+    algo.load_dataset(args)
+    # shrink the two multimodal clients' private shards to one batch each: this is a plumbing run
+    for t in algo.mm_local_trainers:
+        t.train_loader.indices = t.train_loader.indices[:16]
+        t.train_loader.batch_size = 16
+    server = algo.engine.model
+    assert type(server).__name__ == 'PCME' and sum(p.numel() for p in server.parameters()) > 150e6   # ResNet101 + BERT
+    before = server.store().flat.clone()
+    scores = algo.train(0)
+    # public representations of the server and of both clients were produced for the same 16 items, in loader order
+    assert algo.global_img_feature.shape == (16, 256) and algo.global_txt_feature.shape == (16, 256)
+    assert len(algo.distill_index) == 16 and sorted(algo.distill_index) == algo.distill_index
+    # con_w aggregates: convex combinations of unit-norm client rows
+    for agg in (algo.img_vec, algo.txt_vec):
+        assert agg.shape == (16, 256) and torch.isfinite(agg).all() and float(agg.norm(dim=1).max()) <= 1.0 + 1e-4
+    # the server moved (public training + distillation), shadows follow the masters, the scheduler stepped
+    assert not torch.equal(before, server.store().flat)
+    w = server.linear.weight
+    assert torch.equal(w._w16, w.data.to(torch.bfloat16))
+    assert algo.engine.optimizer.param_groups[0]['lr'] < args.server_lr
+    # Recall@K report of the COCO-1K style protocol (2 folds of 8 here)
+    nf = scores['test']['n_fold']
+    for d in ('i2t', 't2i'):
+        assert 0.0 <= nf[d]['recall_1'] <= nf[d]['recall_5'] <= nf[d]['recall_10'] <= 100.0
+    assert scores['test']['rsum'] == scores['test']['i2t']['rsum'] + scores['test']['t2i']['rsum']
+    # clients: models trained, old-model snapshot kept by address for the next round
+    for t in algo.mm_local_trainers:
+        assert t._core.old_model is not None and t.local_epoch == 1
+
+
+def test_orchestrator_refuses_cpu_without_emulation():
+    MMFL = _mmfl()
+    args = _args()
+    if torch.cuda.is_available():
+        pytest.skip('a CUDA device is present: the orchestrator runs on it')
+    algo = MMFL(args, None)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        algo.create_model(args)
