@@ -430,6 +430,15 @@ def run_ours(args):
         line['roofline'] = roofline
     line['roofline_sim'] = roofline_sim
     line['roofline_hbm'] = roofline_hbm
+    if 'A' in phases and phase_ms.get('A_server_train'):
+        # whole server train step against the tensor roofline: algorithmic FLOPs of SURVEY 8d (63.8 GFLOP per pair:
+        # ResNet101 46.8 + BERT-base at L = 32 16.4 + heads) over the measured step time, everything included
+        # (BatchNorm / optimizer / launch gaps count as lost tensor time)
+        step_ms = phase_ms['A_server_train'] / S
+        step_tf = 63.8e9 * B / (step_ms * 1e-3) / 1e12
+        line['roofline_step'] = {'bound': 'tensor', 'kernel': 'one server train step (all kernels, CUDA graph replay)',
+                                 'achieved': round(step_tf, 1), 'peak': peak_tf, 'unit': 'TFLOP/s',
+                                 'frac': round(step_tf / peak_tf, 4), 'ms': round(step_ms, 2), 'traffic': None}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline(steps=1, warmup=0)
     if rank == 0:
