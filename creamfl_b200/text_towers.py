@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import ops, tower_ops as T, towers as _towers
-from .towers import BF16, PIENet, ParamStore, StoreMixin, _Linear, grad_target
+from .towers import PIENet, ParamStore, StoreMixin, _Linear, grad_target
 
 
 class _GRUParams(nn.Module):
@@ -86,7 +86,7 @@ class _TextTowerFn(torch.autograd.Function):
         t = b * l
         h, dw, hd = tw.hidden, tw.word_dim, tw.word_dim // 2
         kp = T.pad8(dw)
-        pie, rnn = tw.pie_net, tw.rnn
+        pie = tw.pie_net
         ln = pie.layer_norm
         for p_ in tw.tower_params():
             grad_target(p_)

@@ -450,12 +450,12 @@ def install(monkeypatch, exact=False):
     which turns the comparison with the fp32 oracle into a sharp check of the host-side sequencing (1e-4 instead of
     the bf16 noise floor)."""
     import sys
-    from creamfl_b200 import ops, tower_ops, towers, text_towers
+    from creamfl_b200 import ops, tower_ops, towers
     me = sys.modules[__name__]
     monkeypatch.setattr(me, 'BF16', torch.float32 if exact else torch.bfloat16)
     monkeypatch.setattr(me, 'EXACT', bool(exact))
     if exact:
-        for mod in (towers, tower_ops, text_towers):
+        for mod in (towers, tower_ops):
             monkeypatch.setattr(mod, 'BF16', torch.float32)
     monkeypatch.setattr(towers, '_require_cuda', lambda dev: None)
     for name in _OPS:
