@@ -428,3 +428,107 @@ int creamfl_scale_relu_bwd(const float* dy, const float* y, int64_t n, float sca
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- dropout variants
+static inline DropSpec make_drop(const void* rng, int site, float p) {
+  DropSpec d{};
+  if (rng != nullptr && site >= 0 && p > 0.0f) {
+    d.rng = reinterpret_cast<const unsigned long long*>(rng);
+    d.site = site;
+    d.thresh = drop_thresh16(p);
+    d.scale = 1.0f / (1.0f - p);
+  }
+  return d;
+}
+static int check_p(const char* who, float p) {
+  if (!(p >= 0.0f && p < 1.0f)) {
+    set_error("%s: dropout probability %g outside [0, 1)", who, (double)p);
+    return CFL_EINVAL;
+  }
+  return CFL_OK;
+}
+
+extern "C" int creamfl_gemm_bf16_drop(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn, int M,
+                                      int N, int K, void* out, int64_t ldo, int out_bf16, const float* bias,
+                                      const void* add, int64_t ld_add, int add_bf16, const void* rng, int site,
+                                      float p_drop, void* stream) {
+  if (!a || !b || !out) {
+    set_error("gemm_bf16_drop: null pointer");
+    return CFL_EINVAL;
+  }
+  int rc = check_p("gemm_bf16_drop", p_drop);
+  if (rc) return rc;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.split_k = 1;
+  p.out = out; p.ldo = ldo; p.out_bf16 = out_bf16;
+  p.bias = bias; p.act = 0; p.alpha = 1.0f;
+  p.add = add; p.ld_add = ld_add; p.add_bf16 = add_bf16;
+  p.drop = make_drop(rng, site, p_drop);
+  return gemm_bf16(a, lda, a_mn, b, ldb, b_mn, p, S(stream));
+}
+
+extern "C" int creamfl_layernorm_fwd_drop(const void* x, const void* res, const float* gamma, const float* beta,
+                                          float eps, int R, int D, int is_bf16, void* y, float* mean, float* rstd,
+                                          const void* rng, int site, float p_drop, void* stream) {
+  if (!x || !gamma || !beta || !y) {
+    set_error("layernorm_fwd_drop: null pointer");
+    return CFL_EINVAL;
+  }
+  int rc = check_p("layernorm_fwd_drop", p_drop);
+  if (rc) return rc;
+  return layernorm_fwd_drop(x, res, gamma, beta, eps, R, D, is_bf16, y, mean, rstd, make_drop(rng, site, p_drop),
+                            S(stream));
+}
+
+extern "C" int creamfl_layernorm_bwd_drop(const void* dy, const void* x, const void* res, const float* gamma,
+                                          const float* mean, const float* rstd, int R, int D, int is_bf16, void* dx,
+                                          void* dx_drop, float* dgamma, float* dbeta, float* dx_colsum, void* ws,
+                                          size_t ws_bytes, const void* rng, int site_in, int site_out, float p_drop,
+                                          void* stream) {
+  if (!dy || !x || !gamma || !mean || !rstd || !dx || !ws) {
+    set_error("layernorm_bwd_drop: null pointer");
+    return CFL_EINVAL;
+  }
+  int rc = check_p("layernorm_bwd_drop", p_drop);
+  if (rc) return rc;
+  return layernorm_bwd_drop(dy, x, res, gamma, mean, rstd, R, D, is_bf16, dx, dx_drop, dgamma, dbeta, dx_colsum, ws,
+                            ws_bytes, make_drop(rng, site_in, p_drop), make_drop(rng, site_out, p_drop), S(stream));
+}
+
+extern "C" int creamfl_attn_fwd_drop(const void* qkv, const float* mask, int B, int L, int H, int head_dim, void* ctx,
+                                     void* probs, const void* rng, int site, float p_drop, void* stream) {
+  if (!qkv || !mask || !ctx || !probs) {
+    set_error("attn_fwd_drop: null pointer");
+    return CFL_EINVAL;
+  }
+  int rc = check_p("attn_fwd_drop", p_drop);
+  if (rc) return rc;
+  return attn_fwd_drop(qkv, mask, B, L, H, head_dim, ctx, probs, make_drop(rng, site, p_drop), S(stream));
+}
+
+extern "C" int creamfl_attn_bwd_drop(const void* qkv, const void* probs, const void* dctx, int B, int L, int H,
+                                     int head_dim, void* dqkv, float* dbias, const void* rng, int site, float p_drop,
+                                     void* stream) {
+  if (!qkv || !probs || !dctx || !dqkv) {
+    set_error("attn_bwd_drop: null pointer");
+    return CFL_EINVAL;
+  }
+  int rc = check_p("attn_bwd_drop", p_drop);
+  if (rc) return rc;
+  return attn_bwd_drop(qkv, probs, dctx, B, L, H, head_dim, dqkv, dbias, make_drop(rng, site, p_drop), S(stream));
+}
+
+extern "C" int creamfl_dropout_mask(const void* rng, int site, int64_t n, float p_drop, void* keep_u8, void* stream) {
+  int rc = check_p("dropout_mask", p_drop);
+  if (rc) return rc;
+  if (p_drop <= 0.0f || site < 0) {
+    set_error("dropout_mask: needs p > 0 and site >= 0");
+    return CFL_EINVAL;
+  }
+  return dropout_mask(make_drop(rng, site, p_drop), n, keep_u8, S(stream));
+}
+
+extern "C" int creamfl_rng_tick(void* rng, void* stream) {
+  return rng_tick(reinterpret_cast<unsigned long long*>(rng), S(stream));
+}

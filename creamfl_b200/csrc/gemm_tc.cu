@@ -227,6 +227,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (etid < BN) { s_csum[etid] = 0.0; s_csq[etid] = 0.0; }
       asm volatile("bar.sync 3, 256;" ::: "memory");
     }
+    // dropout of the linear output (HF BertSelfOutput / BertOutput: dense -> dropout -> + residual): the mask is a
+    // function of (seed, step, site, row * N + column) and is regenerated by the backward kernels (philox.cuh)
+    const bool do_drop = p.drop.rng != nullptr;
+    const unsigned long long drop_seed = do_drop ? p.drop.rng[0] : 0ull;
+    const uint32_t drop_step = do_drop ? (uint32_t)p.drop.rng[1] : 0u;
     int it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
       const int m_blk = u % num_m;
@@ -294,6 +299,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (full_chunk || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+          }
+          if (do_drop) {
+            const unsigned long long e8 = ((unsigned long long)row * (unsigned long long)p.N + col0) >> 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (full_chunk || col0 + 8 * j < p.N) {
+                const uint32_t keep = drop_keep8(drop_seed, drop_step, (uint32_t)p.drop.site, e8 + j, p.drop.thresh);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[8 * j + i] = ((keep >> i) & 1u) ? f[8 * j + i] * p.drop.scale : 0.0f;
+              }
+            }
           }
           if (ADD_TMA) {
             // residual tile staged by the producer: same 128-byte-row swizzled layout as the output staging
@@ -581,6 +597,10 @@ int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long l
   }
   if ((p.split_k > 1 || p.atomic_out) && (p.out_bf16 || p.act != 0 || p.out2 != nullptr)) {
     set_error("gemm_bf16: split-K requires fp32 output without activation");
+    return CFL_EINVAL;
+  }
+  if (p.drop.rng != nullptr && (p.split_k > 1 || p.atomic_out || (p.N & 7))) {
+    set_error("gemm_bf16: dropout needs split_k == 1, a plain output and N %% 8 == 0 (N=%d)", p.N);
     return CFL_EINVAL;
   }
   if ((p.act == 4 || p.act == 5) && p.aux == nullptr) {

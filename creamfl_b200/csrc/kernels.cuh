@@ -1,6 +1,7 @@
 // Internal host-side entry points of the kernel translation units (shared by capi.cu).
 #pragma once
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace cfl {
 // gemm_tc.cu
@@ -23,6 +24,7 @@ struct GemmParams {
   long long ldo2;  // pitch of out2 (0: same as ldo)
   int tma_out;     // set by gemm_bf16: bf16 output leaves through a staged TMA store
   double* stats;   // optional [2N]: += per-column sum and sum of squares of the bf16 output (BatchNorm statistics)
+  DropSpec drop;   // optional dropout of (acc*alpha + bias) BEFORE the residual add (HF BertSelfOutput / BertOutput)
 };
 int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, GemmParams p,
               cudaStream_t stream);
@@ -81,6 +83,14 @@ int layernorm_fwd(const void*, const void*, const float*, const float*, float, i
                   cudaStream_t);
 int layernorm_bwd(const void*, const void*, const void*, const float*, const float*, const float*, int, int, int,
                   void*, float*, float*, float*, void*, size_t, cudaStream_t);
+int layernorm_fwd_drop(const void*, const void*, const float*, const float*, float, int, int, int, void*, float*, float*,
+                       DropSpec, cudaStream_t);
+int layernorm_bwd_drop(const void*, const void*, const void*, const float*, const float*, const float*, int, int, int,
+                       void*, void*, float*, float*, float*, void*, size_t, DropSpec, DropSpec, cudaStream_t);
+int attn_fwd_drop(const void*, const float*, int, int, int, int, void*, void*, DropSpec, cudaStream_t);
+int attn_bwd_drop(const void*, const void*, const void*, int, int, int, int, void*, float*, DropSpec, cudaStream_t);
+int dropout_mask(DropSpec, long long, void*, cudaStream_t);
+int rng_tick(unsigned long long*, cudaStream_t);
 int colsum_bf16(const void*, int, int, long long, float*, cudaStream_t);
 int add_bf16(const void*, const void*, long long, void*, cudaStream_t);
 int embed_fwd(const long long*, const long long*, const float*, const float*, const float*, int, int, int, void*,

@@ -733,7 +733,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, int R, int D, T* __restrict__ y,
-                     float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out, DropSpec drop) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -777,6 +777,12 @@ layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const f
       load8<float>(beta + k, b);
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = fmaf((v[c][i] - mean) * rstd, g[i], b[i]);
+      if (drop.rng != nullptr) {   // y = dropout(LayerNorm(x)) (HF BertEmbeddings)
+        const uint32_t keep = drop_keep8(drop.rng[0], (uint32_t)drop.rng[1], (uint32_t)drop.site,
+                                         ((unsigned long long)row * D + k) >> 3, drop.thresh);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? o[i] * drop.scale : 0.0f;
+      }
       store8<T>(y + (long long)row * D + k, o);
     }
   }
@@ -793,7 +799,10 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ xin, const T* __restrict__ res_in,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
-                     int R, int D, T* __restrict__ dx, float* __restrict__ part /* [gridDim.x, 3, D] */) {
+                     int R, int D, T* __restrict__ dx, float* __restrict__ part /* [gridDim.x, 3, D] */,
+                     DropSpec din /* dy is the gradient of dropout(LN(x)): masked on load */,
+                     DropSpec dout /* also emit dx_drop = dropout'(dx), the gradient of the dense layer under the LN */,
+                     T* __restrict__ dx_drop) {
   extern __shared__ float sh[];  // [warps][3][D]
   const int warps = blockDim.x >> 5;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -812,6 +821,12 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ xin, const 
       if (k < D) {
         float d[8], xv[8], gm[8];
         load8<T>(dy + (long long)row * D + k, d);
+        if (din.rng != nullptr) {
+          const uint32_t keep = drop_keep8(din.rng[0], (uint32_t)din.rng[1], (uint32_t)din.site,
+                                           ((unsigned long long)row * D + k) >> 3, din.thresh);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = ((keep >> i) & 1u) ? d[i] * din.scale : 0.0f;
+        }
         load8<T>(xin + (long long)row * D + k, xv);
         if (res_in) {
           float r[8];
@@ -839,11 +854,18 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ xin, const 
       if (k < D) {
         float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          o[i] = rs * (g[c][i] - s1 - xh[c][i] * s2);
-          ax[c][i] += o[i];          // column sums of dx: the bias gradient of the linear layer feeding this LayerNorm
-        }
+        for (int i = 0; i < 8; ++i) o[i] = rs * (g[c][i] - s1 - xh[c][i] * s2);
         store8<T>(dx + (long long)row * D + k, o);
+        if (dout.rng != nullptr) {
+          const uint32_t keep = drop_keep8(dout.rng[0], (uint32_t)dout.rng[1], (uint32_t)dout.site,
+                                           ((unsigned long long)row * D + k) >> 3, dout.thresh);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? o[i] * dout.scale : 0.0f;
+          store8<T>(dx_drop + (long long)row * D + k, o);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          ax[c][i] += o[i];          // column sums: the bias gradient of the linear layer feeding this LayerNorm
       }
     }
   }
@@ -887,6 +909,11 @@ size_t layernorm_bwd_workspace_bytes(int D) { return (size_t)kLnBwdBlocks * 3 * 
 
 int layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, float eps, int R, int D,
                   int is_bf16, void* y, float* mean, float* rstd, cudaStream_t st) {
+  return layernorm_fwd_drop(x, res, gamma, beta, eps, R, D, is_bf16, y, mean, rstd, DropSpec{}, st);
+}
+
+int layernorm_fwd_drop(const void* x, const void* res, const float* gamma, const float* beta, float eps, int R, int D,
+                       int is_bf16, void* y, float* mean, float* rstd, DropSpec drop, cudaStream_t st) {
   if (R <= 0 || D <= 0 || (D & 7) || D > kLnMaxChunks * 256) {
     set_error("layernorm_fwd: bad shape R=%d D=%d (D %% 8 == 0, D <= %d)", R, D, kLnMaxChunks * 256);
     return CFL_EINVAL;
@@ -895,17 +922,29 @@ int layernorm_fwd(const void* x, const void* res, const float* gamma, const floa
   if (is_bf16)
     layernorm_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(res), gamma, beta, eps, R, D,
-        reinterpret_cast<__nv_bfloat16*>(y), mean, rstd);
+        reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, drop);
   else
     layernorm_fwd_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x),
                                                       reinterpret_cast<const float*>(res), gamma, beta, eps, R, D,
-                                                      reinterpret_cast<float*>(y), mean, rstd);
+                                                      reinterpret_cast<float*>(y), mean, rstd, drop);
   return check_launch("layernorm_fwd");
 }
 
 int layernorm_bwd(const void* dy, const void* xin, const void* res_in, const float* gamma, const float* mean,
                   const float* rstd, int R, int D, int is_bf16, void* dx, float* dgamma, float* dbeta, float* dx_colsum,
                   void* ws, size_t ws_bytes, cudaStream_t st) {
+  return layernorm_bwd_drop(dy, xin, res_in, gamma, mean, rstd, R, D, is_bf16, dx, nullptr, dgamma, dbeta, dx_colsum,
+                            ws, ws_bytes, DropSpec{}, DropSpec{}, st);
+}
+
+int layernorm_bwd_drop(const void* dy, const void* xin, const void* res_in, const float* gamma, const float* mean,
+                       const float* rstd, int R, int D, int is_bf16, void* dx, void* dx_drop, float* dgamma,
+                       float* dbeta, float* dx_colsum, void* ws, size_t ws_bytes, DropSpec din, DropSpec dout,
+                       cudaStream_t st) {
+  if (dout.rng != nullptr && dx_drop == nullptr) {
+    set_error("layernorm_bwd: the dropout output needs a dx_drop buffer");
+    return CFL_EINVAL;
+  }
   if (R <= 0 || D <= 0 || (D & 7) || D > kLnMaxChunks * 256) {
     set_error("layernorm_bwd: bad shape R=%d D=%d", R, D);
     return CFL_EINVAL;
@@ -924,13 +963,13 @@ int layernorm_bwd(const void* dy, const void* xin, const void* res_in, const flo
     layernorm_bwd_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(xin),
         reinterpret_cast<const __nv_bfloat16*>(res_in), gamma, mean, rstd, R, D, reinterpret_cast<__nv_bfloat16*>(dx),
-        part);
+        part, din, dout, reinterpret_cast<__nv_bfloat16*>(dx_drop));
   } else {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     layernorm_bwd_kernel<float><<<blocks, 256, smem, st>>>(
         reinterpret_cast<const float*>(dy), reinterpret_cast<const float*>(xin), reinterpret_cast<const float*>(res_in),
-        gamma, mean, rstd, R, D, reinterpret_cast<float*>(dx), part);
+        gamma, mean, rstd, R, D, reinterpret_cast<float*>(dx), part, din, dout, reinterpret_cast<float*>(dx_drop));
   }
   ln_param_reduce_kernel<<<(3 * D + 255) / 256, 256, 0, st>>>(part, blocks, D, dgamma, dbeta, dx_colsum);
   return check_launch("layernorm_bwd");
@@ -1107,9 +1146,32 @@ __device__ __forceinline__ void load_rows(const __nv_bfloat16* __restrict__ src,
   }
 }
 
+// Dropout of the attention probabilities of one (sequence, head): a[i*lp + j] (and, if given, the transposed copy
+// at[j*lp + i]) is multiplied by keep / (1 - p).  Element index = ((b*H + h)*L + i)*L + j in the [B, H, L, L] tensor;
+// one Philox call per 8-element block of that index space (blocks may straddle rows when L % 8 != 0).
+__device__ __forceinline__ void attn_drop_apply(const DropSpec& drop, int b, int h, int H, int L, int lp, float* a,
+                                                float* at) {
+  const unsigned long long seed = drop.rng[0];
+  const uint32_t step = (uint32_t)drop.rng[1];
+  const unsigned long long base = ((unsigned long long)b * H + h) * (unsigned long long)(L * L);
+  const unsigned long long end = base + (unsigned long long)(L * L);
+  for (unsigned long long blk = (base >> 3) + threadIdx.x; blk <= ((end - 1) >> 3); blk += blockDim.x) {
+    const uint32_t keep = drop_keep8(seed, step, (uint32_t)drop.site, blk, drop.thresh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const unsigned long long e = blk * 8 + i;
+      if (e < base || e >= end) continue;
+      const int rel = (int)(e - base), ii = rel / L, jj = rel % L;
+      const float m = ((keep >> i) & 1u) ? drop.scale : 0.0f;
+      a[ii * lp + jj] *= m;
+      if (at) at[jj * lp + ii] *= m;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ mask, int L, int H, float scale,
-                __nv_bfloat16* __restrict__ ctx, __nv_bfloat16* __restrict__ probs) {
+                __nv_bfloat16* __restrict__ ctx, __nv_bfloat16* __restrict__ probs, DropSpec drop) {
   extern __shared__ __align__(16) float att_sm[];
   const int Lp = (L + 3) & ~3;
   const int lp = Lp + 4;
@@ -1165,6 +1227,10 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__
     }
   }
   __syncthreads();
+  if (drop.rng != nullptr) {   // HF: context = dropout(softmax(scores)) V; the saved probabilities stay un-dropped
+    attn_drop_apply(drop, b, h, H, L, lp, sp, nullptr);
+    __syncthreads();
+  }
   for (int t = threadIdx.x; t < tiles * (kAttD / 4); t += blockDim.x) {
     const int i0 = (t / (kAttD / 4)) * 4, d0 = (t % (kAttD / 4)) * 4;
     float acc[4][4] = {};
@@ -1184,7 +1250,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__
 __global__ void __launch_bounds__(128)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ probs,
                 const __nv_bfloat16* __restrict__ dctx, int L, int H, float scale, __nv_bfloat16* __restrict__ dqkv,
-                float* __restrict__ dbias /* [3*H*64] += column sums of dqkv, or null */) {
+                float* __restrict__ dbias /* [3*H*64] += column sums of dqkv, or null */, DropSpec drop) {
   extern __shared__ __align__(16) float att_sm[];
   __shared__ float s_bias[3 * kAttD];
   for (int e = threadIdx.x; e < 3 * kAttD; e += blockDim.x) s_bias[e] = 0.0f;
@@ -1224,6 +1290,12 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
       for (int y = 0; y < 4; ++y) sds[(i0 + x) * lp + j0 + y] = acc[x][y];
   }
   __syncthreads();
+  if (drop.rng != nullptr) {
+    // forward was ctx = (P o M) V with M = keep / (1 - p): dP = (dO V^T) o M, dV = (P o M)^T dO; the softmax
+    // backward below keeps using the un-dropped P
+    attn_drop_apply(drop, b, h, H, L, lp, sds, spt);
+    __syncthreads();
+  }
   // dS = P * (dP - rowsum(dP * P)) * scale
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = w; i < Lp; i += 4) {
@@ -1276,6 +1348,11 @@ static size_t attn_smem(int L, int mats, int sq_mats) {
 }
 
 int attn_fwd(const void* qkv, const float* mask, int B, int L, int H, int dh, void* ctx, void* probs, cudaStream_t st) {
+  return attn_fwd_drop(qkv, mask, B, L, H, dh, ctx, probs, DropSpec{}, st);
+}
+
+int attn_fwd_drop(const void* qkv, const float* mask, int B, int L, int H, int dh, void* ctx, void* probs,
+                  DropSpec drop, cudaStream_t st) {
   if (B <= 0 || L <= 0 || L > kAttMaxL || dh != kAttD || H <= 0) {
     set_error("attn_fwd: unsupported shape B=%d L=%d H=%d dh=%d (L <= %d, head dim %d)", B, L, H, dh, kAttMaxL, kAttD);
     return CFL_EINVAL;
@@ -1287,12 +1364,17 @@ int attn_fwd(const void* qkv, const float* mask, int B, int L, int H, int dh, vo
   }
   attn_fwd_kernel<<<B * H, 128, attn_smem(L, 3, 1), st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), mask, L, H,
                                                           0.125f, reinterpret_cast<__nv_bfloat16*>(ctx),
-                                                          reinterpret_cast<__nv_bfloat16*>(probs));
+                                                          reinterpret_cast<__nv_bfloat16*>(probs), drop);
   return check_launch("attn_fwd");
 }
 
 int attn_bwd(const void* qkv, const void* probs, const void* dctx, int B, int L, int H, int dh, void* dqkv,
              float* dbias, cudaStream_t st) {
+  return attn_bwd_drop(qkv, probs, dctx, B, L, H, dh, dqkv, dbias, DropSpec{}, st);
+}
+
+int attn_bwd_drop(const void* qkv, const void* probs, const void* dctx, int B, int L, int H, int dh, void* dqkv,
+                  float* dbias, DropSpec drop, cudaStream_t st) {
   if (B <= 0 || L <= 0 || L > kAttMaxL || dh != kAttD || H <= 0) {
     set_error("attn_bwd: unsupported shape");
     return CFL_EINVAL;
@@ -1305,8 +1387,44 @@ int attn_bwd(const void* qkv, const void* probs, const void* dctx, int B, int L,
   attn_bwd_kernel<<<B * H, 128, attn_smem(L, 4, 4), st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                           reinterpret_cast<const __nv_bfloat16*>(probs),
                                                           reinterpret_cast<const __nv_bfloat16*>(dctx), L, H, 0.125f,
-                                                          reinterpret_cast<__nv_bfloat16*>(dqkv), dbias);
+                                                          reinterpret_cast<__nv_bfloat16*>(dqkv), dbias, drop);
   return check_launch("attn_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------ dropout plumbing
+// out[e] = 1 if element e of `site` survives the dropout of the current step, else 0 (the very function the fused
+// kernels evaluate; exported so that parity tests can hand the identical masks to the oracle).
+__global__ void __launch_bounds__(256) dropout_mask_kernel(DropSpec drop, long long n, uint8_t* __restrict__ out) {
+  const long long blocks = (n + 7) >> 3;
+  for (long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x; blk < blocks;
+       blk += (long long)gridDim.x * blockDim.x) {
+    const uint32_t keep = drop_keep8(drop.rng[0], (uint32_t)drop.rng[1], (uint32_t)drop.site,
+                                     (unsigned long long)blk, drop.thresh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (blk * 8 + i < n) out[blk * 8 + i] = (uint8_t)((keep >> i) & 1u);
+  }
+}
+__global__ void rng_tick_kernel(unsigned long long* rng) { rng[1] += 1ull; }
+
+int dropout_mask(DropSpec drop, long long n, void* out, cudaStream_t st) {
+  if (drop.rng == nullptr || n <= 0 || out == nullptr) {
+    set_error("dropout_mask: rng state, n > 0 and an output buffer are required");
+    return CFL_EINVAL;
+  }
+  long long grid = ((n + 7) / 8 + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  dropout_mask_kernel<<<(unsigned)grid, 256, 0, st>>>(drop, n, reinterpret_cast<uint8_t*>(out));
+  return check_launch("dropout_mask");
+}
+
+int rng_tick(unsigned long long* rng, cudaStream_t st) {
+  if (rng == nullptr) {
+    set_error("rng_tick: null state");
+    return CFL_EINVAL;
+  }
+  rng_tick_kernel<<<1, 1, 0, st>>>(rng);
+  return check_launch("rng_tick");
 }
 
 // ------------------------------------------------------------------------------------------------ PIE pooling

@@ -6,8 +6,9 @@ MMClientTrainer.py:133-135): global-norm clipping is folded into the same pass. 
 clients (torch.optim.SGD(lr 1e-4, momentum 0.9, weight_decay 5e-5), ClientTrainer.py:287-288).
 
 It subclasses torch.optim.Optimizer so that the reference's lr schedulers (CosineAnnealingLR, optimizers.py:53-55)
-drive it unchanged; hyper-parameters and the step counter live on the device, so a captured CUDA graph of the step
-stays valid when the schedule changes the learning rate.
+drive it unchanged; hyper-parameters and the step counter live on the device.  A captured CUDA graph of the step reads
+the device hyper-parameter buffer, which `prepare()` re-uploads whenever `param_groups` changed: the engines call it
+before EVERY graph replay (engine._GraphCache.run), so a scheduler step reaches the captured kernels.
 """
 from __future__ import annotations
 
@@ -137,6 +138,14 @@ class FusedOptimizer(torch.optim.Optimizer):
             _p(self._total), _p(self._stats), _p(self._flag), _p(self._tnorm), _p(self._lacc), _stream()),
             'optimizer_step')
         _ops._launches += 4
+
+    def state_tensors(self):
+        """Every device tensor a step() mutates besides the parameters themselves: moments, the step counter / clip
+        state and scratch, and the gradient buffers of parameters outside a ParamStore (used to snapshot / restore
+        around the warm-up run of a CUDA-graph capture)."""
+        self.prepare()
+        return list(self._keep) + [self._state, self._total, self._flag, self._tnorm, self._lacc] + \
+            [g for _, g in self._loose]
 
     def zero_grad(self, set_to_none: bool = False) -> None:
         """Zeroes in place (the kernels accumulate into persistent gradient buffers)."""

@@ -36,6 +36,56 @@ def _chk(rc: int, what: str, launches: int = 1) -> None:
     _ops._launches += launches
 
 
+# --------------------------------------------------------------------------------------------------- dropout
+class DropoutState:
+    """Device-side RNG state of the fused dropouts: int64[2] = {seed, step} (include/creamfl_b200.h, "BERT dropout").
+    `tick()` advances the step with a one-thread kernel (capturable: a replayed CUDA graph draws new masks);
+    `snapshot()` is the frozen copy one forward/backward pair reads; `keep_mask` exports the mask of a site."""
+
+    def __init__(self, seed: int, p: float, device):
+        self.p = float(p)
+        self.rng = torch.tensor([int(seed) & 0x7fffffffffffffff, 0], dtype=torch.int64, device=device)
+
+    def tick(self) -> None:
+        _need_cuda(self.rng)
+        _chk(_lib.load().creamfl_rng_tick(_p(self.rng), _stream()), "rng_tick")
+
+    def snapshot(self) -> "DropoutState":
+        snap = DropoutState.__new__(DropoutState)
+        snap.p, snap.rng = self.p, self.rng.clone()
+        return snap
+
+    def keep_mask(self, site: int, n: int) -> torch.Tensor:
+        """uint8 [n]: 1 where element e of `site` survives at the current step."""
+        _need_cuda(self.rng)
+        out = torch.empty(n, dtype=torch.uint8, device=self.rng.device)
+        _chk(_lib.load().creamfl_dropout_mask(_p(self.rng), int(site), int(n), self.p, _p(out), _stream()),
+             "dropout_mask")
+        return out
+
+
+def _drop_args(drop):
+    """(rng pointer, site, p) of an optional (DropoutState, site) pair."""
+    if drop is None:
+        return None, -1, 0.0
+    state, site = drop
+    return _p(state.rng), int(site), float(state.p)
+
+
+def gemm_drop(a, b, bias, add, drop, out=None):
+    """out = dropout(a b^T + bias) + add  (bf16; HF BertSelfOutput / BertOutput: dense -> dropout -> + residual)."""
+    _need_cuda(a, b, bias, add, out)
+    m, k = a.shape
+    n = b.shape[0]
+    if out is None:
+        out = torch.empty((m, n), dtype=BF16, device=a.device)
+    rng, site, pd = _drop_args(drop)
+    _chk(_lib.load().creamfl_gemm_bf16_drop(_p(a), a.stride(0), 0, _p(b), b.stride(0), 0, m, n, k, _p(out),
+                                            out.stride(0), 1, _p(bias), _p(add), add.stride(0) if add is not None else 0,
+                                            1, rng, site, pd, _stream()), "gemm_bf16_drop")
+    return out
+
+
 # --------------------------------------------------------------------------------------------------- convolution
 def conv_out_hw(h: int, w: int, r: int, s: int, stride: int, pad: int):
     return (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
@@ -165,26 +215,45 @@ def maxpool_bwd(dy, idx, x_shape):
 
 
 # --------------------------------------------------------------------------------------------------- LayerNorm
-def layernorm_fwd(x, gamma, beta, eps, res=None):
+def layernorm_fwd(x, gamma, beta, eps, res=None, drop=None):
+    """drop = (DropoutState, site): y = dropout(LayerNorm(x + res))."""
     r, d = x.shape
     y = torch.empty_like(x)
     mean = torch.empty(r, dtype=torch.float32, device=x.device)
     rstd = torch.empty(r, dtype=torch.float32, device=x.device)
-    _chk(_lib.load().creamfl_layernorm_fwd(_p(x), _p(res), _p(gamma), _p(beta), eps, r, d, int(x.dtype == BF16), _p(y),
-                                           _p(mean), _p(rstd), _stream()), "layernorm_fwd")
+    if drop is None:
+        _chk(_lib.load().creamfl_layernorm_fwd(_p(x), _p(res), _p(gamma), _p(beta), eps, r, d, int(x.dtype == BF16),
+                                               _p(y), _p(mean), _p(rstd), _stream()), "layernorm_fwd")
+    else:
+        rng, site, pd = _drop_args(drop)
+        _chk(_lib.load().creamfl_layernorm_fwd_drop(_p(x), _p(res), _p(gamma), _p(beta), eps, r, d,
+                                                    int(x.dtype == BF16), _p(y), _p(mean), _p(rstd), rng, site, pd,
+                                                    _stream()), "layernorm_fwd_drop")
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, res=None, dx_colsum=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, res=None, dx_colsum=None, drop_in=None, drop_out=None):
+    """drop_in: dy is the gradient of dropout(LayerNorm(.)) (masked on load).  drop_out: returns (dx, dx_drop) with
+    dx_drop = dropout'(dx), the gradient of the dense layer feeding this LayerNorm; dx_colsum then sums dx_drop."""
     r, d = x.shape
     lib = _lib.load()
     dx = torch.empty_like(x)
     nb = lib.creamfl_layernorm_bwd_workspace_bytes(d)
     ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
-    _chk(lib.creamfl_layernorm_bwd(_p(dy), _p(x), _p(res), _p(gamma), _p(mean), _p(rstd), r, d, int(x.dtype == BF16),
-                                   _p(dx), _p(dgamma), _p(dbeta), _p(dx_colsum), _p(ws), nb, _stream()),
-         "layernorm_bwd", 2)
-    return dx
+    if drop_in is None and drop_out is None:
+        _chk(lib.creamfl_layernorm_bwd(_p(dy), _p(x), _p(res), _p(gamma), _p(mean), _p(rstd), r, d,
+                                       int(x.dtype == BF16), _p(dx), _p(dgamma), _p(dbeta), _p(dx_colsum), _p(ws), nb,
+                                       _stream()), "layernorm_bwd", 2)
+        return dx
+    state = (drop_in or drop_out)[0]
+    dx_drop = torch.empty_like(x) if drop_out is not None else None
+    _chk(lib.creamfl_layernorm_bwd_drop(_p(dy), _p(x), _p(res), _p(gamma), _p(mean), _p(rstd), r, d,
+                                        int(x.dtype == BF16), _p(dx), _p(dx_drop), _p(dgamma), _p(dbeta),
+                                        _p(dx_colsum), _p(ws), nb, _p(state.rng),
+                                        drop_in[1] if drop_in is not None else -1,
+                                        drop_out[1] if drop_out is not None else -1, float(state.p), _stream()),
+         "layernorm_bwd_drop", 2)
+    return (dx, dx_drop) if drop_out is not None else dx
 
 
 def colsum_into(x, out):
@@ -220,17 +289,29 @@ def embed_bwd(ids, token_type, dh, seq_len, dword, dpos, dtyp):
                                        _stream()), "embed_bwd")
 
 
-def attn_fwd(qkv, mask, b, l, heads):
+def attn_fwd(qkv, mask, b, l, heads, drop=None):
+    """drop = (DropoutState, site): ctx = dropout(softmax(...)) v; `probs` keeps the un-dropped probabilities."""
     ctx = torch.empty((b * l, heads * 64), dtype=BF16, device=qkv.device)
     probs = torch.empty((b, heads, l, l), dtype=BF16, device=qkv.device)
-    _chk(_lib.load().creamfl_attn_fwd(_p(qkv), _p(mask), b, l, heads, 64, _p(ctx), _p(probs), _stream()), "attn_fwd")
+    if drop is None:
+        _chk(_lib.load().creamfl_attn_fwd(_p(qkv), _p(mask), b, l, heads, 64, _p(ctx), _p(probs), _stream()),
+             "attn_fwd")
+    else:
+        rng, site, pd = _drop_args(drop)
+        _chk(_lib.load().creamfl_attn_fwd_drop(_p(qkv), _p(mask), b, l, heads, 64, _p(ctx), _p(probs), rng, site, pd,
+                                               _stream()), "attn_fwd_drop")
     return ctx, probs
 
 
-def attn_bwd(qkv, probs, dctx, b, l, heads, dbias=None):
+def attn_bwd(qkv, probs, dctx, b, l, heads, dbias=None, drop=None):
     dqkv = torch.empty_like(qkv)
-    _chk(_lib.load().creamfl_attn_bwd(_p(qkv), _p(probs), _p(dctx), b, l, heads, 64, _p(dqkv), _p(dbias), _stream()),
-         "attn_bwd")
+    if drop is None:
+        _chk(_lib.load().creamfl_attn_bwd(_p(qkv), _p(probs), _p(dctx), b, l, heads, 64, _p(dqkv), _p(dbias),
+                                          _stream()), "attn_bwd")
+    else:
+        rng, site, pd = _drop_args(drop)
+        _chk(_lib.load().creamfl_attn_bwd_drop(_p(qkv), _p(probs), _p(dctx), b, l, heads, 64, _p(dqkv), _p(dbias), rng,
+                                               site, pd, _stream()), "attn_bwd_drop")
     return dqkv
 
 

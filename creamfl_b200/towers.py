@@ -613,12 +613,20 @@ class _BertPooler(nn.Module):
 
 
 class BertEncoder(nn.Module):
-    """bert-base-uncased geometry (HF BertConfig defaults); dropout is not applied (the parity
-    protocol runs the reference with dropout frozen)."""
+    """bert-base-uncased geometry (HF BertConfig defaults), including its train-mode dropout:
+    hidden_dropout_prob = attention_probs_dropout_prob = 0.1 at 37 sites per forward (embeddings, and per layer the
+    attention probabilities, the attention output dense and the FFN output dense).  The reference trains with it on
+    (pcme.py:31 builds HF BertModel with default config; retrieval_trainer.py:187 / MMFL.py:293 call model.train()).
+    The masks are Philox-generated inside the kernels (csrc/philox.cuh) and regenerated in the backward; eval mode
+    applies none.  `dropout_p = 0` reproduces the frozen-dropout parity protocol of SURVEY 3.2."""
 
-    def __init__(self, vocab=30522, hidden=768, layers=12, heads=12, ffn=3072, max_pos=512, types=2, eps=1e-12):
+    def __init__(self, vocab=30522, hidden=768, layers=12, heads=12, ffn=3072, max_pos=512, types=2, eps=1e-12,
+                 dropout_p=0.1, seed=None):
         super().__init__()
         self.hidden, self.heads = hidden, heads
+        self.dropout_p = float(dropout_p)
+        self._seed = int(torch.initial_seed() if seed is None else seed)
+        self._drop_state = None
         self.embeddings = _BertEmbeddings(vocab, hidden, max_pos, types, eps)
         self.encoder = _BertEncoderStack(layers, hidden, ffn, eps)
         self.pooler = _BertPooler(hidden)
@@ -629,6 +637,21 @@ class BertEncoder(nn.Module):
                 nn.init.normal_(m.weight, std=0.02)
         with torch.no_grad():
             self.embeddings.word_embeddings.weight[0].zero_()
+
+    def dropout_state(self, device) -> 'T.DropoutState':
+        """Device RNG state {seed, step} of this tower's dropouts (created lazily on the tower's device)."""
+        st = self._drop_state
+        if st is None or st.rng.device != device or st.p != self.dropout_p:
+            st = self._drop_state = T.DropoutState(self._seed, self.dropout_p, device)
+        return st
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == '_drop_state' else copy.deepcopy(v, memo)
+        return new
 
     def qkv_groups(self):
         groups = []
@@ -650,9 +673,16 @@ class _BertFn(torch.autograd.Function):
         d, heads = bert.hidden, bert.heads
         need = any(ctx.needs_input_grad)
         emb = bert.embeddings
+        # train-mode dropout: advance the tower's RNG step, freeze a copy for this forward/backward pair
+        drop_state = None
+        if bert.training and bert.dropout_p > 0.0:
+            live = bert.dropout_state(ids.device)
+            live.tick()
+            drop_state = live.snapshot()
+        ds = (lambda site: (drop_state, site)) if drop_state is not None else (lambda site: None)
         e = T.embed_fwd(ids, token_type, emb.word_embeddings.weight, emb.position_embeddings.weight,
                         emb.token_type_embeddings.weight, l)
-        h, m0, r0 = T.layernorm_fwd(e, emb.LayerNorm.weight, emb.LayerNorm.bias, emb.LayerNorm.eps)
+        h, m0, r0 = T.layernorm_fwd(e, emb.LayerNorm.weight, emb.LayerNorm.bias, emb.LayerNorm.eps, drop=ds(0))
         saved_layers = []
         maskf = mask.to(torch.float32).contiguous()
         n_layers = len(bert.encoder.layer)
@@ -661,19 +691,26 @@ class _BertFn(torch.autograd.Function):
             wqkv, _ = store.fused([s.query.weight, s.key.weight, s.value.weight], 3 * d, d)
             bqkv_view = store.flat[store.offsets[id(s.query.bias)]:store.offsets[id(s.query.bias)] + 3 * d]
             qkv = ops.gemm_bf16(h, wqkv, bias=bqkv_view)
-            ctxv, probs = T.attn_fwd(qkv, maskf, b, l, heads)
+            ctxv, probs = T.attn_fwd(qkv, maskf, b, l, heads, drop=ds(1 + 3 * li))
             # pcme.py:44 reads last_hidden_state[:, 0] only: after the attention of the LAST layer every row-wise op
             # (output projection, LayerNorms, FFN) runs on the B [CLS] rows instead of the B*L tokens
             last = li == n_layers - 1
             a_in = ctxv.view(b, l * d)[:, :d] if last else ctxv
             r_in = h.view(b, l * d)[:, :d] if last else h
-            ao = ops.gemm_bf16(a_in, lyr.attention.output.dense.weight._w16, bias=lyr.attention.output.dense.bias,
-                               add=r_in)
+            if drop_state is not None:      # dense -> dropout -> + residual (HF BertSelfOutput)
+                ao = T.gemm_drop(a_in, lyr.attention.output.dense.weight._w16, lyr.attention.output.dense.bias, r_in,
+                                 ds(2 + 3 * li))
+            else:
+                ao = ops.gemm_bf16(a_in, lyr.attention.output.dense.weight._w16,
+                                   bias=lyr.attention.output.dense.bias, add=r_in)
             ln1 = lyr.attention.output.LayerNorm
             h1, m1, r1 = T.layernorm_fwd(ao, ln1.weight, ln1.bias, ln1.eps)
             ff, pre = ops.gemm_bf16(h1, lyr.intermediate.dense.weight._w16, bias=lyr.intermediate.dense.bias,
                                     act=ops.ACT_GELU, want_preact=True)
-            fo = ops.gemm_bf16(ff, lyr.output.dense.weight._w16, bias=lyr.output.dense.bias, add=h1)
+            if drop_state is not None:      # HF BertOutput
+                fo = T.gemm_drop(ff, lyr.output.dense.weight._w16, lyr.output.dense.bias, h1, ds(3 + 3 * li))
+            else:
+                fo = ops.gemm_bf16(ff, lyr.output.dense.weight._w16, bias=lyr.output.dense.bias, add=h1)
             ln2 = lyr.output.LayerNorm
             h2, m2, r2 = T.layernorm_fwd(fo, ln2.weight, ln2.bias, ln2.eps)
             if need:
@@ -682,15 +719,16 @@ class _BertFn(torch.autograd.Function):
         cls = h                                             # [B, d]: the last layer already reduced to the [CLS] rows
         out = ops.gemm_bf16(cls, lin.weight._w16, bias=lin.bias, out_dtype=torch.float32)
         ctx.model = model
-        ctx.saved = (ids, token_type, e, m0, r0, saved_layers, h, b, l) if need else None
+        ctx.saved = (ids, token_type, e, m0, r0, saved_layers, h, b, l, drop_state) if need else None
         return out
 
     @staticmethod
     def backward(ctx, dout):
         model = ctx.model
         bert, lin, store = model.txt_enc, model.linear, model.store()
-        ids, token_type, e, m0, r0, saved_layers, h_last, b, l = ctx.saved
+        ids, token_type, e, m0, r0, saved_layers, h_last, b, l, drop_state = ctx.saved
         ctx.saved = None
+        ds = (lambda site: (drop_state, site)) if drop_state is not None else (lambda site: None)
         d, heads = bert.hidden, bert.heads
         t = b * l
         dout16 = ops.to_bf16(dout.contiguous().float())
@@ -703,40 +741,45 @@ class _BertFn(torch.autograd.Function):
             h_in, qkv, probs, ctxv, ao, m1, r1, h1, pre, ff, fo, m2, r2 = sv
             last = li == n_layers - 1
             ln2, ln1 = lyr.output.LayerNorm, lyr.attention.output.LayerNorm
+            # d_fo: gradient at the LayerNorm input (-> residual branch); d_fo_d: the same through the dropout of the
+            # dense output (-> weight / bias / input gradients of the dense layer)
             d_fo = T.layernorm_bwd(dh, fo, ln2.weight, m2, r2, grad_target(ln2.weight), grad_target(ln2.bias),
-                                   dx_colsum=grad_target(lyr.output.dense.bias))
-            ops.gemm_bf16(d_fo, ff, a_mn=True, b_mn=True, out=grad_target(lyr.output.dense.weight), split_k=0,
+                                   dx_colsum=grad_target(lyr.output.dense.bias), drop_out=ds(3 + 3 * li))
+            d_fo, d_fo_d = d_fo if drop_state is not None else (d_fo, d_fo)
+            ops.gemm_bf16(d_fo_d, ff, a_mn=True, b_mn=True, out=grad_target(lyr.output.dense.weight), split_k=0,
                           accumulate=True)
-            d_pre = ops.gemm_bf16(d_fo, lyr.output.dense.weight._w16, b_mn=True, act=ops.ACT_DGELU, aux=pre)
+            d_pre = ops.gemm_bf16(d_fo_d, lyr.output.dense.weight._w16, b_mn=True, act=ops.ACT_DGELU, aux=pre)
             ops.gemm_bf16(d_pre, h1, a_mn=True, b_mn=True, out=grad_target(lyr.intermediate.dense.weight), split_k=0,
                           accumulate=True)
             T.colsum_into(d_pre, grad_target(lyr.intermediate.dense.bias))
             d_h1 = ops.gemm_bf16(d_pre, lyr.intermediate.dense.weight._w16, b_mn=True, add=d_fo)
             d_ao = T.layernorm_bwd(d_h1, ao, ln1.weight, m1, r1, grad_target(ln1.weight), grad_target(ln1.bias),
-                                   dx_colsum=grad_target(lyr.attention.output.dense.bias))
+                                   dx_colsum=grad_target(lyr.attention.output.dense.bias), drop_out=ds(2 + 3 * li))
+            d_ao, d_ao_d = d_ao if drop_state is not None else (d_ao, d_ao)
             a_in = ctxv.view(b, l * d)[:, :d] if last else ctxv
-            ops.gemm_bf16(d_ao, a_in, a_mn=True, b_mn=True, out=grad_target(lyr.attention.output.dense.weight),
+            ops.gemm_bf16(d_ao_d, a_in, a_mn=True, b_mn=True, out=grad_target(lyr.attention.output.dense.weight),
                           split_k=0, accumulate=True)
             if last:
                 # scatter the [CLS]-row gradients back to token rows: every other row of the last layer is dead
                 d_ctx = torch.zeros((t, d), dtype=BF16, device=dout.device)
-                ops.gemm_bf16(d_ao, lyr.attention.output.dense.weight._w16, b_mn=True, out=d_ctx.view(b, l * d)[:, :d])
+                ops.gemm_bf16(d_ao_d, lyr.attention.output.dense.weight._w16, b_mn=True,
+                              out=d_ctx.view(b, l * d)[:, :d])
                 d_res = torch.zeros((t, d), dtype=BF16, device=dout.device)
                 d_res.view(b, l * d)[:, :d].copy_(d_ao)
             else:
-                d_ctx = ops.gemm_bf16(d_ao, lyr.attention.output.dense.weight._w16, b_mn=True)
+                d_ctx = ops.gemm_bf16(d_ao_d, lyr.attention.output.dense.weight._w16, b_mn=True)
                 d_res = d_ao
             s = lyr.attention.self
             for p_ in (s.query.weight, s.key.weight, s.value.weight, s.query.bias, s.key.bias, s.value.bias):
                 grad_target(p_)
             wqkv, gqkv = store.fused([s.query.weight, s.key.weight, s.value.weight], 3 * d, d)
             _, gbqkv = store.fused([s.query.bias, s.key.bias, s.value.bias], 3 * d)
-            d_qkv = T.attn_bwd(qkv, probs, d_ctx, b, l, heads, dbias=gbqkv)
+            d_qkv = T.attn_bwd(qkv, probs, d_ctx, b, l, heads, dbias=gbqkv, drop=ds(1 + 3 * li))
             ops.gemm_bf16(d_qkv, h_in, a_mn=True, b_mn=True, out=gqkv, split_k=0, accumulate=True)
             dh = ops.gemm_bf16(d_qkv, wqkv, b_mn=True, add=d_res)
         emb = bert.embeddings
         de = T.layernorm_bwd(dh, e, emb.LayerNorm.weight, m0, r0, grad_target(emb.LayerNorm.weight),
-                             grad_target(emb.LayerNorm.bias))
+                             grad_target(emb.LayerNorm.bias), drop_in=ds(0))
         T.embed_bwd(ids, token_type, de, l, grad_target(emb.word_embeddings.weight),
                     grad_target(emb.position_embeddings.weight), grad_target(emb.token_type_embeddings.weight))
         return (None, None, None, None) + (None,) * (len(ctx.needs_input_grad) - 4)
@@ -757,9 +800,11 @@ class PCME(StoreMixin, nn.Module):
         self.embed_dim = get('embed_dim')
         self.n_embeddings = get('n_samples_inference', 0) or 1
         if get('not_bert', False):
-            raise NotImplementedError('the GRU text tower (config.not_bert) is served by creamfl_b200.clients.ClientPCME')
+            raise NotImplementedError('config.not_bert: build the model with get_model(), which returns the '
+                                      'ResNet + GRU variant (creamfl_b200.clients.ClientPCME)')
         self.img_enc = EncoderImage(config, mlp_local)
-        self.txt_enc = BertEncoder()
+        # HF BertConfig defaults (0.1); `bert_dropout: 0` gives the frozen-dropout parity protocol of SURVEY 3.2
+        self.txt_enc = BertEncoder(dropout_p=get('bert_dropout', 0.1))
         self.linear = _Linear(768, self.embed_dim)
         self.tokenizer = None
 
@@ -826,5 +871,13 @@ class ImageModel(StoreMixin, nn.Module):
 
 
 def get_model(word2idx, config, mlp_local=False):
-    """Mirror of src/networks/models/__init__.py:6-7."""
+    """Mirror of src/networks/models/__init__.py:6-7.  config.not_bert selects the GRU text tower
+    (pcme.py:28-29,37-38; with ResNet50 when it is the server, MMFL.py:82-85)."""
+    get = config.get if hasattr(config, 'get') else (lambda k, d=None: getattr(config, k, d))
+    if get('not_bert', False):
+        if mlp_local:
+            raise NotImplementedError('mlp_local heads are hard-wired to 512-d in the reference (SURVEY appendix B)')
+        from .clients import ClientPCME
+        vocab = len(word2idx) if word2idx else get('vocab_size', 11755)
+        return ClientPCME(vocab, get('embed_dim'), cnn_type=get('cnn_type', 'resnet18'), word_dim=get('word_dim', 300))
     return PCME(word2idx, config, mlp_local)

@@ -261,6 +261,42 @@ int creamfl_seq_pool_bwd(const void* x_bf16, const void* h_bf16, const float* w2
 int creamfl_scale_relu_fwd(const float* x, int64_t n, float scale, float* y, void* stream);
 int creamfl_scale_relu_bwd(const float* dy, const float* y, int64_t n, float scale, float* dx, void* stream);
 
+/* ---- BERT dropout (HF BertConfig defaults hidden_dropout_prob = attention_probs_dropout_prob = 0.1, constructed
+ * at src/networks/models/pcme.py:31 and run under model.train() at src/algorithms/retrieval_trainer.py:187 and
+ * MMFL.py:293; replaces the 37 nn.Dropout / F.dropout calls of one BertModel forward).  Masks are never stored:
+ * every kernel regenerates them with Philox4x32-10 from
+ *   rng   : device uint64[2] {seed, step} (creamfl_rng_tick advances `step` once per training step - inside a
+ *           captured CUDA graph too, so replays draw fresh masks)
+ *   site  : which dropout of the forward (0 embeddings, 1 + 3*layer attention probabilities, 2 + 3*layer attention
+ *           output dense, 3 + 3*layer FFN output dense); site < 0, rng == NULL or p == 0 disable the dropout
+ *   element index e inside the site's tensor; element e is kept iff the 16-bit Philox field (e & 7) of counter
+ *   {e >> 3, site, step}, key seed, is >= round(p * 65536); survivors are scaled by 1 / (1 - p).
+ * creamfl_dropout_mask writes that keep mask (uint8 [n]) so parity tests can feed identical masks to the oracle. */
+int creamfl_rng_tick(void* rng, void* stream);
+int creamfl_dropout_mask(const void* rng, int site, int64_t n, float p_drop, void* keep_u8, void* stream);
+/* out[M,N] = dropout(A B^T + bias) + add   (element index row * N + column; N % 8 == 0) */
+int creamfl_gemm_bf16_drop(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn, int M, int N,
+                           int K, void* out, int64_t ldo, int out_bf16, const float* bias, const void* add,
+                           int64_t ld_add, int add_bf16, const void* rng, int site, float p_drop, void* stream);
+/* y = dropout(LayerNorm(x + res))   (HF BertEmbeddings; element index row * D + column) */
+int creamfl_layernorm_fwd_drop(const void* x, const void* res, const float* gamma, const float* beta, float eps, int R,
+                               int D, int is_bf16, void* y, float* mean, float* rstd, const void* rng, int site,
+                               float p_drop, void* stream);
+/* creamfl_layernorm_bwd with (a) site_in >= 0: dy is the gradient of dropout(LayerNorm(.)) and is masked on load,
+ * (b) site_out >= 0: dx_drop = dropout'(dx) is written next to dx - the gradient of the dense layer whose dropped
+ * output (plus residual) this LayerNorm normalises - and dx_colsum sums dx_drop instead of dx */
+int creamfl_layernorm_bwd_drop(const void* dy, const void* x, const void* res, const float* gamma, const float* mean,
+                               const float* rstd, int R, int D, int is_bf16, void* dx, void* dx_drop, float* dgamma,
+                               float* dbeta, float* dx_colsum, void* workspace, size_t workspace_bytes,
+                               const void* rng, int site_in, int site_out, float p_drop, void* stream);
+/* ctx = dropout(softmax(q k^T / 8 + mask)) v; probs keeps the un-dropped probabilities
+ * (element index ((b*H + h)*L + i)*L + j) */
+int creamfl_attn_fwd_drop(const void* qkv_bf16, const float* mask, int B, int L, int H, int head_dim, void* ctx_bf16,
+                          void* probs_bf16, const void* rng, int site, float p_drop, void* stream);
+int creamfl_attn_bwd_drop(const void* qkv_bf16, const void* probs_bf16, const void* dctx_bf16, int B, int L, int H,
+                          int head_dim, void* dqkv_bf16, float* dbias, const void* rng, int site, float p_drop,
+                          void* stream);
+
 /* ---- fused optimizer step: global-norm clipping + AdamP / Adam / SGD-momentum + bf16 shadow refresh in four
  * launches for any number of tensors.  Replaces adamp.AdamP.step (third-party adamp==0.3.0, call site
  * src/algorithms/optimizers.py:24-28), clip_grad_norm_ (retrieval_trainer.py:211-214) and torch.optim.SGD

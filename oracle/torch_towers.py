@@ -83,12 +83,16 @@ class RefPCME(nn.Module):
     """reference src/networks/models/pcme.py:15-57 with the BERT tower and pre-tokenised inputs (the reference
     tokenises strings on the host inside forward, pcme.py:40-42)."""
 
-    def __init__(self, cnn_type, embed_dim, bert_config=None):
+    def __init__(self, cnn_type, embed_dim, bert_config=None, bert_dropout=0.0):
         super().__init__()
         from transformers import BertConfig, BertModel
         cfg = bert_config or BertConfig()
-        cfg.hidden_dropout_prob = 0.0             # parity protocol: dropout frozen (SURVEY.md 3.2)
-        cfg.attention_probs_dropout_prob = 0.0
+        # bert_dropout = 0: dropout frozen (SURVEY.md 3.2).  bert_dropout = 0.1 is what the reference trains with
+        # (HF defaults, pcme.py:31); run the forward under `frozen_dropout` to feed it given keep masks.
+        cfg.hidden_dropout_prob = float(bert_dropout)
+        cfg.attention_probs_dropout_prob = float(bert_dropout)
+        if bert_dropout > 0:
+            cfg._attn_implementation = 'eager'    # the eager path calls F.dropout on the probabilities (patchable)
         self.embed_dim = embed_dim
         self.img_enc = RefEncoderImage(cnn_type, embed_dim)
         self.txt_enc = BertModel(cfg)
@@ -100,6 +104,33 @@ class RefPCME(nn.Module):
                                       token_type_ids=token_type_ids)
         cap = l2_normalize(self.linear(caption_output['last_hidden_state'][:, 0, :]))     # pcme.py:44
         return {'image_features': image_output['embedding'], 'caption_features': cap}
+
+
+class frozen_dropout:
+    """Context manager that replaces `torch.nn.functional.dropout` (reached by nn.Dropout and by HF's eager
+    attention) with a multiplication by caller-supplied keep masks: `provider(call_index, shape)` returns the keep
+    mask (0/1, broadcastable to `shape`) of the call_index-th train-mode dropout of the forward.  For HF BertModel
+    the call order is: embeddings (0), then per layer attention probabilities (1 + 3l), attention output (2 + 3l),
+    FFN output (3 + 3l) - the site numbering of include/creamfl_b200.h."""
+
+    def __init__(self, provider):
+        self.provider, self.calls, self._orig = provider, 0, None
+
+    def __enter__(self):
+        self._orig = F.dropout
+
+        def masked(input, p=0.5, training=True, inplace=False):
+            if not training or p == 0.0:
+                return input
+            keep = self.provider(self.calls, tuple(input.shape)).to(input.dtype).to(input.device)
+            self.calls += 1
+            return input * keep / (1.0 - p)
+        torch.nn.functional.dropout = masked
+        return self
+
+    def __exit__(self, *exc):
+        torch.nn.functional.dropout = self._orig
+        return False
 
 
 def fill_deterministic(module: nn.Module, seed: int = 0) -> None:

@@ -14,7 +14,8 @@ class MMClientTrainer:
         self.args, self.train_loader, self.client, self.logger = args, train_loader, client, logger
         self.client_idx = client
         self.local_epochs, self.local_epoch, self.cur_epoch = args.local_epochs, 0, 0
-        self._core = MMClient(embed_dim=args.feature_dim, interintra_weight=args.interintra_weight)
+        self._core = MMClient(embed_dim=args.feature_dim, interintra_weight=args.interintra_weight,
+                              use_graphs=not getattr(args, 'no_cuda_graphs', True))
         self.model, self.criterion, self.optimizer = self._core.model, self._core.criterion, self._core.optimizer
         self.device = self._core.device
 
@@ -34,7 +35,9 @@ class MMClientTrainer:
         if not (intra or inter):
             return
         g_img, g_txt = global_img_feature.to(dev).float(), global_txt_feature.to(dev).float()
-        g_img16, g_txt16 = ops.to_bf16(g_img), ops.to_bf16(g_txt)
+        g_img16 = g_txt16 = None
+        if not self._core.use_graphs:          # (the graphed client keeps persistent fp32 + bf16 copies itself)
+            g_img16, g_txt16 = ops.to_bf16(g_img), ops.to_bf16(g_txt)
         lut = distill_lookup(distill_index, dev)
         for images, captions, captions_word, caption_lens, _, _, index in global_train_loader:
             d_idx = lut[torch.as_tensor(index, device=dev)]

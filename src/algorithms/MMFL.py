@@ -53,7 +53,8 @@ class MMFL:
         a = self.args
         self.config = {
             'model': {'embed_dim': a.feature_dim, 'cnn_type': 'resnet50' if a.not_bert else 'resnet101',
-                      'not_bert': False, 'n_samples_inference': 7},
+                      'not_bert': bool(a.not_bert), 'n_samples_inference': 7},           # MMFL.py:82-85
+            'cuda_graphs': not getattr(a, 'no_cuda_graphs', True),
             'optimizer': {'name': 'adamp', 'learning_rate': a.server_lr, 'weight_decay': 0.0},
             'lr_scheduler': {'name': 'cosine_annealing', 'T_max': 30},
             'criterion': {'name': 'pcme', 'init_negative_scale': 15, 'init_shift': 15},
@@ -88,16 +89,16 @@ class MMFL:
         n_priv = args.private_samples
         if args.num_img_clients > 0:
             import numpy as np
-            part = data_partitioner('cifar100', n_priv, 10, 'hetero', 0.1, np.arange(n_priv) % 100, seed=2021,
-                                    min_size=min(10, n_priv // 400))
+            part = data_partitioner('cifar100', n_priv, args.num_img_clients, 'hetero', 0.1, np.arange(n_priv) % 100,
+                                    seed=2021, min_size=min(10, n_priv // 400))     # get_FL_trainloader(.., num_clients)
             for i in range(args.num_img_clients):
                 loader = SyntheticLabelled('image', part[i], 512, 100, image_size=args.client_image_size, seed=i)
                 self.img_local_trainers.append(ClientTrainer(args, 'Cifar100', 'Cifar100', None, None, loader,
                                                              self.logger, gpuid=str(self.device), client_id=i))
         if args.num_txt_clients > 0:
             import numpy as np
-            part = data_partitioner('AG_NEWS', n_priv, 10, 'hetero', 0.1, np.arange(n_priv) % 4, seed=2021,
-                                    min_size=min(3000, n_priv // 40))
+            part = data_partitioner('AG_NEWS', n_priv, args.num_txt_clients, 'hetero', 0.1, np.arange(n_priv) % 4,
+                                    seed=2021, min_size=min(3000, n_priv // 40))
             for i in range(args.num_txt_clients):
                 loader = SyntheticLabelled('text', part[i], 512, 4, seed=100 + i)
                 self.txt_local_trainers.append(ClientTrainer(args, 'AG_NEWS', 'AG_NEWS', None, None, loader,
@@ -123,7 +124,8 @@ class MMFL:
         core = self.engine._core                                                                          # step 3
         img_feature, txt_feature, distill_index = [], [], []
         for images, captions, captions_word, caption_lens, _, _, index in self.dataloaders_global[f'train_subset_eval_{n}']:
-            fi, ft = core.extract(images.to(core.device, non_blocking=True), captions_word)
+            fi, ft = core.extract(images.to(core.device, non_blocking=True),
+                                  self.engine.text_input(captions, captions_word, caption_lens))
             img_feature.append(fi.clone())
             txt_feature.append(ft.clone())
             distill_index.extend(index)
@@ -153,6 +155,10 @@ class MMFL:
         rsum = test_scores['test']['n_fold']['rsum'] if args.test_folds else test_scores['test']['rsum']
         if self.best_score < rsum:
             self.best_score, self.best_scores = rsum, test_scores        # (the reference never updates best_score, :276)
+            self.best_metadata = {'best_score': rsum, 'best_epoch': round_n + 1}
+            core.save_checkpoint(args.name + '-best_model.pt')                                            # :281
+        if round_n == args.comm_rounds - 1:
+            core.save_checkpoint(args.name + '-last_model.pt')                                            # :284
         self.engine.lr_scheduler.step()                                                                   # step 7
         return test_scores
 
@@ -172,6 +178,7 @@ class MMFL:
         self.logger.log('start distilling')
         for images, captions, captions_word, caption_lens, _, _, index in self.dataloaders_global[f'train_subset_{n}']:
             d_idx = lut[torch.as_tensor(index, device=core.device)]
-            core.distill_step(images.to(core.device, non_blocking=True), captions_word, d_idx, agg_img, agg_txt,
+            core.distill_step(images.to(core.device, non_blocking=True),
+                              self.engine.text_input(captions, captions_word, caption_lens), d_idx, agg_img, agg_txt,
                               img_terms=img_terms if agg_img is not None else 0,
                               txt_terms=txt_terms if agg_txt is not None else 0)

@@ -26,7 +26,9 @@ class TrainerEngine:
         self._core = ServerEngine(embed_dim=model_cfg['embed_dim'], cnn_type=model_cfg.get('cnn_type', 'resnet101'),
                                   lr=opt_cfg.get('learning_rate', 2e-4),
                                   grad_clip=config.get('train', {}).get('grad_clip', 2.0),
-                                  kd_weight=config.get('kd_weight', 0.3))
+                                  kd_weight=config.get('kd_weight', 0.3), not_bert=model_cfg.get('not_bert', False),
+                                  vocab_size=len(word2idx) if word2idx else 11755,
+                                  use_graphs=config.get('cuda_graphs', False))
         self.model, self.criterion, self.optimizer = self._core.model, self._core.criterion, self._core.optimizer
         self.lr_scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(
             self.optimizer, T_max=config.get('lr_scheduler', {}).get('T_max', 30))
@@ -42,6 +44,13 @@ class TrainerEngine:
         """apex O2 in the reference (retrieval_trainer.py:107-111); the CUDA towers already run bf16 storage with
         fp32 accumulation and need no loss scaling."""
 
+    def text_input(self, captions, captions_word, caption_lens):
+        """What the server's text tower consumes from a loader batch: BERT tokens / caption strings
+        (pcme.py:40-43), or the vocabulary-id sentences + lengths of the `--not_bert` GRU server (pcme.py:37-38)."""
+        if self._core.not_bert:
+            return captions.to(self._core.device, non_blocking=True), caption_lens
+        return captions_word
+
     def train(self, tr_loader, pub_data_ratio=1.):
         """One public-data epoch (retrieval_trainer.py:185-214)."""
         dev = self._core.device
@@ -49,7 +58,8 @@ class TrainerEngine:
         for idx, (images, captions, captions_word, caption_lens, _a, _b, index) in enumerate(tr_loader):
             if idx == int(len(tr_loader) * pub_data_ratio):
                 break
-            last = self._core.train_step(images.to(dev, non_blocking=True), captions_word)
+            last = self._core.train_step(images.to(dev, non_blocking=True),
+                                         self.text_input(captions, captions_word, caption_lens))
         return last
 
     @torch.no_grad()

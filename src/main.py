@@ -64,6 +64,8 @@ def args():
     p('--test_images', type=int, default=5000)
     p('--test_folds', type=int, default=5)
     p('--pub_batch_size', type=int, default=128)
+    p('--no_cuda_graphs', action='store_true', default=False,
+      help='launch every kernel eagerly (default: each step function is captured as a CUDA graph, the path bench.py times)')
 
 
 args()

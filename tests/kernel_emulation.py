@@ -191,25 +191,96 @@ def scale_relu_bwd(dy, y, scale):
     return torch.where(y > 0, dy * scale, torch.zeros_like(dy))
 
 
-def layernorm_fwd(x, gamma, beta, eps, res=None):
+# ---- dropout (include/creamfl_b200.h "BERT dropout"): Philox4x32-10 restated in numpy, independent of csrc/philox.cuh
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10 (Salmon et al., SC'11): uint32 arrays in, four uint32 arrays out."""
+    import numpy as np
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) for c in (c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    m32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c0
+        p1 = np.uint64(0xCD9E8D57) * c2
+        n0 = ((p1 >> np.uint64(32)) ^ c1 ^ k0) & m32
+        n1 = p1 & m32
+        n2 = ((p0 >> np.uint64(32)) ^ c3 ^ k1) & m32
+        n3 = p0 & m32
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        k0 = (k0 + np.uint64(0x9E3779B9)) & m32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & m32
+    return c0, c1, c2, c3
+
+
+def keep_mask_np(seed, step, site, n, p):
+    """uint8 [n] keep mask of a dropout site: element e is kept iff 16-bit field (e & 7) of Philox(counter
+    {e >> 3, site, step}, key seed) >= round(p * 65536)."""
+    import numpy as np
+    blocks = (n + 7) // 8
+    e8 = np.arange(blocks, dtype=np.uint64)
+    r = philox4x32_10(e8 & np.uint64(0xFFFFFFFF), e8 >> np.uint64(32), np.full(blocks, site, dtype=np.uint64),
+                      np.full(blocks, step & 0xFFFFFFFF, dtype=np.uint64), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    thresh = np.uint64(int(p * 65536.0 + 0.5))
+    fields = np.stack([f for w in r for f in (w & np.uint64(0xFFFF), w >> np.uint64(16))], axis=1)   # [blocks, 8]
+    return (fields >= thresh).astype(np.uint8).reshape(-1)[:n]
+
+
+def _dropstate_tick(self):
+    self.rng[1] += 1
+
+
+def _dropstate_keep_mask(self, site, n):
+    seed, step = (int(v) for v in self.rng.tolist())
+    return torch.from_numpy(keep_mask_np(seed, step, int(site), int(n), self.p))
+
+
+def _mask_scale(drop, shape):
+    state, site = drop
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return _dropstate_keep_mask(state, site, n).view(*shape).float() / (1.0 - state.p)
+
+
+def gemm_drop(a, b, bias, add, drop, out=None):
+    acc = a.float() @ b.float().t()
+    if bias is not None:
+        acc = acc + bias.float()
+    if drop is not None:
+        acc = acc * _mask_scale(drop, acc.shape)
+    if add is not None:
+        acc = acc + add.float()
+    if out is None:
+        return acc.to(BF16)
+    out.copy_(acc.to(out.dtype))
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, eps, res=None, drop=None):
     s = x.float() + (res.float() if res is not None else 0)
     mean = s.mean(-1)
     var = s.var(-1, unbiased=False)
     rstd = (var + eps).rsqrt()
     y = (s - mean[:, None]) * rstd[:, None] * gamma + beta
+    if drop is not None:
+        y = y * _mask_scale(drop, y.shape)
     return y.to(x.dtype), mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, res=None, dx_colsum=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, res=None, dx_colsum=None, drop_in=None, drop_out=None):
     s = x.float() + (res.float() if res is not None else 0)
     xhat = (s - mean[:, None]) * rstd[:, None]
     dy = dy.float()
+    if drop_in is not None:
+        dy = dy * _mask_scale(drop_in, dy.shape)
     dgamma += (dy * xhat).sum(0)
     dbeta += dy.sum(0)
     g = dy * gamma
     dx = rstd[:, None] * (g - g.mean(-1, keepdim=True) - xhat * (g * xhat).mean(-1, keepdim=True))
+    dxd = dx * _mask_scale(drop_out, dx.shape) if drop_out is not None else dx
     if dx_colsum is not None:
-        dx_colsum += dx.sum(0)
+        dx_colsum += dxd.sum(0)
+    if drop_out is not None:
+        return dx.to(x.dtype), dxd.to(x.dtype)
     return dx.to(x.dtype)
 
 
@@ -372,22 +443,27 @@ def _split_heads(qkv, b, l, heads):
     return q, k, v
 
 
-def attn_fwd(qkv, mask, b, l, heads):
+def attn_fwd(qkv, mask, b, l, heads, drop=None):
     q, k, v = _split_heads(qkv, b, l, heads)
     s = q @ k.transpose(-1, -2) * 0.125
     s = s + torch.where(mask > 0.5, 0.0, -3.0e38)[:, None, None, :]                     # HF extended mask
-    p = torch.softmax(s, dim=-1)
-    ctx = (p @ v).permute(0, 2, 1, 3).reshape(b * l, heads * 64)
-    return ctx.to(BF16), p.to(BF16)
+    p = torch.softmax(s, dim=-1).to(BF16)          # rounded once: the kernel multiplies the bf16 probabilities
+    pd = p.float() * _mask_scale(drop, p.shape) if drop is not None else p.float()
+    ctx = (pd @ v).permute(0, 2, 1, 3).reshape(b * l, heads * 64)
+    return ctx.to(BF16), p
 
 
-def attn_bwd(qkv, probs, dctx, b, l, heads, dbias=None):
+def attn_bwd(qkv, probs, dctx, b, l, heads, dbias=None, drop=None):
     q, k, v = _split_heads(qkv, b, l, heads)
     p = probs.float()
     do = dctx.float().view(b, l, heads, 64).permute(0, 2, 1, 3)
     dp = do @ v.transpose(-1, -2)
+    pd = p
+    if drop is not None:
+        m = _mask_scale(drop, p.shape)
+        dp, pd = dp * m, p * m
     ds = p * (dp - (dp * p).sum(-1, keepdim=True)) * 0.125
-    dq, dk, dv = ds @ k, ds.transpose(-1, -2) @ q, p.transpose(-1, -2) @ do
+    dq, dk, dv = ds @ k, ds.transpose(-1, -2) @ q, pd.transpose(-1, -2) @ do
     dqkv = torch.stack([dq, dk, dv], 0).permute(1, 3, 0, 2, 4).reshape(b * l, 3 * heads * 64)
     if dbias is not None:
         dbias += dqkv.sum(0)
@@ -441,7 +517,7 @@ _TOWER_OPS = ('wemb_gather', 'wemb_scatter', 'gru_fwd', 'gru_bwd', 'seq_pool_fwd
               'scale_relu_bwd', 'layernorm_fwd', 'layernorm_bwd', 'act_bwd', 'colsum_into', 'relu_inplace', 'conv_fprop',
               'conv_dgrad', 'conv_wgrad', 'im2col_images', 'bn_train_fwd', 'bn_eval_fwd', 'bn_train_bwd', 'maxpool_fwd',
               'maxpool_bwd', 'embed_fwd', 'embed_bwd', 'attn_fwd', 'attn_bwd', 'pie_pool_fwd', 'pie_pool_bwd',
-              'avgpool_fwd', 'avgpool_bwd')
+              'avgpool_fwd', 'avgpool_bwd', 'gemm_drop')
 
 
 def install(monkeypatch, exact=False):
@@ -462,6 +538,8 @@ def install(monkeypatch, exact=False):
         monkeypatch.setattr(ops, name, getattr(me, name))
     for name in _TOWER_OPS:
         monkeypatch.setattr(tower_ops, name, getattr(me, name))
+    monkeypatch.setattr(tower_ops.DropoutState, 'tick', _dropstate_tick)
+    monkeypatch.setattr(tower_ops.DropoutState, 'keep_mask', _dropstate_keep_mask)
 
 
 # ================================================================================================ engine level

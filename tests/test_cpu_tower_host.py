@@ -22,14 +22,15 @@ def _rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def _pcme_pair(embed_dim=64, layers=2, seed=5):
+def _pcme_pair(embed_dim=64, layers=2, seed=5, dropout=0.0):
+    """dropout = 0: the frozen-dropout parity protocol; tests/test_cpu_dropout.py covers 0.1."""
     from transformers import BertConfig
     from creamfl_b200 import towers
     from oracle import torch_towers as RT
-    ref = RT.RefPCME('resnet18', embed_dim, BertConfig(num_hidden_layers=layers))
+    ref = RT.RefPCME('resnet18', embed_dim, BertConfig(num_hidden_layers=layers), bert_dropout=dropout)
     RT.fill_deterministic(ref, seed=seed)
-    mine = towers.PCME(None, {'embed_dim': embed_dim, 'cnn_type': 'resnet18'})
-    mine.txt_enc = towers.BertEncoder(layers=layers)
+    mine = towers.PCME(None, {'embed_dim': embed_dim, 'cnn_type': 'resnet18', 'bert_dropout': dropout})
+    mine.txt_enc = towers.BertEncoder(layers=layers, dropout_p=dropout, seed=1234)
     mine.load_state_dict(ref.state_dict(), strict=True)
     return ref.train(), mine.train()
 

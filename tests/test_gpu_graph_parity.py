@@ -1,0 +1,180 @@
+"""Parity of the configuration bench.py actually times: CUDA-graph replay of the step functions, the learning-rate
+schedule reaching captured kernels, and the NCCL data-parallel server.
+
+The kernels accumulate weight gradients with fp32 atomics (split-K `red.global.add`), so two EAGER runs of the same
+step from the same state already differ in the last bits.  "Graph replay == eager" is therefore asserted against
+that measured run-to-run noise: max|graph - eager| <= 4 * max|eager' - eager| + one fp32 ulp of the group's largest value, per tensor group, on the flat parameter buffer, BatchNorm running statistics / counters, criterion
+parameters, AdamP moments and the step's losses."""
+import os
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope='module')
+def engine():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from creamfl_b200 import engine as e
+    return e
+
+
+def _server_inputs(B, L, seed):
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randn(B, 3, 224, 224, generator=g).cuda()
+    lens = torch.sort(torch.randint(8, L + 1, (B,), generator=g), descending=True).values
+    lens[0] = L
+    mask = (torch.arange(L)[None] < lens[:, None]).long()
+    ids = torch.randint(1000, 30522, (B, L), generator=g)
+    ids[:, 0] = 101
+    return images, {'input_ids': (ids * mask).cuda(), 'attention_mask': mask.cuda()}
+
+
+def _groups(eng):
+    st = eng.model.store()
+    out = {'params': st.flat.clone(), 'shadow': st.shadow.float().clone(),
+           'bn': torch.cat([b.detach().float().flatten() for b in eng.model.buffers()]),
+           'moments': torch.cat([t.flatten() for t in eng.optimizer._keep])}
+    if eng.criterion is not None:
+        out['criterion'] = torch.cat([p.detach().flatten() for p in eng.criterion.parameters()])
+    return out
+
+
+def _maxdiff(a, b):
+    return {k: float((a[k].double() - b[k].double()).abs().max()) for k in a}
+
+
+def _assert_within_noise(test, base, noise_run, what):
+    d, noise = _maxdiff(test, base), _maxdiff(noise_run, base)
+    floor = {k: 1e-6 * max(1.0, float(base[k].abs().max())) for k in d}       # one fp32 ulp of the group's largest value
+    bad = {k: (d[k], noise[k]) for k in d if d[k] > 4 * noise[k] + floor[k]}
+    assert not bad, (what, bad)
+
+
+def _run_server(engine, graphs, steps, batches, sched=False, dropout=0.1):
+    torch.manual_seed(7)                      # identical random init and dropout seed for every run
+    srv = engine.ServerEngine(256, 'resnet101', lr=2e-4, use_graphs=graphs, bert_dropout=dropout)
+    scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(srv.optimizer, T_max=3) if sched else None
+    losses = []
+    for s in range(steps):
+        images, tok = batches[s % len(batches)]
+        losses.append(srv.train_step(images, tok).item())
+        if scheduler is not None:
+            scheduler.step()
+    torch.cuda.synchronize()
+    return srv, _groups(srv), losses
+
+
+def test_server_graph_replay_equals_eager_over_three_steps(engine):
+    batches = [_server_inputs(16, 32, 100 + s) for s in range(2)]
+    _, eager, l_eager = _run_server(engine, False, 3, batches)
+    _, eager2, l_eager2 = _run_server(engine, False, 3, batches)
+    srv, graph, l_graph = _run_server(engine, True, 3, batches)
+    assert int(srv.model.img_enc.cnn.bn1.num_batches_tracked) == 3          # the capture's warm-up was rolled back
+    assert float(srv.optimizer._state[0]) == 3.0                            # AdamP step counter
+    _assert_within_noise(graph, eager, eager2, 'server graph vs eager')
+    for a, b, c in zip(l_graph, l_eager, l_eager2):
+        assert abs(a - b) <= 4 * abs(c - b) + 1e-4 * abs(b)
+
+
+def test_lr_schedule_reaches_captured_optimizer(engine):
+    """after lr_scheduler.step() a replayed graph must use the new learning rate."""
+    batches = [_server_inputs(8, 16, 200)]
+    _, eager, _ = _run_server(engine, False, 3, batches, sched=True, dropout=0.0)
+    _, eager2, _ = _run_server(engine, False, 3, batches, sched=True, dropout=0.0)
+    _, graph, _ = _run_server(engine, True, 3, batches, sched=True, dropout=0.0)
+    _assert_within_noise(graph, eager, eager2, 'cosine schedule under graphs')
+    _, const_lr, _ = _run_server(engine, True, 3, batches, sched=False, dropout=0.0)
+    # the schedule matters: with T_max = 3 the third step runs at a quarter of the initial rate
+    assert _maxdiff(const_lr, eager)['params'] > 20 * (_maxdiff(eager2, eager)['params'] + 1e-7)
+
+
+def _client_inputs(B, L, n_pub, seed):
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randn(B, 3, 224, 224, generator=g).cuda()
+    lens = torch.sort(torch.randint(5, L + 1, (B,), generator=g), descending=True).values
+    lens[0] = L
+    caps = (torch.randint(4, 11755, (B, L), generator=g) * (torch.arange(L)[None] < lens[:, None])).cuda()
+    d_idx = torch.randperm(n_pub, generator=g)[:B].cuda()
+    return images, caps, lens, d_idx
+
+
+def _run_client(engine, graphs, banks):
+    torch.manual_seed(9)
+    cl = engine.MMClient(256, use_graphs=graphs)
+    g_img, g_txt = banks
+    losses = []
+    cl.begin_round()
+    for s in range(3):
+        images, caps, lens, d_idx = _client_inputs(16, 24, g_img.shape[0], 300 + s)
+        losses.append(cl.private_step(images, caps, lens).item())
+        losses.append(cl.contrast_step(images, caps, lens, d_idx, g_img, g_txt).item())
+    fi, ft = cl.generate(*_client_inputs(16, 24, g_img.shape[0], 400)[:3])
+    torch.cuda.synchronize()
+    out = _groups(cl)
+    out['generated'] = torch.cat([fi.flatten(), ft.flatten()]).clone()
+    return cl, out, losses
+
+
+def test_client_graph_replay_equals_eager(engine):
+    g = torch.Generator().manual_seed(1)
+    unit = lambda x: x / x.norm(dim=-1, keepdim=True)
+    banks = (unit(torch.randn(4096, 256, generator=g)).cuda(), unit(torch.randn(4096, 256, generator=g)).cuda())
+    _, eager, _ = _run_client(engine, False, banks)
+    _, eager2, _ = _run_client(engine, False, banks)
+    cl, graph, _ = _run_client(engine, True, banks)
+    _assert_within_noise(graph, eager, eager2, 'client graph vs eager')
+    # different caption-length profiles reuse ONE graph per step kind (lengths are a graph input, not a key)
+    assert len(cl._cache.graphs) == 3, list(cl._cache.graphs)
+    assert float(cl.optimizer._state[0]) == 6.0
+
+
+def test_banks_refreshed_in_place_reach_the_captured_contrast_step(engine):
+    g = torch.Generator().manual_seed(2)
+    unit = lambda x: x / x.norm(dim=-1, keepdim=True)
+    g_img, g_txt = unit(torch.randn(2048, 256, generator=g)).cuda(), unit(torch.randn(2048, 256, generator=g)).cuda()
+    torch.manual_seed(11)
+    cl = engine.MMClient(256, use_graphs=True)
+    cl.begin_round()
+    images, caps, lens, d_idx = _client_inputs(8, 16, 2048, 500)
+    l0 = cl.contrast_step(images, caps, lens, d_idx, g_img, g_txt).item()
+    torch.manual_seed(11)
+    ce = engine.MMClient(256, use_graphs=False)
+    ce.begin_round()
+    assert abs(ce.contrast_step(images, caps, lens, d_idx, g_img, g_txt).item() - l0) < 1e-3 * abs(l0)
+    # a new round's server features (new tensors): the graph must see them
+    g_img2, g_txt2 = unit(g_img + 0.5 * torch.randn_like(g_img)), unit(g_txt + 0.5 * torch.randn_like(g_txt))
+    l1 = cl.contrast_step(images, caps, lens, d_idx, g_img2, g_txt2).item()
+    l1e = ce.contrast_step(images, caps, lens, d_idx, g_img2, g_txt2).item()
+    assert abs(l1 - l1e) < 2e-3 * abs(l1e)
+    assert len(cl._cache.graphs) == 1
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def test_data_parallel_server_step_equals_single_process_mean_gradient(engine, tmp_path):
+    """2 ranks over NCCL, one batch each: the replicated server's step == one process averaging the two gradients."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
+    out = tmp_path / 'dp.pt'
+    env = dict(os.environ, PYTHONPATH=str(ROOT))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', str(_free_port()),
+                        str(ROOT / 'tests' / 'dp_worker.py'), str(out)], capture_output=True, text=True, env=env,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = torch.load(out)
+    assert res['ranks_equal'] <= 1e-7, res                      # both replicas hold the same parameters after the step
+    assert res['dp_vs_single'] <= 4 * res['single_vs_single'] + 1e-7, res
+    assert res['graph_dp_vs_single'] <= 4 * res['single_vs_single'] + 1e-7, res

@@ -177,7 +177,7 @@ def test_pcme_train_step(env, batch, seq):
     ref = RT.RefPCME('resnet18', 256)
     RT.fill_deterministic(ref, seed=5)
     ref = ref.cuda().train()
-    mine = towers.PCME(None, {'embed_dim': 256, 'cnn_type': 'resnet18'})
+    mine = towers.PCME(None, {'embed_dim': 256, 'cnn_type': 'resnet18', 'bert_dropout': 0.0})   # frozen-dropout protocol
     mine.load_state_dict(ref.state_dict(), strict=True)
     mine = mine.cuda().train()
     g = torch.Generator().manual_seed(6)
