@@ -38,13 +38,13 @@ def _mmfl():
     return MMFL
 
 
-def test_one_round_two_clients_on_cpu(monkeypatch):
+def test_one_round_two_clients_on_cpu(monkeypatch, tmp_path):
     KE.install_engine(monkeypatch)
     import random
     random.seed(0)
     torch.manual_seed(0)
     MMFL = _mmfl()
-    args = _args()
+    args = _args(name=str(tmp_path / 'plumbing'))        # MMFL.py:281,284 saves '<name>-{best,last}_model.pt' (0.6 GB)
     algo = MMFL(args, None)
     algo.create_model(args)
     algo.load_dataset(args)
@@ -72,6 +72,11 @@ def test_one_round_two_clients_on_cpu(monkeypatch):
     for d in ('i2t', 't2i'):
         assert 0.0 <= nf[d]['recall_1'] <= nf[d]['recall_5'] <= nf[d]['recall_10'] <= 100.0
     assert scores['test']['rsum'] == scores['test']['i2t']['rsum'] + scores['test']['t2i']['rsum']
+    # checkpoints in the reference's format: {'net': state_dict} with torchvision / HF key names
+    ck = torch.load(tmp_path / 'plumbing-last_model.pt', map_location='cpu')
+    assert set(ck) == {'net'} and 'img_enc.cnn.layer3.22.conv2.weight' in ck['net'] and \
+        'txt_enc.encoder.layer.11.output.dense.weight' in ck['net'] and ck['net']['linear.weight'].shape == (256, 768)
+    assert (tmp_path / 'plumbing-best_model.pt').exists()
     # clients: models trained, old-model snapshot kept by address for the next round
     for t in algo.mm_local_trainers:
         assert t._core.old_model is not None and t.local_epoch == 1

@@ -12,10 +12,10 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def test_main_runs_one_round():
+def test_main_runs_one_round(tmp_path):
     if not torch.cuda.is_available():
         pytest.skip('needs a CUDA device')
-    cmd = [sys.executable, str(ROOT / 'src' / 'main.py'), '--name', 'smoke', '--server_lr', '1e-5', '--seed', '0',
+    cmd = [sys.executable, str(ROOT / 'src' / 'main.py'), '--name', str(tmp_path / 'smoke'), '--server_lr', '1e-5', '--seed', '0',
            '--feature_dim', '256', '--pub_data_num', '256', '--agg_method', 'con_w', '--contrast_local_intra',
            '--contrast_local_inter', '--num_img_clients', '1', '--num_txt_clients', '1', '--num_mm_clients', '1',
            '--client_num_per_round', '3', '--local_epochs', '1', '--comm_rounds', '1', '--interintra_weight', '0.5',
