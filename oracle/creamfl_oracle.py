@@ -295,6 +295,31 @@ def adamp_step(params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor], ex
     return fired
 
 
+class AdamPRestated(torch.optim.Optimizer):
+    """`adamp.AdamP` as the reference constructs it (src/algorithms/optimizers.py:24-28: lr, betas (0.9, 0.999),
+    eps 1e-8, weight_decay 0, delta 0.1, wd_ratio 0.1, nesterov False) - a torch.optim.Optimizer around `adamp_step`,
+    in the parameters' own dtype and device, one tensor at a time like the package.  Used by bench.py's baseline legs
+    (host CPU and eager-torch-on-GPU) so that they pay the reference optimizer's cost; PARITY UNPINNED like
+    `adamp_step` itself."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, delta=0.1, wd_ratio=0.1):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, delta=delta,
+                                      wd_ratio=wd_ratio))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        for group in self.param_groups:
+            for p in group['params']:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st['step'], st['exp_avg'], st['exp_avg_sq'] = 0, torch.zeros_like(p), torch.zeros_like(p)
+                st['step'] += 1
+                adamp_step([p], [p.grad], [st['exp_avg']], [st['exp_avg_sq']], st['step'], group['lr'], group['betas'],
+                           group['eps'], group['weight_decay'], group['delta'], group['wd_ratio'])
+
+
 def sgd_momentum_step(params, grads, bufs, step: int, lr: float, momentum: float = 0.9, weight_decay: float = 0.0):
     """torch.optim.SGD semantics (ClientTrainer.py:287-288): g += wd*p; buf = g (first step) or mom*buf + g; p -= lr*buf."""
     for p, g, buf in zip(params, grads, bufs):

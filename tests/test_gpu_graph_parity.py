@@ -3,7 +3,8 @@ schedule reaching captured kernels, and the NCCL data-parallel server.
 
 The kernels accumulate weight gradients with fp32 atomics (split-K `red.global.add`), so two EAGER runs of the same
 step from the same state already differ in the last bits.  "Graph replay == eager" is therefore asserted against
-that measured run-to-run noise: max|graph - eager| <= 4 * max|eager' - eager| + one fp32 ulp of the group's largest value, per tensor group, on the flat parameter buffer, BatchNorm running statistics / counters, criterion
+that measured run-to-run noise (||graph - eager||_2 <= 3 * max ||eager' - eager||_2 over further eager runs, per
+tensor group), on the flat parameter buffer, BatchNorm running statistics / counters, criterion
 parameters, AdamP moments and the step's losses."""
 import os
 import socket
@@ -47,14 +48,19 @@ def _groups(eng):
     return out
 
 
-def _maxdiff(a, b):
-    return {k: float((a[k].double() - b[k].double()).abs().max()) for k in a}
+def _l2diff(a, b):
+    return {k: float((a[k].double() - b[k].double()).norm()) for k in a}
 
 
-def _assert_within_noise(test, base, noise_run, what):
-    d, noise = _maxdiff(test, base), _maxdiff(noise_run, base)
-    floor = {k: 1e-6 * max(1.0, float(base[k].abs().max())) for k in d}       # one fp32 ulp of the group's largest value
-    bad = {k: (d[k], noise[k]) for k in d if d[k] > 4 * noise[k] + floor[k]}
+def _assert_within_noise(test, base, noise_runs, what):
+    """||test - base||_2 <= 3 * max_i ||noise_i - base||_2 + floor, per tensor group.  L2 norms over 10^5..10^8
+    elements concentrate, so a semantically identical run sits at ratio ~1; AdamP's first steps move every element by
+    ~lr whatever the gradient magnitude, so the MAX difference is dominated by a few sign flips of near-zero gradients
+    and is not a usable statistic."""
+    d = _l2diff(test, base)
+    noise = {k: max(_l2diff(n, base)[k] for n in noise_runs) for k in d}
+    floor = {k: 1e-6 * float(base[k].double().norm()) for k in d}             # fp32 rounding of the group itself
+    bad = {k: (d[k], noise[k]) for k in d if d[k] > 3 * noise[k] + floor[k]}
     assert not bad, (what, bad)
 
 
@@ -62,10 +68,12 @@ def _run_server(engine, graphs, steps, batches, sched=False, dropout=0.1):
     torch.manual_seed(7)                      # identical random init and dropout seed for every run
     srv = engine.ServerEngine(256, 'resnet101', lr=2e-4, use_graphs=graphs, bert_dropout=dropout)
     scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(srv.optimizer, T_max=3) if sched else None
-    losses = []
+    losses, srv.moved = [], []
     for s in range(steps):
         images, tok = batches[s % len(batches)]
+        before = srv.model.store().flat.clone()
         losses.append(srv.train_step(images, tok).item())
+        srv.moved.append(float((srv.model.store().flat - before).abs().mean()))     # mean |update| of this step
         if scheduler is not None:
             scheduler.step()
     torch.cuda.synchronize()
@@ -75,25 +83,34 @@ def _run_server(engine, graphs, steps, batches, sched=False, dropout=0.1):
 def test_server_graph_replay_equals_eager_over_three_steps(engine):
     batches = [_server_inputs(16, 32, 100 + s) for s in range(2)]
     _, eager, l_eager = _run_server(engine, False, 3, batches)
-    _, eager2, l_eager2 = _run_server(engine, False, 3, batches)
+    noise = [_run_server(engine, False, 3, batches) for _ in range(3)]
     srv, graph, l_graph = _run_server(engine, True, 3, batches)
     assert int(srv.model.img_enc.cnn.bn1.num_batches_tracked) == 3          # the capture's warm-up was rolled back
     assert float(srv.optimizer._state[0]) == 3.0                            # AdamP step counter
-    _assert_within_noise(graph, eager, eager2, 'server graph vs eager')
-    for a, b, c in zip(l_graph, l_eager, l_eager2):
-        assert abs(a - b) <= 4 * abs(c - b) + 1e-4 * abs(b)
+    assert int(srv.model.txt_enc.dropout_state(srv.device).rng[1]) == 3     # dropout RNG step: one tick per step
+    _assert_within_noise(graph, eager, [n[1] for n in noise], 'server graph vs eager')
+    # step 1 runs on identical parameters: its loss (forward only, fp64 BatchNorm statistics) agrees to fp32 rounding
+    assert abs(l_graph[0] - l_eager[0]) <= 1e-5 * abs(l_eager[0])
+    # later losses sit on parameters that already carry the atomics noise of the earlier updates
+    for a, b, *cs in zip(l_graph[1:], l_eager[1:], *[n[2][1:] for n in noise]):
+        assert abs(a - b) <= 4 * max(abs(c - b) for c in cs) + 1e-2 * abs(b)
 
 
 def test_lr_schedule_reaches_captured_optimizer(engine):
-    """after lr_scheduler.step() a replayed graph must use the new learning rate."""
+    """after lr_scheduler.step() a replayed graph must use the new learning rate.  AdamP's first updates
+    have |update| ~ lr per element whatever the gradient, so the mean |update| of a step is a sharp read-out of the
+    learning rate the kernels used: CosineAnnealingLR(T_max=3) runs the steps at 1, 0.75 and 0.25 of the base rate."""
     batches = [_server_inputs(8, 16, 200)]
-    _, eager, _ = _run_server(engine, False, 3, batches, sched=True, dropout=0.0)
-    _, eager2, _ = _run_server(engine, False, 3, batches, sched=True, dropout=0.0)
-    _, graph, _ = _run_server(engine, True, 3, batches, sched=True, dropout=0.0)
-    _assert_within_noise(graph, eager, eager2, 'cosine schedule under graphs')
-    _, const_lr, _ = _run_server(engine, True, 3, batches, sched=False, dropout=0.0)
-    # the schedule matters: with T_max = 3 the third step runs at a quarter of the initial rate
-    assert _maxdiff(const_lr, eager)['params'] > 20 * (_maxdiff(eager2, eager)['params'] + 1e-7)
+    s_eager, eager, _ = _run_server(engine, False, 3, batches, sched=True, dropout=0.0)
+    noise = [_run_server(engine, False, 3, batches, sched=True, dropout=0.0)[1] for _ in range(2)]
+    s_graph, graph, _ = _run_server(engine, True, 3, batches, sched=True, dropout=0.0)
+    _assert_within_noise(graph, eager, noise, 'cosine schedule under graphs')
+    s_const, _, _ = _run_server(engine, True, 3, batches, sched=False, dropout=0.0)
+    for k in range(3):
+        assert abs(s_graph.moved[k] - s_eager.moved[k]) <= 0.03 * s_eager.moved[k], (k, s_graph.moved, s_eager.moved)
+    assert s_graph.moved[0] == pytest.approx(2e-4, rel=0.15)                # first Adam step: |update| = lr
+    assert s_graph.moved[2] / s_graph.moved[0] < 0.30                       # 0.25 x (|m/sqrt(v)| <= 1)
+    assert s_const.moved[2] / s_const.moved[0] > 0.45                       # a graph stuck at the base rate would sit here
 
 
 def _client_inputs(B, L, n_pub, seed):
@@ -106,13 +123,13 @@ def _client_inputs(B, L, n_pub, seed):
     return images, caps, lens, d_idx
 
 
-def _run_client(engine, graphs, banks):
+def _run_client(engine, graphs, banks, steps=3):
     torch.manual_seed(9)
     cl = engine.MMClient(256, use_graphs=graphs)
     g_img, g_txt = banks
     losses = []
     cl.begin_round()
-    for s in range(3):
+    for s in range(steps):
         images, caps, lens, d_idx = _client_inputs(16, 24, g_img.shape[0], 300 + s)
         losses.append(cl.private_step(images, caps, lens).item())
         losses.append(cl.contrast_step(images, caps, lens, d_idx, g_img, g_txt).item())
@@ -127,10 +144,17 @@ def test_client_graph_replay_equals_eager(engine):
     g = torch.Generator().manual_seed(1)
     unit = lambda x: x / x.norm(dim=-1, keepdim=True)
     banks = (unit(torch.randn(4096, 256, generator=g)).cuda(), unit(torch.randn(4096, 256, generator=g)).cuda())
+    # one step pair from identical state: only one update's worth of atomics noise separates two runs
+    _, eager1, l_eager1 = _run_client(engine, False, banks, steps=1)
+    noise1 = [_run_client(engine, False, banks, steps=1)[1] for _ in range(3)]
+    _, graph1, l_graph1 = _run_client(engine, True, banks, steps=1)
+    _assert_within_noise(graph1, eager1, noise1, 'client graph vs eager, 1 step')
+    assert abs(l_graph1[0] - l_eager1[0]) <= 1e-5 * abs(l_eager1[0])        # private-step loss: identical parameters
+    # three step pairs: the noise has been amplified by the earlier updates on both sides
     _, eager, _ = _run_client(engine, False, banks)
-    _, eager2, _ = _run_client(engine, False, banks)
+    noise = [_run_client(engine, False, banks)[1] for _ in range(4)]
     cl, graph, _ = _run_client(engine, True, banks)
-    _assert_within_noise(graph, eager, eager2, 'client graph vs eager')
+    _assert_within_noise(graph, eager, noise, 'client graph vs eager')
     # different caption-length profiles reuse ONE graph per step kind (lengths are a graph input, not a key)
     assert len(cl._cache.graphs) == 3, list(cl._cache.graphs)
     assert float(cl.optimizer._state[0]) == 6.0
