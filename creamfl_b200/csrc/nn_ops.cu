@@ -96,88 +96,68 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, double*
   }
 }
 
+// Per-channel affine of the normalisation and running-statistics update (torch semantics: biased variance for the
+// normalisation, unbiased for running_var, momentum 0.1).  Zeroes `sums` for the next use.
+__global__ void bn_finalize_kernel(double* __restrict__ sums, long long P, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   long long* __restrict__ num_batches_tracked) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;   // nn.BatchNorm2d's counter, no extra launch
+  const double m = sums[c] / (double)P;
+  double var = sums[C + c] / (double)P - m * m;
+  if (var < 0.0) var = 0.0;
+  sums[c] = 0.0;
+  sums[C + c] = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  mean_out[c] = (float)m;
+  rstd_out[c] = rstd;
+  const float sc = gamma[c] * rstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)m * sc;
+  if (running_mean) {
+    const double unbiased = P > 1 ? var * (double)P / (double)(P - 1) : var;
+    running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// eval mode: scale/shift from the running statistics
+__global__ void bn_eval_affine_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      float eps, const float* __restrict__ running_mean,
+                                      const float* __restrict__ running_var, float* __restrict__ scale,
+                                      float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] * rsqrtf(running_var[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] - running_mean[c] * sc;
+}
+
 // y = [relu]( x * scale[c] + shift[c] [+ res] ).
 // Elementwise BatchNorm kernels: C/8 divides the block size, so with a grid stride that is a multiple of the block
 // size every 16-byte vector a thread touches belongs to the same 8 channels - the per-channel coefficients are
 // loaded once into registers and kEwVec vectors are in flight per thread per tensor.
 constexpr int kEwVec = 4;
 constexpr int kEwThreads = 256;
-
-// Where the per-channel affine of bn_apply_kernel comes from.  The finalisation of the batch statistics is folded
-// into the apply kernel (it used to be a one-block launch between two dependent launches, 208 of them per ResNet101
-// training step): every thread derives the coefficients of ITS 8 channels from the fp64 sums, block 0 additionally
-// publishes mean / rstd (the backward needs them) and updates the running statistics, and the last block to finish
-// re-zeroes the sums for the next accumulation (launch counter in sums[2C], the "last block done" pattern).
-struct BnSource {
-  int mode;                     // 1: train (from sums), 2: eval (from running statistics)
-  double* sums;                 // [2C] sum, sum of squares; [2C] (as uint32) launch counter
-  long long P;
-  const float* gamma;
-  const float* beta;
-  float eps, momentum;
-  float* running_mean;          // train: updated; eval: read
-  float* running_var;
-  float* mean_out;              // train: [C] batch mean / rstd for the backward
-  float* rstd_out;
-  long long* num_batches_tracked;
-};
-
-__device__ __forceinline__ void bn_last_block_rezero(double* sums, int C) {
-  __shared__ int s_last;
-  __syncthreads();                                   // every thread of this block has consumed the sums
-  if (threadIdx.x == 0) {
-    __threadfence();
-    unsigned* counter = reinterpret_cast<unsigned*>(sums + 2 * C);
-    s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  if (s_last) {
-    for (int e = threadIdx.x; e < 2 * C; e += blockDim.x) sums[e] = 0.0;
-    if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(sums + 2 * C) = 0u;
-  }
+__device__ __forceinline__ void load_coef8(const float* __restrict__ a, int c0, float (&o)[8]) {
+  const float4 lo = *reinterpret_cast<const float4*>(a + c0), hi = *reinterpret_cast<const float4*>(a + c0 + 4);
+  o[0] = lo.x; o[1] = lo.y; o[2] = lo.z; o[3] = lo.w; o[4] = hi.x; o[5] = hi.y; o[6] = hi.z; o[7] = hi.w;
 }
 
 __global__ void __launch_bounds__(kEwThreads)
-bn_apply_kernel(const __nv_bfloat16* __restrict__ x, BnSource src, const __nv_bfloat16* __restrict__ res, int relu,
-                long long total8, int C, __nv_bfloat16* __restrict__ y) {
+bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                const __nv_bfloat16* __restrict__ res, int relu, long long total8, int C,
+                __nv_bfloat16* __restrict__ y) {
   const long long stride = (long long)gridDim.x * kEwThreads;
   const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
   float sc[8], sf[8];
   const int c0 = (int)((first * 8) % C);
-  if (src.mode == 1) {
-    // block 0, threads [0, C/8): c0 = 8 * threadIdx.x covers every channel exactly once (C <= 2048)
-    const bool publish = blockIdx.x == 0 && threadIdx.x < (C >> 3);
-    const double invP = 1.0 / (double)src.P;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 + i;
-      const double m = src.sums[c] * invP;
-      double var = src.sums[C + c] * invP - m * m;
-      if (var < 0.0) var = 0.0;
-      const float rstd = 1.0f / sqrtf((float)var + src.eps);
-      const float g = src.gamma[c] * rstd;
-      sc[i] = g;
-      sf[i] = src.beta[c] - (float)m * g;
-      if (publish) {
-        src.mean_out[c] = (float)m;
-        src.rstd_out[c] = rstd;
-        if (src.running_mean) {   // torch: biased variance normalises, the unbiased one feeds running_var
-          const double unbiased = src.P > 1 ? var * (double)src.P / (double)(src.P - 1) : var;
-          src.running_mean[c] = (1.0f - src.momentum) * src.running_mean[c] + src.momentum * (float)m;
-          src.running_var[c] = (1.0f - src.momentum) * src.running_var[c] + src.momentum * (float)unbiased;
-        }
-      }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && src.num_batches_tracked) *src.num_batches_tracked += 1;
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 + i;
-      const float g = src.gamma[c] * rsqrtf(src.running_var[c] + src.eps);
-      sc[i] = g;
-      sf[i] = src.beta[c] - src.running_mean[c] * g;
-    }
-  }
+  load_coef8(scale, c0, sc);
+  load_coef8(shift, c0, sf);
   for (long long t0 = first; t0 < total8; t0 += kEwVec * stride) {
     bf16x8 xv[kEwVec], rv[kEwVec];
 #pragma unroll
@@ -208,7 +188,6 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, BnSource src, const __nv_bf
       reinterpret_cast<bf16x8*>(y)[t] = pack8(f);
     }
   }
-  if (src.mode == 1) bn_last_block_rezero(src.sums, C);
 }
 
 // sums[0..C) += sum_p g ; sums[C..2C) += sum_p g * xhat    with g = dy * (y > 0 if relu)
@@ -284,45 +263,48 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   }
 }
 
-// dx = a*g + b*x + c0 with a = gamma*rstd, b = -gamma*rstd^2*S2/P, c0 = -a*S1/P - b*mean (train mode), S1 = sum g,
-// S2 = sum g*xhat accumulated by bn_bwd_reduce_kernel; optionally g itself is written out (gradient of the residual
-// branch).  The coefficient finalisation is folded in like in bn_apply_kernel: every thread derives the coefficients
-// of its 8 channels, block 0 adds dbeta += S1, dgamma += S2, the last block re-zeroes the sums.
+// dbeta += S1, dgamma += S2;  coefficients of dx = a*g + b*x + c0 with
+//   a = gamma*rstd, b = -gamma*rstd^2*S2/P, c0 = -a*S1/P - b*mean     (train mode)
+__global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, long long P, int C, const float* __restrict__ gamma,
+                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                       const float* __restrict__ beta /* non-null: also emit the gate affine */,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ coef /* [5, C] */) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s1 = sums[c], s2 = sums[C + c];
+  sums[c] = 0.0;
+  sums[C + c] = 0.0;
+  if (dbeta) dbeta[c] += (float)s1;
+  if (dgamma) dgamma[c] += (float)s2;
+  const double a = (double)gamma[c] * rstd[c];
+  const double b = -a * rstd[c] * s2 / (double)P;
+  coef[c] = (float)a;
+  coef[C + c] = (float)b;
+  coef[2 * C + c] = (float)(-a * s1 / (double)P - b * mean[c]);
+  if (beta) {   // affine of the forward output as a function of x: y_pre = gs*x + gb (the ReLU gate of bn_bwd_apply)
+    coef[3 * C + c] = gamma[c] * rstd[c];
+    coef[4 * C + c] = beta[c] - mean[c] * gamma[c] * rstd[c];
+  }
+}
+
+// dx = a*g + b*x + c0 ; optionally g itself is written out (gradient of the residual branch)
 constexpr int kBwdVec = 4;
 __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
-                    const __nv_bfloat16* __restrict__ x, double* __restrict__ sums, long long P,
-                    const float* __restrict__ gamma, const float* __restrict__ beta /* non-null: ReLU gate from x */,
-                    const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta, long long total8, int C, __nv_bfloat16* __restrict__ dx,
-                    __nv_bfloat16* __restrict__ g_out) {
+                    const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef,
+                    const float* __restrict__ gate /* [2, C] affine of the ReLU gate, or null */, long long total8, int C,
+                    __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ g_out) {
   const long long stride = (long long)gridDim.x * kEwThreads;
   const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
   float ca[8], cb[8], cc[8], gs[8], gb[8];
   const int c0 = (int)((first * 8) % C);
-  const bool gate = beta != nullptr;
-  {
-    const bool publish = blockIdx.x == 0 && threadIdx.x < (C >> 3);
-    const double invP = 1.0 / (double)P;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 + i;
-      const double s1 = sums[c], s2 = sums[C + c];
-      const float rs = rstd[c], mu = mean[c], ga = gamma[c];
-      const double a = (double)ga * rs;
-      const double b = -a * rs * s2 * invP;
-      ca[i] = (float)a;
-      cb[i] = (float)b;
-      cc[i] = (float)(-a * s1 * invP - b * mu);
-      if (gate) {   // affine of the forward output as a function of x: y_pre = gs*x + gb
-        gs[i] = ga * rs;
-        gb[i] = beta[c] - mu * ga * rs;
-      }
-      if (publish) {
-        if (dbeta) dbeta[c] += (float)s1;
-        if (dgamma) dgamma[c] += (float)s2;
-      }
-    }
+  load_coef8(coef, c0, ca);
+  load_coef8(coef + C, c0, cb);
+  load_coef8(coef + 2 * C, c0, cc);
+  if (gate) {
+    load_coef8(gate, c0, gs);
+    load_coef8(gate + C, c0, gb);
   }
   for (long long t0 = first; t0 < total8; t0 += kBwdVec * stride) {
     bf16x8 rd[kBwdVec], rx[kBwdVec], ry[kBwdVec];
@@ -358,7 +340,6 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
       reinterpret_cast<bf16x8*>(dx)[t] = pack8(o);
     }
   }
-  bn_last_block_rezero(sums, C);
 }
 
 // grid for the elementwise BatchNorm kernels: enough blocks to fill the machine, every thread loops
@@ -406,37 +387,34 @@ int bn_train_fwd(const void* x, long long P, int C, const float* gamma, const fl
                  float* running_mean, float* running_var, double* sums, float* mean, float* rstd, float* scale,
                  float* shift, const void* res, int relu, int stats_ready, long long* num_batches_tracked, void* y,
                  cudaStream_t st) {
-  (void)scale; (void)shift;    // per-channel affine now lives in registers of the apply kernel
   int rc = bn_check("bn_train_fwd", P, C);
   if (rc) return rc;
   if (!stats_ready && (rc = bn_stats_only(x, P, C, sums, st))) return rc;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, beta, eps, momentum, running_mean,
+                                                       running_var, mean, rstd, scale, shift, num_batches_tracked);
   const long long total8 = P * C / 8;
-  BnSource src{1, sums, P, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, num_batches_tracked};
   bn_apply_kernel<<<ew_grid(total8, kEwVec), kEwThreads, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), src, reinterpret_cast<const __nv_bfloat16*>(res), relu, total8, C,
-      reinterpret_cast<__nv_bfloat16*>(y));
+      reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(res), relu,
+      total8, C, reinterpret_cast<__nv_bfloat16*>(y));
   return check_launch("bn_train_fwd");
 }
 
 int bn_eval_fwd(const void* x, long long P, int C, const float* gamma, const float* beta, float eps,
                 const float* running_mean, const float* running_var, float* scale, float* shift, const void* res,
                 int relu, void* y, cudaStream_t st) {
-  (void)scale; (void)shift;
   int rc = bn_check("bn_eval_fwd", P, C);
   if (rc) return rc;
+  bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, eps, running_mean, running_var, scale, shift);
   const long long total8 = P * C / 8;
-  BnSource src{2, nullptr, P, gamma, beta, eps, 0.0f, const_cast<float*>(running_mean),
-               const_cast<float*>(running_var), nullptr, nullptr, nullptr};
   bn_apply_kernel<<<ew_grid(total8, kEwVec), kEwThreads, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), src, reinterpret_cast<const __nv_bfloat16*>(res), relu, total8, C,
-      reinterpret_cast<__nv_bfloat16*>(y));
+      reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(res), relu,
+      total8, C, reinterpret_cast<__nv_bfloat16*>(y));
   return check_launch("bn_eval_fwd");
 }
 
 int bn_train_bwd(const void* dy, const void* y_or_null, const void* x, long long P, int C, const float* gamma,
                  const float* beta, int relu_from_x, const float* mean, const float* rstd, double* sums, float* coef,
                  float* dgamma, float* dbeta, void* dx, void* g_out, cudaStream_t st) {
-  (void)coef;
   int rc = bn_check("bn_train_bwd", P, C);
   if (rc) return rc;
   const int gate_from_x = (relu_from_x && y_or_null == nullptr && beta != nullptr) ? 1 : 0;
@@ -445,11 +423,13 @@ int bn_train_bwd(const void* dy, const void* y_or_null, const void* x, long long
   bn_bwd_reduce_kernel<<<bn_reduce_grid(P, C), kBnThreads, smem, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_or_null),
       reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, gamma, beta, gate_from_x, P, C, sums);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, mean, rstd, gate_from_x ? beta : nullptr,
+                                                          dgamma, dbeta, coef);
   const long long total8 = P * C / 8;
   bn_bwd_apply_kernel<<<ew_grid(total8, kBwdVec), kEwThreads, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_or_null),
-      reinterpret_cast<const __nv_bfloat16*>(x), sums, P, gamma, gate_from_x ? beta : nullptr, mean, rstd, dgamma, dbeta,
-      total8, C, reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(g_out));
+      reinterpret_cast<const __nv_bfloat16*>(x), coef, gate_from_x ? coef + 3 * C : nullptr, total8, C,
+      reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(g_out));
   return check_launch("bn_train_bwd");
 }
 

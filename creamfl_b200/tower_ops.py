@@ -148,11 +148,10 @@ def im2col_images(images: torch.Tensor, r: int, s: int, stride: int, pad: int, p
 
 # --------------------------------------------------------------------------------------------------- BatchNorm
 class BNScratch:
-    """Per-layer scratch of the BatchNorm kernels: fp64 sums [2C] + one launch-counter slot (the kernels leave all
-    of it zero again), and the legacy per-channel scratch arrays of the ABI."""
+    """Per-layer scratch of the BatchNorm kernels (fp64 sums, per-channel affine / backward coefficients)."""
 
     def __init__(self, c: int, device):
-        self.sums = torch.zeros(2 * c + 1, dtype=torch.float64, device=device)
+        self.sums = torch.zeros(2 * c, dtype=torch.float64, device=device)
         self.scale = torch.empty(c, dtype=torch.float32, device=device)
         self.shift = torch.empty(c, dtype=torch.float32, device=device)
         self.coef = torch.empty(5 * c, dtype=torch.float32, device=device)
@@ -169,7 +168,7 @@ def bn_train_fwd(x, gamma, beta, running_mean, running_var, sc: BNScratch, eps, 
                                           _p(running_var), _p(sc.sums), _p(mean), _p(rstd), _p(sc.scale), _p(sc.shift),
                                           _p(res), int(relu), int(stats_ready), _p(num_batches_tracked), _p(y),
                                           _stream()), "bn_train_fwd",
-         1 if stats_ready else 2)
+         2 if stats_ready else 3)
     return y, mean, rstd
 
 
@@ -179,7 +178,7 @@ def bn_eval_fwd(x, gamma, beta, running_mean, running_var, sc: BNScratch, eps, r
     y = torch.empty_like(x)
     _chk(_lib.load().creamfl_bn_eval_fwd(_p(x), p, c, _p(gamma), _p(beta), eps, _p(running_mean), _p(running_var),
                                          _p(sc.scale), _p(sc.shift), _p(res), int(relu), _p(y), _stream()),
-         "bn_eval_fwd", 1)
+         "bn_eval_fwd", 2)
     return y
 
 
@@ -194,7 +193,7 @@ def bn_train_bwd(dy, y_mask, x, gamma, mean, rstd, sc: BNScratch, dgamma, dbeta,
     _chk(_lib.load().creamfl_bn_train_bwd(_p(dy), _p(y_mask), _p(x), p, c, _p(gamma), _p(beta), int(relu_from_x),
                                           _p(mean), _p(rstd), _p(sc.sums), _p(sc.coef), _p(dgamma), _p(dbeta), _p(dx),
                                           _p(g), _stream()),
-         "bn_train_bwd", 2)
+         "bn_train_bwd", 3)
     return dx, g
 
 

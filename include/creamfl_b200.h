@@ -149,10 +149,8 @@ int creamfl_im2col_nchw_f32(const float* images, int N, int C, int H, int W, int
                             int col_pitch, void* col_bf16, void* stream);
 
 /* ---- BatchNorm2d over NHWC bf16 (P = N*H*W pixels), fused with the residual add and ReLU of the ResNet blocks.
- * train: batch statistics (fp64 accumulation in `sums`: 2*C + 1 doubles, all zero on entry and on exit - [0, 2C)
- * hold sum and sum of squares, the last element is the launch counter of the "last block re-zeroes" protocol: the
- * finalisation of the statistics is folded into the apply kernel, there is no separate finalize launch), running
- * stats updated with `momentum`; keeps mean/rstd for the backward.  scale/shift: unused (kept for ABI stability).
+ * train: batch statistics (fp64 accumulation in `sums`, 2*C doubles, zero on entry and on exit), running stats
+ * updated with `momentum`; keeps mean/rstd for the backward.  scale/shift: C-float scratch each.
  * num_batches_tracked (optional, device int64 scalar) is incremented (nn.BatchNorm2d's buffer). */
 int creamfl_bn_train_fwd(const void* x_bf16, int64_t P, int C, const float* gamma, const float* beta, float eps,
                          float momentum, float* running_mean, float* running_var, double* sums, float* mean,
@@ -166,7 +164,7 @@ int creamfl_bn_eval_fwd(const void* x_bf16, int64_t P, int C, const float* gamma
 /* g = dy * gate;  dgamma += sum g*xhat, dbeta += sum g;  dx = BN'(g).  The ReLU gate is (y > 0) when y_bf16 is
  * given (needed when a residual was added before the ReLU), (gamma*xhat + beta > 0) recomputed from x when y_bf16 is
  * null and relu_from_x != 0 (saves reading y), and 1 otherwise.  g_out (optional) receives g (gradient of the
- * residual branch).  sums: the same 2*C + 1 doubles as the forward (zero on entry and on exit); coef: unused. */
+ * residual branch).  coef: 5*C floats scratch. */
 int creamfl_bn_train_bwd(const void* dy_bf16, const void* y_bf16, const void* x_bf16, int64_t P, int C,
                          const float* gamma, const float* beta, int relu_from_x, const float* mean, const float* rstd,
                          double* sums, float* coef, float* dgamma, float* dbeta, void* dx_bf16, void* g_out_bf16,

@@ -326,7 +326,7 @@ def conv_fprop(x, w2d, r, s_, stride, pad, bn_sums=None):
     if bn_sums is not None:                     # statistics of the bf16 output, accumulated
         y2 = y.double().reshape(-1, cout)
         bn_sums[:cout] += y2.sum(0)
-        bn_sums[cout:2 * cout] += (y2 * y2).sum(0)
+        bn_sums[cout:] += (y2 * y2).sum(0)
     return y
 
 
@@ -364,9 +364,9 @@ def bn_train_fwd(x, gamma, beta, running_mean, running_var, sc, eps, momentum, r
     p = x2.shape[0]
     if not stats_ready:
         sc.sums[:c] += x2.sum(0)
-        sc.sums[c:2 * c] += (x2 * x2).sum(0)
+        sc.sums[c:] += (x2 * x2).sum(0)
     m = sc.sums[:c] / p
-    var = (sc.sums[c:2 * c] / p - m * m).clamp_min(0)
+    var = (sc.sums[c:] / p - m * m).clamp_min(0)
     sc.sums.zero_()
     rstd = (1.0 / torch.sqrt(var + eps)).float()
     mean = m.float()
