@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import ops, tower_ops as T
 from .text_towers import GRUEncoderText, TextClient  # noqa: F401  (re-exported: src/networks/language_model.py)
-from .towers import EncoderImage, ResNet, StoreMixin, _Linear, grad_target
+from .towers import EncoderImage, ResNet, StoreMixin, _Linear, fork_stream, grad_target
 
 
 class ClientPCME(StoreMixin, nn.Module):
@@ -50,8 +50,11 @@ class ClientPCME(StoreMixin, nn.Module):
 
     def forward(self, images, sentences, captions_word, lengths):
         self.store()
-        image_output = self.img_enc(images)
-        caption_output = self.txt_enc(sentences, lengths)
+        # GRU text tower (a latency-bound recurrence) on a forked stream next to the image tower (towers.fork_stream)
+        with fork_stream(images.device, getattr(self, 'overlap_towers', True)) as side:
+            with side:
+                caption_output = self.txt_enc(sentences, lengths)
+            image_output = self.img_enc(images)
         return {
             'image_features': image_output['embedding'], 'image_attentions': None, 'image_residuals': None,
             'image_logsigma': None, 'image_logsigma_att': None,

@@ -511,7 +511,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         atomicAdd(p.stats + p.N + acc_n_blk * BN + etid, s_csq[etid]);
       }
     }
-    if (p.tma_out && issuer) tma_store_wait<0>();
+    // the staging buffers must have been READ before the CTA (and its shared memory) goes away; the global writes of
+    // the bulk stores complete with the grid (kernel-boundary semantics), no need to sit on them here
+    if (p.tma_out && issuer) tma_store_wait_read<0>();
   }
 
   tc_fence_before();

@@ -27,6 +27,7 @@ CUDA graphs.  A step function (`use_graphs=True`) is captured once per input sha
 from __future__ import annotations
 
 import copy
+import weakref
 from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -38,7 +39,7 @@ from .clients import ClientPCME, ImageClient, text_supervised_loss, unimodal_sup
 from .criterions import get_criterion
 from .optim import FusedOptimizer
 from .text_towers import TextClient
-from .towers import PCME
+from .towers import PCME, fork_stream
 
 PCME_CRITERION_CFG = {'init_shift': 15, 'init_negative_scale': 15, 'num_samples': 7}    # coco.yaml:41-47
 MAX_GRAPHS = 12           # cached graphs per engine before the least recently used one is dropped
@@ -56,14 +57,21 @@ def _features(output: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, torch.Tens
     return output['image_features'], output['caption_features']
 
 
-_POOLS: Dict[int, object] = {}
+_POOLS: Dict[int, list] = {}          # device index -> [pool handle, number of live graphs in the pool]
 
 
-def _graph_pool(device: torch.device):
+def _graph_pool(device: torch.device) -> list:
+    """The memory pool shared by every captured step of a device.  A pool dies with its last graph, so the handle is
+    renewed once no graph of the previous pool is alive (engines come and go in tests)."""
     key = device.index if device.index is not None else torch.cuda.current_device()
-    if key not in _POOLS:
-        _POOLS[key] = torch.cuda.graph_pool_handle()
-    return _POOLS[key]
+    entry = _POOLS.get(key)
+    if entry is None or entry[1] == 0:
+        entry = _POOLS[key] = [torch.cuda.graph_pool_handle(), 0]
+    return entry
+
+
+def _release_pool(entry: list) -> None:
+    entry[1] -= 1
 
 
 class GraphedStep:
@@ -93,8 +101,11 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         l0 = ops.launches()
         dev = next(iter(self.static.values())).device
-        with torch.cuda.graph(self.graph, pool=_graph_pool(dev), capture_error_mode='thread_local'):
+        pool = _graph_pool(dev)
+        with torch.cuda.graph(self.graph, pool=pool[0], capture_error_mode='thread_local'):
             self.out = fn(**self.static)
+        pool[1] += 1
+        weakref.finalize(self, _release_pool, pool)
         self.launches = ops.launches() - l0          # kernels of ours inside one replay
 
     def __call__(self, **inputs):
@@ -401,12 +412,17 @@ class MMClient(_Banked):
                        inter: bool = True, loss_scale: bool = False) -> torch.Tensor:
         self.model.train()
         self.optimizer.zero_grad()
-        out_img, out_txt = _features(self.model(images, captions, None, lengths))
         b = images.shape[0]
         loss_intra = loss_inter = None
+        # the old model's forward (no grad) is a third independent branch next to the two towers of the model: it runs
+        # on its own forked stream (inside a captured graph: a parallel branch of the graph)
+        with fork_stream(images.device, intra and getattr(self, 'overlap_old_model', True), slot=1) as side:
+            if intra:
+                with side, torch.no_grad():
+                    self.old_model.overlap_towers = False
+                    old_img, old_txt = _features(self.old_model(images, captions, None, lengths))
+            out_img, out_txt = _features(self.model(images, captions, None, lengths))
         if intra:
-            with torch.no_grad():
-                old_img, old_txt = _features(self.old_model(images, captions, None, lengths))
             loss_intra = ops.moon_intra_loss(out_img, old_img, g_img, d_idx, 2.0, 2 * b) + \
                 ops.moon_intra_loss(out_txt, old_txt, g_txt, d_idx, 2.0, 2 * b)
         if inter:
@@ -534,13 +550,15 @@ class UnimodalClient(_Banked):
         for m in (self.model, self.old_model):
             self._mode(m, True)                                                          # :372-375
         self.optimizer.zero_grad()
-        feat = self._embed(self.model, x, lengths)
+        with fork_stream(x.device, intra and getattr(self, 'overlap_old_model', True), slot=1) as side:
+            if intra:
+                with side, torch.no_grad():
+                    old = self._embed(self.old_model, x, lengths)
+            feat = self._embed(self.model, x, lengths)
         loss_inter = loss_moon = None
         if inter:
             loss_inter = ops.infonce_loss(feat, g_other16, d_idx, 2.0)                    # :388,398-401
         if intra:
-            with torch.no_grad():
-                old = self._embed(self.old_model, x, lengths)
             loss_moon = ops.moon_intra_loss(feat, old, g_same, d_idx, 2.0, feat.shape[0])  # :404-414
         loss = combine_contrast(loss_moon, loss_inter, self.w, loss_scale)
         loss.backward()

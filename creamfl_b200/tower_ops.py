@@ -21,9 +21,9 @@ _ws_cache: dict = {}
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:
-    """Grow-only scratch buffer per device (stream-ordered reuse; contents are dead once the consuming kernel has
-    been enqueued)."""
-    key = (device.type, device.index)
+    """Grow-only scratch buffer per (device, stream): reuse is stream-ordered (contents are dead once the consuming
+    kernel has been enqueued), and towers running concurrently on forked streams never share one."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream if device.type == 'cuda' else 0)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)

@@ -142,6 +142,49 @@ class ParamStore:
         return self.params[0].data_ptr() == self.first_ptr
 
 
+class fork_stream:
+    """`with fork_stream(device) as side: with side: <branch>; <main work>` - runs <branch> on a side stream forked
+    from the current stream and joins it on exit (capturable: inside a CUDA-graph capture the fork / join become
+    graph edges and the two branches replay concurrently).  `enabled=False` (or a CPU device) runs everything inline."""
+    _streams = {}
+
+    def __init__(self, device, enabled: bool = True, slot: int = 0):
+        import os
+        self.enabled = bool(enabled) and device.type == 'cuda' and os.environ.get('CREAMFL_NO_OVERLAP') != '1'
+        self.device, self.slot = device, slot
+        self.side = self.main = None
+
+    class _Branch:
+        def __init__(self, outer):
+            self.outer, self.ctx = outer, None
+
+        def __enter__(self):
+            o = self.outer
+            if o.enabled:
+                o.side.wait_stream(o.main)
+                self.ctx = torch.cuda.stream(o.side)
+                self.ctx.__enter__()
+            return self
+
+        def __exit__(self, *exc):
+            if self.ctx is not None:
+                self.ctx.__exit__(*exc)
+            return False
+
+    def __enter__(self):
+        if self.enabled:
+            key = (self.device.index, self.slot)
+            if key not in fork_stream._streams:
+                fork_stream._streams[key] = torch.cuda.Stream(self.device)
+            self.side, self.main = fork_stream._streams[key], torch.cuda.current_stream(self.device)
+        return fork_stream._Branch(self)
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            self.main.wait_stream(self.side)
+        return False
+
+
 def grad_target(p: nn.Parameter) -> torch.Tensor:
     """The fp32 buffer a kernel accumulates d(loss)/dp into.  Handles `optimizer.zero_grad(set_to_none=True)`."""
     if p.grad is None:
@@ -842,8 +885,13 @@ class PCME(StoreMixin, nn.Module):
 
     def forward(self, images, sentences, captions_word, lengths):
         self.store()
-        image_output = self.img_enc(images)
-        caption_output = self.text_forward(captions_word)
+        # the two towers share nothing until the loss: the text tower (tensor-bound GEMMs) is forked onto a side
+        # stream so that it fills the SMs the image tower's HBM- / latency-bound kernels leave idle; autograd replays
+        # each tower's backward on its forward stream, the towers write disjoint regions of the flat gradient buffer
+        with fork_stream(images.device, getattr(self, 'overlap_towers', True)) as side:
+            with side:
+                caption_output = self.text_forward(captions_word)
+            image_output = self.img_enc(images)
         return {
             'image_features': image_output['embedding'],
             'image_attentions': image_output.get('attention'),
