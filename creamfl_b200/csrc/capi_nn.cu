@@ -532,3 +532,24 @@ extern "C" int creamfl_dropout_mask(const void* rng, int site, int64_t n, float 
 extern "C" int creamfl_rng_tick(void* rng, void* stream) {
   return rng_tick(reinterpret_cast<unsigned long long*>(rng), S(stream));
 }
+
+// ---------------------------------------------------------------------------------------------- fused ResNet stem
+extern "C" int creamfl_stem_supported(int H, int W) { return stem_supported(3, H, W, 7, 7, 2, 3, 64) ? 1 : 0; }
+
+extern "C" int creamfl_stem_fprop(const float* images, int N, int H, int W, const void* w_bf16, int64_t w_pitch,
+                                  void* y_bf16, void* stream) {
+  if (!images || !w_bf16 || !y_bf16) {
+    set_error("stem_fprop: null pointer");
+    return CFL_EINVAL;
+  }
+  return stem_fprop(images, w_bf16, w_pitch, N, H, W, y_bf16, S(stream));
+}
+
+extern "C" int creamfl_stem_wgrad(const float* images, const void* dy_bf16, int N, int H, int W, float* dw,
+                                  void* stream) {
+  if (!images || !dy_bf16 || !dw) {
+    set_error("stem_wgrad: null pointer");
+    return CFL_EINVAL;
+  }
+  return stem_wgrad(images, dy_bf16, N, H, W, dw, S(stream));
+}

@@ -39,7 +39,9 @@ struct GemmCfg {
   static constexpr int kOutBytes = kBM * BN * 2;            // bf16 output tile staged for the TMA store
   static constexpr int kOutBufs = (BN == 256) ? 1 : 2;      // staging buffers (BN = 256: 64 KB, single)
   static constexpr int kAddBufs = ADD_TMA ? 2 : 0;
-  static constexpr int kStatBytes = ADD_TMA ? 0 : 2 * BN * 8;   // per-column (sum, sum of squares) fp64 accumulators
+  // BatchNorm statistics: every epilogue thread owns one (row group, column pair) slot of fp64 accumulators
+  // (sum, sum of squares): [512 / BN row groups][BN] doubles x 2 = 8 KB, no shared-memory atomics
+  static constexpr int kStatBytes = ADD_TMA ? 0 : 2 * 512 * 8;
   static constexpr int kSmemBytes =
       kStages * kStageBytes + (kOutBufs + kAddBufs) * kOutBytes + 1024 /*align*/ + 256 /*barriers*/ + kStatBytes;
   static constexpr uint32_t kTmemCols = 2 * BN;              // two accumulator buffers (power of two)
@@ -91,8 +93,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* dfull = tempty + 2;                              // [2] residual tile landed
   uint64_t* dempty = dfull + 2;                              // [2] residual tile consumed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
-  double* s_csum = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [BN] (only if kStatBytes)
-  double* s_csq = s_csum + BN;                                                          // [BN]
+  double* s_csum = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [RG][BN] (only if kStatBytes)
+  double* s_csq = s_csum + 512;                                                         // [RG][BN], RG = 512 / BN
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -223,8 +225,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool do_stats = STATS && !ADD_TMA && p.stats != nullptr && p.tma_out;
     const int etid = threadIdx.x - 128;
     int acc_n_blk = -1;
+    constexpr int kStatRG = 512 / BN;      // row groups of the column-sum pass below
     if (do_stats) {
-      if (etid < BN) { s_csum[etid] = 0.0; s_csq[etid] = 0.0; }
+      for (int e = etid; e < 512; e += 256) { s_csum[e] = 0.0; s_csq[e] = 0.0; }
       asm volatile("bar.sync 3, 256;" ::: "memory");
     }
     // dropout of the linear output (HF BertSelfOutput / BertOutput: dense -> dropout -> + residual): the mask is a
@@ -249,10 +252,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (do_stats && acc_n_blk != n_blk) {
         if (acc_n_blk >= 0) {
           if (etid < BN && acc_n_blk * BN + etid < p.N) {
-            atomicAdd(p.stats + acc_n_blk * BN + etid, s_csum[etid]);
-            atomicAdd(p.stats + p.N + acc_n_blk * BN + etid, s_csq[etid]);
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int g = 0; g < kStatRG; ++g) { a += s_csum[g * BN + etid]; b += s_csq[g * BN + etid]; }
+            atomicAdd(p.stats + acc_n_blk * BN + etid, a);
+            atomicAdd(p.stats + p.N + acc_n_blk * BN + etid, b);
           }
-          if (etid < BN) { s_csum[etid] = 0.0; s_csq[etid] = 0.0; }
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+          for (int e = etid; e < 512; e += 256) { s_csum[e] = 0.0; s_csq[e] = 0.0; }
           asm volatile("bar.sync 3, 256;" ::: "memory");
         }
         acc_n_blk = n_blk;
@@ -317,7 +324,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int du = (ctile & 63) >> 3;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 pk = *reinterpret_cast<const uint4*>(dbase + sw128_offset(rloc, du + j));
+              const uint4 pk = lds128(smem_u32(dbase) + sw128_offset(rloc, du + j));
               const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -423,7 +430,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 4; ++j) {
             const uint4 pk = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
                                         pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-            *reinterpret_cast<uint4*>(rbase + sw128_offset(rloc, unit0 + j)) = pk;
+            sts128(smem_u32(rbase) + sw128_offset(rloc, unit0 + j), pk);
           }
         } else if (live) {
           if (p.split_k > 1 || p.atomic_out) {
@@ -490,25 +497,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int col = cp * 2;
           const uint8_t* cbase = stile + (col >> 6) * (kBM * 128) + (col & 7) * 2;
           const int unit = (col & 63) >> 3;
+          const uint32_t cbase_u32 = smem_u32(cbase);
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
           for (int r = rg * RPT; r < (rg + 1) * RPT; ++r) {
-            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(cbase + sw128_offset(r, unit)));
+            const uint32_t raw = lds32(cbase_u32 + sw128_offset(r, unit));
+            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw));
             s0 += v.x; s1 += v.y;
             q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1);
           }
-          atomicAdd(&s_csum[col], (double)s0);       // fp64: the accumulation order cannot change the statistics
-          atomicAdd(&s_csum[col + 1], (double)s1);
-          atomicAdd(&s_csq[col], (double)q0);
-          atomicAdd(&s_csq[col + 1], (double)q1);
+          // this thread's own fp64 slots (row group rg, columns col, col + 1): plain read-modify-write, no atomics
+          const uint32_t ps = smem_u32(s_csum + rg * BN + col), pq = smem_u32(s_csq + rg * BN + col);
+          sts_f64(ps, lds_f64(ps) + (double)s0);
+          sts_f64(ps + 8, lds_f64(ps + 8) + (double)s1);
+          sts_f64(pq, lds_f64(pq) + (double)q0);
+          sts_f64(pq + 8, lds_f64(pq + 8) + (double)q1);
         }
       }
     }
     if (do_stats) {
       asm volatile("bar.sync 3, 256;" ::: "memory");
       if (acc_n_blk >= 0 && etid < BN && acc_n_blk * BN + etid < p.N) {
-        atomicAdd(p.stats + acc_n_blk * BN + etid, s_csum[etid]);
-        atomicAdd(p.stats + p.N + acc_n_blk * BN + etid, s_csq[etid]);
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int g = 0; g < kStatRG; ++g) { a += s_csum[g * BN + etid]; b += s_csq[g * BN + etid]; }
+        atomicAdd(p.stats + acc_n_blk * BN + etid, a);
+        atomicAdd(p.stats + p.N + acc_n_blk * BN + etid, b);
       }
     }
     // the staging buffers must have been READ before the CTA (and its shared memory) goes away; the global writes of

@@ -65,6 +65,10 @@ namespace cfl {
 int conv_same_fprop(const void*, const void*, int, int, int, int, int, int, int, void*, cudaStream_t);
 int conv_same_dgrad(const void*, const void*, int, int, int, int, int, int, int, void*, const void*, cudaStream_t);
 int conv_same_wgrad(const void*, const void*, int, int, int, int, int, int, int, float*, cudaStream_t);
+// stem_tc.cu
+bool stem_supported(int C, int H, int W, int R, int S, int stride, int pad, int Cout);
+int stem_fprop(const float* x, const void* wt, long long ldw, int N, int H, int W, void* y, cudaStream_t stream);
+int stem_wgrad(const float* x, const void* dy, int N, int H, int W, float* dw, cudaStream_t stream);
 // nn_ops.cu
 int bn_train_fwd(const void*, long long, int, const float*, const float*, float, float, float*, float*, double*,
                  float*, float*, float*, float*, const void*, int, int, long long*, void*, cudaStream_t);

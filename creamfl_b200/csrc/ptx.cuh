@@ -21,6 +21,35 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- explicit shared-space accesses
+// Pointers carved out of the dynamic shared-memory block through integer alignment arithmetic lose their address
+// space: the compiler then emits GENERIC loads / stores (LD.E / ST.E with descriptor set-up) instead of LDS / STS.
+// Hot shared-memory traffic goes through these wrappers on 32-bit shared addresses (smem_u32).
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  // no "memory" clobber: volatile asm statements keep their order relative to the fences / barriers (also volatile),
+  // and the compiler stays free to schedule the surrounding arithmetic
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) { return __uint_as_float(lds32(addr)); }
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v));
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

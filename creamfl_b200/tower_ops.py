@@ -146,6 +146,28 @@ def im2col_images(images: torch.Tensor, r: int, s: int, stride: int, pad: int, p
     return col
 
 
+def stem_supported(h: int, w: int) -> bool:
+    return bool(_lib.load().creamfl_stem_supported(int(h), int(w)))
+
+
+def stem_fprop(images: torch.Tensor, w16: torch.Tensor) -> torch.Tensor:
+    """fp32 NCHW images, bf16 filters [64, pitch >= 147] -> bf16 NHWC [N, Ho, Wo, 64] (conv 7x7/2 pad 3), patches
+    assembled in shared memory."""
+    _need_cuda(images, w16)
+    n, c, h, w = images.shape
+    ho, wo = conv_out_hw(h, w, 7, 7, 2, 3)
+    y = torch.empty((n, ho, wo, 64), dtype=BF16, device=images.device)
+    _chk(_lib.load().creamfl_stem_fprop(_p(images), n, h, w, _p(w16), w16.stride(0), _p(y), _stream()), "stem_fprop")
+    return y
+
+
+def stem_wgrad(images: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor) -> None:
+    """dw (fp32 [64, 147], contiguous) += dy^T patches(images); dy bf16 NHWC [N, Ho, Wo, 64]."""
+    _need_cuda(images, dy, dw)
+    n, c, h, w = images.shape
+    _chk(_lib.load().creamfl_stem_wgrad(_p(images), _p(dy), n, h, w, _p(dw), _stream()), "stem_wgrad")
+
+
 # --------------------------------------------------------------------------------------------------- BatchNorm
 class BNScratch:
     """Per-layer scratch of the BatchNorm kernels (fp64 sums, per-channel affine / backward coefficients)."""

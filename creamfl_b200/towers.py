@@ -421,26 +421,35 @@ class _StemFn(torch.autograd.Function):
         n, c, h, w = images.shape
         need = any(ctx.needs_input_grad)
         w16 = net.stem_shadow()
-        col = T.im2col_images(images, 7, 7, 2, 3, w16.shape[1])
-        ho, wo = T.conv_out_hw(h, w, 7, 7, 2, 3)
-        o = ops.gemm_bf16(col, w16).view(n, ho, wo, 64)
+        images = images.contiguous()
+        fused = images.dtype == torch.float32 and T.stem_supported(h, w)
+        if fused:
+            # patches assembled in shared memory inside the implicit GEMM (csrc/stem_tc.cu): no patch matrix in HBM
+            col = None
+            o = T.stem_fprop(images, w16)
+        else:
+            col = T.im2col_images(images, 7, 7, 2, 3, w16.shape[1])
+            ho, wo = T.conv_out_hw(h, w, 7, 7, 2, 3)
+            o = ops.gemm_bf16(col, w16).view(n, ho, wo, 64)
         a, s = net.bn1.fwd(o)
         y, idx = T.maxpool_fwd(a, want_idx=need)
         ctx.net = net
-        # the patch matrix (0.5 GB at batch 128) is kept for the weight gradient instead of being rebuilt: HBM capacity
-        # is plentiful (180 GB), the rebuild was a 0.37 ms pass over 0.57 GB
-        ctx.saved = (col, o, a, s, idx) if need else None
+        ctx.saved = (images if fused else col, fused, o, a, s, idx) if need else None
         return y
 
     @staticmethod
     def backward(ctx, dy):
         net = ctx.net
-        col, o, a, s, idx = ctx.saved
+        src, fused, o, a, s, idx = ctx.saved
         ctx.saved = None
         da = T.maxpool_bwd(dy.contiguous(), idx, a.shape)
         do, _ = net.bn1.bwd(da, None, o, s, relu_from_x=True)
         g = grad_target(net.conv1.weight)                         # [64, 147] fp32
-        ops.gemm_bf16(do.view(-1, 64), col, a_mn=True, b_mn=True, out=g, split_k=0, accumulate=True, n_cols=g.shape[1])
+        if fused:
+            T.stem_wgrad(src, do, g)                              # patches re-assembled in shared memory from the images
+        else:
+            ops.gemm_bf16(do.view(-1, 64), src, a_mn=True, b_mn=True, out=g, split_k=0, accumulate=True,
+                          n_cols=g.shape[1])
         return (None, None) + (None,) * (len(ctx.needs_input_grad) - 2)
 
 

@@ -148,6 +148,17 @@ int creamfl_conv2d_wgrad(const void* dy_bf16, const void* x_bf16, const void* co
 int creamfl_im2col_nchw_f32(const float* images, int N, int C, int H, int W, int R, int S, int stride, int pad,
                             int col_pitch, void* col_bf16, void* stream);
 
+/* ---- fused ResNet stem: conv 7x7 / stride 2 / pad 3, 3 -> 64 channels, straight from fp32 NCHW images (torchvision
+ * ResNet.conv1 reached from image_encoder.py:24,55 and resnet_client.py:164).  The patch operand of the implicit GEMM
+ * is assembled in shared memory, no patch matrix is written to HBM.  Supported when the output row fits one tile
+ * (image width <= 256); creamfl_stem_supported tells (callers fall back to creamfl_im2col_nchw_f32 + creamfl_gemm_bf16).
+ * w_bf16: filters [64, w_pitch >= 147] bf16 in (r, s, c) column order, zeros between 147 and the pitch;
+ * y [N, Ho, Wo, 64] bf16; dw [64, 147] fp32 accumulated (+= dy^T patches). */
+int creamfl_stem_supported(int H, int W);
+int creamfl_stem_fprop(const float* images, int N, int H, int W, const void* w_bf16, int64_t w_pitch, void* y_bf16,
+                       void* stream);
+int creamfl_stem_wgrad(const float* images, const void* dy_bf16, int N, int H, int W, float* dw, void* stream);
+
 /* ---- BatchNorm2d over NHWC bf16 (P = N*H*W pixels), fused with the residual add and ReLU of the ResNet blocks.
  * train: batch statistics (fp64 accumulation in `sums`, 2*C doubles, zero on entry and on exit), running stats
  * updated with `momentum`; keeps mean/rstd for the backward.  scale/shift: C-float scratch each.

@@ -357,6 +357,25 @@ def im2col_images(images, r, s_, stride, pad, pitch):
     return out
 
 
+def stem_supported(h, w):
+    return w <= 256 and w % 4 == 0 and (w + 6 - 7) // 2 + 1 <= 128
+
+
+def stem_fprop(images, w16):
+    """conv 7x7 / stride 2 / pad 3 from fp32 NCHW images; w16 [64, >= 147] in (r, s, c) column order."""
+    wt = w16[:, :147].float().view(64, 7, 7, 3).permute(0, 3, 1, 2)
+    x = images.to(BF16).float()                     # the kernel rounds the patch operand to bf16
+    return F.conv2d(x, wt, stride=2, padding=3).permute(0, 2, 3, 1).contiguous().to(BF16)
+
+
+def stem_wgrad(images, dy, dw):
+    x = images.to(BF16).float()
+    cols = F.unfold(x, (7, 7), padding=3, stride=2)                                   # [N, 3*49, L] in (c, r, s) order
+    n, _, l = cols.shape
+    cols = cols.view(n, 3, 49, l).permute(0, 3, 2, 1).reshape(n * l, 147)             # (r, s, c) order
+    dw += dy.float().reshape(-1, 64).t() @ cols
+
+
 def bn_train_fwd(x, gamma, beta, running_mean, running_var, sc, eps, momentum, res=None, relu=True, stats_ready=False,
                  num_batches_tracked=None):
     c = x.shape[-1]
@@ -517,7 +536,7 @@ _TOWER_OPS = ('wemb_gather', 'wemb_scatter', 'gru_fwd', 'gru_bwd', 'seq_pool_fwd
               'scale_relu_bwd', 'layernorm_fwd', 'layernorm_bwd', 'act_bwd', 'colsum_into', 'relu_inplace', 'conv_fprop',
               'conv_dgrad', 'conv_wgrad', 'im2col_images', 'bn_train_fwd', 'bn_eval_fwd', 'bn_train_bwd', 'maxpool_fwd',
               'maxpool_bwd', 'embed_fwd', 'embed_bwd', 'attn_fwd', 'attn_bwd', 'pie_pool_fwd', 'pie_pool_bwd',
-              'avgpool_fwd', 'avgpool_bwd', 'gemm_drop')
+              'avgpool_fwd', 'avgpool_bwd', 'gemm_drop', 'stem_supported', 'stem_fprop', 'stem_wgrad')
 
 
 def install(monkeypatch, exact=False):

@@ -270,3 +270,36 @@ def test_pie_pool(T, b, p, c, hd):
     assert rel_l2(dx, x64.grad) < 6e-3
     assert rel_l2(dpre, h64.grad * (1 - h.double() ** 2)) < 6e-3
     assert rel_l2(dw2, w64.grad) < 1e-3
+
+
+@pytest.mark.parametrize('n,h,w', [(4, 224, 224), (3, 64, 64), (2, 256, 256), (150, 32, 48), (2, 225, 132)])
+def test_fused_stem_matches_conv7x7(T, n, h, w):
+    """csrc/stem_tc.cu (patch operand assembled in shared memory) against fp64 conv2d / its weight gradient on the same
+    bf16-rounded operands, and against the materialised im2col + GEMM path it replaces."""
+    from creamfl_b200 import ops
+    assert T.stem_supported(h, w)
+    g = torch.Generator().manual_seed(5)
+    images = torch.randn(n, 3, h, w, generator=g)
+    wt = (torch.randn(64, 3, 7, 7, generator=g) * (2.0 / 147) ** 0.5).to(torch.bfloat16)
+    w16 = torch.zeros(64, 152, dtype=torch.bfloat16)
+    w16[:, :147] = wt.permute(0, 2, 3, 1).reshape(64, 147)              # (r, s, c) column order, zero tail to the pitch
+    y = T.stem_fprop(images.cuda(), w16.cuda())
+    ref = F.conv2d(images.to(torch.bfloat16).double(), wt.double(), stride=2, padding=3).permute(0, 2, 3, 1)
+    assert y.shape == ref.shape and rel_l2(y, ref) < 4e-3
+    col = T.im2col_images(images.cuda(), 7, 7, 2, 3, 152)
+    y_old = ops.gemm_bf16(col, w16.cuda()).view(y.shape)
+    assert rel_l2(y, y_old) < 1e-6 or torch.equal(y, y_old)             # same operands, same fp32 accumulation
+    dy = rnd(*y.shape, seed=6)
+    dw = torch.full((64, 147), 0.5, device='cuda')
+    T.stem_wgrad(images.cuda(), dy.cuda(), dw)
+    xd = images.to(torch.bfloat16).double()
+    wd = wt.double().requires_grad_(True)
+    (F.conv2d(xd, wd, stride=2, padding=3) * dy.double().permute(0, 3, 1, 2)).sum().backward()
+    want = wd.grad.permute(0, 2, 3, 1).reshape(64, 147)
+    assert rel_l2(dw - 0.5, want) < 2e-4
+
+
+def test_fused_stem_refuses_wide_images(T):
+    assert not T.stem_supported(300, 300) and not T.stem_supported(64, 130)     # rows travel as 16-byte chunks
+    with pytest.raises(RuntimeError):
+        T.stem_fprop(torch.randn(1, 3, 300, 300).cuda(), torch.zeros(64, 152, dtype=torch.bfloat16).cuda())
