@@ -9,7 +9,10 @@ import ctypes as C
 import re
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "libcreamfl_b200.so"
+import os
+
+# CREAMFL_LIB: development aid (A/B timing of two builds inside one GPU lease); the product loads the in-tree library
+_LIB_PATH = Path(os.environ.get("CREAMFL_LIB") or Path(__file__).resolve().parent / "libcreamfl_b200.so")
 _lib = None
 
 vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
