@@ -20,6 +20,7 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace cfl {
 
@@ -30,20 +31,24 @@ constexpr int kGemmThreads = 384;   // 4 control warps + 8 epilogue warps
 
 // ADD_TMA: the bf16 residual operand of the epilogue (`add`) is prefetched tile by tile into shared memory by the
 // TMA producer (two buffers), so its DRAM latency hides behind the previous tiles instead of stalling the epilogue.
-template <int BN, bool ADD_TMA = false>
+template <int BN, bool ADD_TMA = false, bool CTA2 = false>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBRows = CTA2 ? BN / 2 : BN;          // CTA pair: each CTA stages half of the B tile
+  static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = ADD_TMA ? 3 : ((BN == 256) ? 3 : (BN == 128 ? 4 : 6));
   static constexpr int kOutBytes = kBM * BN * 2;            // bf16 output tile staged for the TMA store
   static constexpr int kOutBufs = (BN == 256) ? 1 : 2;      // staging buffers (BN = 256: 64 KB, single)
   static constexpr int kAddBufs = ADD_TMA ? 2 : 0;
   // BatchNorm statistics: every epilogue thread owns one (row group, column pair) slot of fp64 accumulators
   // (sum, sum of squares): [512 / BN row groups][BN] doubles x 2 = 8 KB, no shared-memory atomics
   static constexpr int kStatBytes = ADD_TMA ? 0 : 2 * 512 * 8;
-  static constexpr int kSmemBytes =
-      kStages * kStageBytes + (kOutBufs + kAddBufs) * kOutBytes + 1024 /*align*/ + 256 /*barriers*/ + kStatBytes;
+  static constexpr int kFixedBytes = (kOutBufs + kAddBufs) * kOutBytes + 1024 /*align*/ + 256 /*barriers*/ + kStatBytes;
+  // single CTA: the round-1 stage counts; CTA pair: smaller stages, as many as fit (at most 8)
+  static constexpr int kPairStages = (227 * 1024 - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = CTA2 ? (kPairStages > 8 ? 8 : kPairStages)
+                                      : (ADD_TMA ? 3 : ((BN == 256) ? 3 : (BN == 128 ? 4 : 6)));
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
   static constexpr uint32_t kTmemCols = 2 * BN;              // two accumulator buffers (power of two)
 };
 
@@ -76,11 +81,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BN, bool A_MN, bool B_MN, bool ADD_TMA, bool STATS>
+// CTA2: the kernel runs as clusters of two CTAs on the two SMs of a TPC; a pair owns a 256 x BN output tile, the
+// leader (cluster rank 0) issues tcgen05.mma.cta_group::2 with M = 256 for both, each CTA loads its own 128 rows of A
+// and HALF of the B tile (L2 -> shared-memory operand traffic per FLOP drops by 1/4 .. 1/3), and each CTA runs the
+// epilogue of its own 128 accumulator rows.
+template <int BN, bool A_MN, bool B_MN, bool ADD_TMA, bool STATS, bool CTA2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, GemmParams p) {
-  using Cfg = GemmCfg<BN, ADD_TMA>;
+  using Cfg = GemmCfg<BN, ADD_TMA, CTA2>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sout = smem + Cfg::kStages * Cfg::kStageBytes;    // [2][kOutBytes], 1024-aligned (stage sizes are)
@@ -99,11 +108,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m = (p.M + kBM - 1) / kBM;
+  // work units: (M block, N block, K split); a CTA pair takes M blocks of 256 rows, rank r of the pair the r-th half
+  const int cta_rank = CTA2 ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int wid = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // worker (CTA or CTA pair) index
+  const int wstride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_m = CTA2 ? (p.M + 2 * kBM - 1) / (2 * kBM) : (p.M + kBM - 1) / kBM;
   const int num_n = (p.N + BN - 1) / BN;
   const int nkb = (p.K + kBK - 1) / kBK;
   const int kb_per = (nkb + p.split_k - 1) / p.split_k;
   const int units = num_m * num_n * p.split_k;
+  auto row_block = [&](int u) { return CTA2 ? 2 * (u % num_m) + cta_rank : u % num_m; };   // 128-row block of this CTA
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -118,15 +133,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);
+      mbar_init(&tempty[i], CTA2 ? 16 : 8);     // pair: the epilogue warps of BOTH CTAs release the leader's buffer
       mbar_init(&dfull[i], 1);
       mbar_init(&dempty[i], 8);
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if (CTA2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot); else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();     // pair: the peer's barriers are initialised too
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -136,12 +153,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
-        const int m_blk = u % num_m;
+      for (int u = wid; u < units; u += wstride, ++it) {
+        const int m_blk = row_block(u);
         const int n_blk = (u / num_m) % num_n;
         const int ks = u / (num_m * num_n);
         const int kb0 = ks * kb_per;
         const int kb1 = min(nkb, kb0 + kb_per);
+        const int b_row0 = n_blk * BN + (CTA2 ? cta_rank * (BN / 2) : 0);     // this CTA's slice of the B tile
         if (ADD_TMA) {
           const int db = it & 1;
           mbar_wait(&dempty[db], ((it >> 1) & 1) ^ 1);
@@ -155,20 +173,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          // pair: both CTAs' bytes are counted on the LEADER's barrier (the MMA issuer waits there)
+          if (!CTA2) mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          else if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+          auto load = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
+            if (CTA2) tma_load_2d_pair(m, &full[stage], dst, c0, c1); else tma_load_2d(m, &full[stage], dst, c0, c1);
+          };
           if constexpr (!A_MN) {
-            tma_load_2d(&tmA, &full[stage], sa, kb * kBK, m_blk * kBM);
+            load(&tmA, sa, kb * kBK, m_blk * kBM);
           } else {
 #pragma unroll
-            for (int j = 0; j < kBM / 64; ++j)
-              tma_load_2d(&tmA, &full[stage], sa + j * 8192, m_blk * kBM + j * 64, kb * kBK);
+            for (int j = 0; j < kBM / 64; ++j) load(&tmA, sa + j * 8192, m_blk * kBM + j * 64, kb * kBK);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(&tmB, &full[stage], sb, kb * kBK, n_blk * BN);
+            load(&tmB, sb, kb * kBK, b_row0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(&tmB, &full[stage], sb + j * 8192, n_blk * BN + j * 64, kb * kBK);
+            for (int j = 0; j < Cfg::kBRows / 64; ++j) load(&tmB, sb + j * 8192, b_row0 + j * 64, kb * kBK);
           }
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -177,14 +198,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && leader) {
+    // ------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(1, kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc = make_idesc(1, CTA2 ? 2 * kBM : kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+      for (int u = wid; u < units; u += wstride, ++it) {
         const int ks = u / (num_m * num_n);
         const int kb0 = ks * kb_per;
         const int kb1 = min(nkb, kb0 + kb_per);
@@ -202,15 +223,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            umma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CTA2) umma_f16_ss_pair(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          if (CTA2) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);   // pair: frees both CTAs' slots
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[buf]);
+        if (CTA2) umma_commit_pair(&tfull[buf]); else umma_commit(&tfull[buf]);
       }
     }
   } else if (warp >= 4) {
@@ -236,8 +258,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const unsigned long long drop_seed = do_drop ? p.drop.rng[0] : 0ull;
     const uint32_t drop_step = do_drop ? (uint32_t)p.drop.rng[1] : 0u;
     int it = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
-      const int m_blk = u % num_m;
+    for (int u = wid; u < units; u += wstride, ++it) {
+      const int m_blk = row_block(u);
       const int n_blk = (u / num_m) % num_n;
       const int ks = u / (num_m * num_n);
       const int buf = it & 1;
@@ -477,7 +499,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&tempty[buf]);
+        if (CTA2) mbar_arrive_leader(&tempty[buf]); else mbar_arrive(&tempty[buf]);
         if (ADD_TMA) mbar_arrive(&dempty[buf]);
       }
       if (p.tma_out) {
@@ -531,18 +553,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();     // pair: no CTA leaves while its peer may still signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (CTA2) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base); else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, bool ADD_TMA = false, bool STATS = false>
+template <int BN, bool A_MN, bool B_MN, bool ADD_TMA = false, bool STATS = false, bool CTA2 = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td,
                        const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, ADD_TMA>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, ADD_TMA, STATS>;
+  using Cfg = GemmCfg<BN, ADD_TMA, CTA2>;
+  static_assert(Cfg::kStages >= 2 && Cfg::kSmemBytes <= 227 * 1024, "shared-memory budget");
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, ADD_TMA, STATS, CTA2>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -552,12 +575,50 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     }
     attr_set = true;
   }
-  const int num_m = (p.M + kBM - 1) / kBM;
   const int num_n = (p.N + BN - 1) / BN;
-  const int units = num_m * num_n * p.split_k;
-  const int grid = units < sm_count() ? units : sm_count();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, td, p);
+  if (!CTA2) {
+    const int num_m = (p.M + kBM - 1) / kBM;
+    const int units = num_m * num_n * p.split_k;
+    const int grid = units < sm_count() ? units : sm_count();
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, td, p);
+  } else {
+    // one cluster of two CTAs (the two SMs of a TPC) per 256-row work unit, persistent over units
+    const int num_m = (p.M + 2 * kBM - 1) / (2 * kBM);
+    const int units = num_m * num_n * p.split_k;
+    const int pairs = units < sm_count() / 2 ? units : sm_count() / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, td, p);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc (CTA pair): cudaLaunchKernelEx: %s", cudaGetErrorString(e));
+      return CFL_ECUDA;
+    }
+  }
   return check_launch("gemm_tc_kernel");
+}
+
+// CTA-pair (tcgen05 cta_group::2) eligibility of an [M, N, K] problem with tile width BN.
+bool gemm_use_pair(int M, int N, int K, int a_mn, int b_mn, int BN) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("CREAMFL_GEMM_2CTA");
+    enabled = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  (void)N; (void)K; (void)a_mn;
+  if (!enabled || (sm_count() & 1)) return false;
+  if (M < 2 * kBM) return false;
+  if (b_mn && BN < 128) return false;          // MN-major B travels in 64-column blocks: half a tile needs >= 64
+  return true;
 }
 
 // Tile width the launcher picks for an [M, N, K] problem (see gemm_bf16 below).
@@ -646,18 +707,24 @@ int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long l
   else
     rc = make_tmap_2d(&ta, a, 2, p.K, p.M, lda, 64, kBK);
   if (rc) return rc;
+  const bool pair = gemm_use_pair(p.M, p.N, p.K, a_mn, b_mn, BN);
   if (!b_mn)
-    rc = make_tmap_2d(&tb, b, 2, p.N, p.K, ldb, kBK, BN);   // BN <= 256 rows per box
+    rc = make_tmap_2d(&tb, b, 2, p.N, p.K, ldb, kBK, pair ? BN / 2 : BN);   // <= 256 rows per box; pair: half a tile
   else
     rc = make_tmap_2d(&tb, b, 2, p.K, p.N, ldb, 64, kBK);
   if (rc) return rc;
 
-#define CFL_DISPATCH(BNV)                                                                      \
-  do {                                                                                         \
-    if (!a_mn && !b_mn) return launch_gemm<BNV, false, false>(ta, tb, tc, td, p, stream);      \
-    if (!a_mn && b_mn) return launch_gemm<BNV, false, true>(ta, tb, tc, td, p, stream);        \
-    if (a_mn && !b_mn) return launch_gemm<BNV, true, false>(ta, tb, tc, td, p, stream);        \
-    return launch_gemm<BNV, true, true>(ta, tb, tc, td, p, stream);                            \
+#define CFL_DISPATCH2(BNV, P2)                                                                          \
+  do {                                                                                                  \
+    if (!a_mn && !b_mn) return launch_gemm<BNV, false, false, false, false, P2>(ta, tb, tc, td, p, stream);  \
+    if (!a_mn && b_mn) return launch_gemm<BNV, false, true, false, false, P2>(ta, tb, tc, td, p, stream);    \
+    if (a_mn && !b_mn) return launch_gemm<BNV, true, false, false, false, P2>(ta, tb, tc, td, p, stream);    \
+    return launch_gemm<BNV, true, true, false, false, P2>(ta, tb, tc, td, p, stream);                        \
+  } while (0)
+#define CFL_DISPATCH(BNV)            \
+  do {                               \
+    if (pair) CFL_DISPATCH2(BNV, true); \
+    CFL_DISPATCH2(BNV, false);       \
   } while (0)
   if (p.stats != nullptr && (!p.tma_out || add_tma || p.act != 0 || p.ldo != p.N)) {
     // statistics cannot ride in the epilogue for this configuration: run the GEMM, then the stand-alone pass
@@ -672,6 +739,10 @@ int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long l
     return bn_stats_only(p.out, p.M, p.N, stats, stream);
   }
   if (add_tma) {
+    if (pair) {
+      if (b_mn) return launch_gemm<128, false, true, true, false, true>(ta, tb, tc, td, p, stream);
+      return launch_gemm<128, false, false, true, false, true>(ta, tb, tc, td, p, stream);
+    }
     if (b_mn) return launch_gemm<128, false, true, true>(ta, tb, tc, td, p, stream);
     return launch_gemm<128, false, false, true>(ta, tb, tc, td, p, stream);
   }
@@ -679,6 +750,11 @@ int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long l
     if (a_mn || b_mn) {
       set_error("gemm_bf16: fused statistics are implemented for K-major operands (forward convolutions)");
       return CFL_EINVAL;
+    }
+    if (pair) {
+      if (BN == 64) return launch_gemm<64, false, false, false, true, true>(ta, tb, tc, td, p, stream);
+      if (BN == 256) return launch_gemm<256, false, false, false, true, true>(ta, tb, tc, td, p, stream);
+      return launch_gemm<128, false, false, false, true, true>(ta, tb, tc, td, p, stream);
     }
     if (BN == 64) return launch_gemm<64, false, false, false, true>(ta, tb, tc, td, p, stream);
     if (BN == 256) return launch_gemm<256, false, false, false, true>(ta, tb, tc, td, p, stream);
@@ -688,6 +764,7 @@ int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long l
   if (BN == 256) CFL_DISPATCH(256);
   CFL_DISPATCH(128);
 #undef CFL_DISPATCH
+#undef CFL_DISPATCH2
 }
 
 }  // namespace cfl

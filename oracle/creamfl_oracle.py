@@ -85,7 +85,7 @@ def moon_intra(z: torch.Tensor, z_old: torch.Tensor, target: torch.Tensor, tau: 
     pos = (z * target).sum(-1, keepdim=True)
     neg = (z * z_old).sum(-1, keepdim=True)
     logits = torch.cat((pos, neg), dim=1) / tau
-    labels = torch.zeros(z.shape[0], dtype=torch.long)
+    labels = torch.zeros(z.shape[0], dtype=torch.long, device=z.device)
     ce = torch.nn.functional.cross_entropy(logits, labels, reduction='sum')
     return ce / (z.shape[0] if denom is None else denom)
 
@@ -94,7 +94,7 @@ def mm_client_contrast_loss(out_img, out_txt, old_img, old_txt, g_img, g_txt, d_
                             loss_scale=False) -> Dict[str, torch.Tensor]:
     """reference MMClientTrainer.py:169-206 (both flags): intra over the stacked [2B,2] logits + inter both ways."""
     b = out_img.shape[0]
-    idx = torch.as_tensor(d_idx, dtype=torch.long)
+    idx = torch.as_tensor(d_idx, dtype=torch.long, device=out_img.device)
     intra = moon_intra(out_img, old_img, g_img[idx], denom=2 * b) + moon_intra(out_txt, old_txt, g_txt[idx],
                                                                                 denom=2 * b)
     inter = inter_infonce(out_img, g_txt, idx) + inter_infonce(out_txt, g_img, idx)
