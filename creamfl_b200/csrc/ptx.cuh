@@ -40,6 +40,12 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+template <int kOff>
+__device__ __forceinline__ uint32_t lds32_off(uint32_t addr) {       // ld.shared [addr + immediate]
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(kOff));
+  return v;
+}
 __device__ __forceinline__ float lds_f32(uint32_t addr) { return __uint_as_float(lds32(addr)); }
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
   double v;

@@ -77,6 +77,48 @@ def test_gemm_epilogues(ops, act):
     assert out16.dtype == torch.bfloat16 and rel_l2(out16, fn(pre)) < 4e-3
 
 
+@pytest.mark.parametrize('m,n,k', [(392, 160, 264), (129, 64, 72), (1000, 768, 768), (4096, 2304, 768), (200, 256, 1024),
+                                   (25088, 1024, 256)])
+@pytest.mark.parametrize('b_mn', [False, True])
+@pytest.mark.parametrize('bias,add', [(True, False), (False, True), (True, True), (False, False)])
+def test_gemm_specialised_store_epilogue(ops, m, n, k, b_mn, bias, add):
+    """The launches that qualify for the specialised bf16-store epilogue (alpha = 1, N % 32 == 0, optional bias, bf16
+    residual through TMA; gemm_tc_lean.cu) against fp64: ragged M, every tile width, single CTA (M < 256) and CTA pair."""
+    a = mk(m, k, 21)
+    b = mk(k, n, 22) if b_mn else mk(n, k, 22)
+    bv = torch.randn(n, generator=torch.Generator().manual_seed(23)) if bias else None
+    av = mk(m, n, 24) if add else None
+    ref = a.double() @ (b.double() if b_mn else b.double().t())
+    if bias:
+        ref = ref + bv.double()
+    if add:
+        ref = ref + av.double()
+    out = ops.gemm_bf16(a.cuda(), b.cuda(), b_mn=b_mn, bias=bv.cuda() if bias else None, add=av.cuda() if add else None)
+    assert out.dtype == torch.bfloat16 and rel_l2(out, ref) < 4e-3
+
+
+def test_gelu_bf16_epilogue_accuracy(ops):
+    """bf16 GELU / dGELU epilogues use the sigmoid-form normal CDF (max |error| 3.1e-5): against erf GELU in fp64 the
+    result stays at the bf16 rounding level (rel-L2 4e-3), tails included (pre-activations up to |x| ~ 12)."""
+    m, n, k = 512, 3072, 768
+    g = torch.Generator().manual_seed(31)
+    a = (torch.randn(m, k, generator=g) * 0.35).to(torch.bfloat16)
+    b = (torch.randn(n, k, generator=g) * 0.35).to(torch.bfloat16)
+    pre = a.double() @ b.double().t()
+    assert pre.abs().max() > 8
+    out, pre_g = ops.gemm_bf16(a.cuda(), b.cuda(), act=ops.ACT_GELU, want_preact=True)
+    assert rel_l2(out, torch.nn.functional.gelu(pre)) < 4e-3
+    ref = torch.nn.functional.gelu(pre)
+    # element-wise: half a bf16 ulp (2^-8 relative at the bottom of a binade) + the approximation's 3.1e-5 / fp32 noise
+    assert bool(((out.double().cpu() - ref).abs() <= 0.004 * ref.abs() + 2e-4).all())
+    x = pre_g.double().cpu().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    dy = mk(m, k, 32)
+    w = mk(k, n, 33)
+    d = ops.gemm_bf16(dy.cuda(), w.cuda(), b_mn=True, act=ops.ACT_DGELU, aux=pre_g)
+    assert rel_l2(d, (dy.double() @ w.double()) * x.grad) < 4e-3
+
+
 @pytest.mark.parametrize('act', ['dgelu', 'drelu'])
 def test_gemm_backward_epilogues(ops, act):
     m, n, k = 256, 3072, 768
