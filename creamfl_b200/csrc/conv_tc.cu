@@ -17,6 +17,7 @@
 // the 7x7 stem go through an explicit im2col buffer + gemm_tc (they are 4 % of the FLOPs).
 #include "kernels.cuh"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace cfl {
 
@@ -34,20 +35,29 @@ struct ConvParams {
 constexpr int kCBM = 128;
 constexpr int kCBK = 64;
 
-template <int BN>
+// CTA2: two CTAs of a cluster (the two SMs of a TPC) own one 256 x BN tile (tcgen05 cta_group::2): each CTA stages
+// its own 128 rows of A and HALF of the B tile, so the L2 -> shared-memory traffic per output element halves against
+// the 128 x 128 single-CTA tile.  The 3x3 convolutions at 14 x 14 ran at the L2 throughput cap (462 MB per launch at
+// 11.9 TB/s, profiles/r02_ncu_gemm_cases.md), not at the tensor pipe.
+template <int BN, bool CTA2 = false>
 struct ConvCfg {
   static constexpr int kABytes = kCBM * kCBK * 2;
-  static constexpr int kBBytes = BN * kCBK * 2;
+  static constexpr int kBRows = CTA2 ? BN / 2 : BN;
+  static constexpr int kBBytes = kBRows * kCBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 128) ? 6 : 8;
+  static constexpr int kStages = CTA2 ? ((BN == 256) ? 6 : 8) : ((BN == 128) ? 6 : 8);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
-  static constexpr uint32_t kTmemCols = (BN == 128) ? 256 : 128;
+  static constexpr uint32_t kTmemCols = (BN == 256) ? 512 : ((BN == 128) ? 256 : 128);
 };
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool CTA2>
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvParams p) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, CTA2>;
+  const int cta_rank = CTA2 ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int wid = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // worker (CTA or CTA pair) index
+  const int wstride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -66,13 +76,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int n_extent = (MODE == 0) ? p.Cout : p.Cin;                 // N of the GEMM
   const int num_n = (n_extent + BN - 1) / BN;
   int num_m, nkb, kb_per, units;
+  // pair: num_m counts 256-row blocks; rank r of the pair owns the 128-row block 2 * m + r
+  constexpr int kRowsPerUnit = CTA2 ? 2 * kCBM : kCBM;
   if (MODE == 2) {
-    num_m = (p.Cout + kCBM - 1) / kCBM;
+    num_m = (p.Cout + kRowsPerUnit - 1) / kRowsPerUnit;
     nkb = pix_tiles;
     kb_per = (nkb + p.split_k - 1) / p.split_k;
     units = num_m * num_n * taps * p.split_k;
   } else {
-    num_m = pix_tiles;
+    num_m = CTA2 ? (pix_tiles + 1) / 2 : pix_tiles;
     const int cred = (MODE == 0) ? p.Cin : p.Cout;
     nkb = taps * (cred / kCBK);
     kb_per = nkb;
@@ -90,13 +102,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], CTA2 ? 8 : 4);      // pair: the epilogue warps of BOTH CTAs release the leader's buffer
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if (CTA2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot); else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();     // pair: the peer's barriers are initialised too
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -105,9 +119,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      // pair: both CTAs' bytes are counted on the LEADER's barrier (the MMA issuer waits there)
+      auto expect = [&](int st) {
+        if (!CTA2) mbar_arrive_expect_tx(&full[st], Cfg::kStageBytes);
+        else if (leader) mbar_arrive_expect_tx(&full[st], 2 * Cfg::kStageBytes);
+      };
+      auto load4 = [&](const CUtensorMap* m, int st, void* dst, int c0, int c1, int c2, int c3) {
+        if (CTA2) tma_load_4d_pair(m, &full[st], dst, c0, c1, c2, c3); else tma_load_4d(m, &full[st], dst, c0, c1, c2, c3);
+      };
+      auto load2 = [&](const CUtensorMap* m, int st, void* dst, int c0, int c1) {
+        if (CTA2) tma_load_2d_pair(m, &full[st], dst, c0, c1); else tma_load_2d(m, &full[st], dst, c0, c1);
+      };
+      const int b_off = CTA2 ? cta_rank * (BN / 2) : 0;      // this CTA's slice of the B tile
+      for (int u = wid; u < units; u += wstride) {
         if (MODE != 2) {
-          const int m_blk = u % num_m;
+          const int m_blk = CTA2 ? 2 * (u % num_m) + cta_rank : u % num_m;
           const int n_blk = u / num_m;
           const int w0 = (m_blk % p.tiles_w) * p.bw;
           const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * p.bh;
@@ -123,14 +149,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
-            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-            tma_load_4d(&tmA, &full[stage], sa, c0, w0 + dw, h0 + dh, n0);
+            expect(stage);
+            load4(&tmA, stage, sa, c0, w0 + dw, h0 + dh, n0);
             if (MODE == 0) {
-              tma_load_2d(&tmB, &full[stage], sb, tap * p.Cin + c0, n_blk * BN);
+              load2(&tmB, stage, sb, tap * p.Cin + c0, n_blk * BN + b_off);
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_2d(&tmB, &full[stage], sb + j * 8192, tap * p.Cin + n_blk * BN + j * 64, c0);
+              for (int j = 0; j < Cfg::kBRows / 64; ++j)
+                load2(&tmB, stage, sb + j * 8192, tap * p.Cin + n_blk * BN + b_off + j * 64, c0);
             }
             if (++stage == Cfg::kStages) {
               stage = 0;
@@ -139,7 +165,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         } else {
           int t = u;
-          const int m_blk = t % num_m; t /= num_m;
+          const int m_blk = CTA2 ? 2 * (t % num_m) + cta_rank : t % num_m; t /= num_m;
           const int n_blk = t % num_n; t /= num_n;
           const int tap = t % taps;
           const int ks = t / taps;
@@ -154,13 +180,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
-            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+            expect(stage);
 #pragma unroll
             for (int j = 0; j < kCBM / 64; ++j)
-              tma_load_4d(&tmA, &full[stage], sa + j * 8192, m_blk * kCBM + j * 64, w0, h0, n0);
+              load4(&tmA, stage, sa + j * 8192, m_blk * kCBM + j * 64, w0, h0, n0);
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_4d(&tmB, &full[stage], sb + j * 8192, n_blk * BN + j * 64, w0 + dw, h0 + dh, n0);
+            for (int j = 0; j < Cfg::kBRows / 64; ++j)
+              load4(&tmB, stage, sb + j * 8192, n_blk * BN + b_off + j * 64, w0 + dw, h0 + dh, n0);
             if (++stage == Cfg::kStages) {
               stage = 0;
               phase ^= 1;
@@ -169,16 +195,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && leader) {
+    // ------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
     if (elect_one()) {
       constexpr bool A_MN = (MODE == 2);
       constexpr bool B_MN = (MODE != 0);
-      constexpr uint32_t idesc = make_idesc(1, kCBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc = make_idesc(1, CTA2 ? 2 * kCBM : kCBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+      for (int u = wid; u < units; u += wstride, ++it) {
         int kb0 = 0, kb1 = nkb;
         if (MODE == 2) {
           const int ks = u / (num_m * num_n * taps);
@@ -199,22 +225,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < kCBK / 16; ++k) {
             const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            umma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CTA2) umma_f16_ss_pair(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          if (CTA2) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);   // pair: frees both CTAs' slots
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[buf]);
+        if (CTA2) umma_commit_pair(&tfull[buf]); else umma_commit(&tfull[buf]);
       }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
     const int q = warp & 3;
     int it = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+    for (int u = wid; u < units; u += wstride, ++it) {
       const int buf = it & 1;
       const uint32_t bphase = (it >> 1) & 1;
       const int rloc = q * 32 + lane;
@@ -223,7 +250,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int n_blk;
       bool has_k = true;
       if (MODE != 2) {
-        const int m_blk = u % num_m;
+        const int m_blk = CTA2 ? 2 * (u % num_m) + cta_rank : u % num_m;
         n_blk = u / num_m;
         const int w = (m_blk % p.tiles_w) * p.bw + rloc % p.bw;
         const int h = ((m_blk / p.tiles_w) % p.tiles_h) * p.bh + (rloc / p.bw) % p.bh;
@@ -232,7 +259,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         row_off = (((long long)n * p.H + h) * p.W + w) * n_extent;
       } else {
         int t = u;
-        const int m_blk = t % num_m; t /= num_m;
+        const int m_blk = CTA2 ? 2 * (t % num_m) + cta_rank : t % num_m; t /= num_m;
         n_blk = t % num_n; t /= num_n;
         const int tap = t % taps;
         const int ks = t / taps;
@@ -296,23 +323,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (lane == 0) { if (CTA2) mbar_arrive_leader(&tempty[buf]); else mbar_arrive(&tempty[buf]); }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();     // pair: no CTA leaves while its peer may still signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (CTA2) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base); else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool CTA2 = false>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, int units,
                        cudaStream_t stream) {
-  using Cfg = ConvCfg<BN>;
-  auto kern = conv_tc_kernel<BN, MODE>;
+  using Cfg = ConvCfg<BN, CTA2>;
+  static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared-memory budget");
+  auto kern = conv_tc_kernel<BN, MODE, CTA2>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -322,9 +350,41 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvP
     }
     attr_set = true;
   }
-  const int grid = units < sm_count() ? units : sm_count();
-  kern<<<grid, 256, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  if (!CTA2) {
+    const int grid = units < sm_count() ? units : sm_count();
+    kern<<<grid, 256, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  } else {
+    // `units` counts 256-row work units: one cluster of two CTAs each, persistent over units
+    const int pairs = units < sm_count() / 2 ? units : sm_count() / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    if (e != cudaSuccess) {
+      set_error("conv_tc (CTA pair): cudaLaunchKernelEx: %s", cudaGetErrorString(e));
+      return CFL_ECUDA;
+    }
+  }
   return check_launch("conv_tc_kernel");
+}
+
+// CTA pairs serve the wide layers (CREAMFL_CONV_2CTA=0 switches them off: A/B measurements)
+static bool conv_pair_enabled() {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("CREAMFL_CONV_2CTA");
+    enabled = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return enabled != 0 && (sm_count() & 1) == 0;
 }
 
 // Largest power of two dividing x, capped.
@@ -368,11 +428,19 @@ int conv_same_fprop(const void* x, const void* wt, int N, int H, int W, int Cin,
   p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
   p.split_k = 1;
   p.out = y;
-  const int BN = (Cout <= 64) ? 64 : 128;
+  const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const bool pair = conv_pair_enabled() && Cout % 128 == 0 && pix_tiles >= 2;
+  const int BN = pair ? (Cout % 256 == 0 ? 256 : 128) : ((Cout <= 64) ? 64 : 128);
   CUtensorMap ta, tb;
   if ((rc = make_tmap_nhwc(&ta, x, N, H, W, Cin, 64, p.bw, p.bh, p.bn, 1))) return rc;
-  if ((rc = make_tmap_2d(&tb, wt, 2, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, 64, BN))) return rc;
-  const int units = p.tiles_w * p.tiles_h * p.tiles_n * ((Cout + BN - 1) / BN);
+  if ((rc = make_tmap_2d(&tb, wt, 2, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, 64, pair ? BN / 2 : BN)))
+    return rc;
+  if (pair) {
+    const int units = ((pix_tiles + 1) / 2) * (Cout / BN);
+    return BN == 256 ? launch_conv<256, 0, true>(ta, tb, p, units, stream)
+                     : launch_conv<128, 0, true>(ta, tb, p, units, stream);
+  }
+  const int units = pix_tiles * ((Cout + BN - 1) / BN);
   return BN == 64 ? launch_conv<64, 0>(ta, tb, p, units, stream) : launch_conv<128, 0>(ta, tb, p, units, stream);
 }
 
@@ -388,11 +456,18 @@ int conv_same_dgrad(const void* dy, const void* wt, int N, int H, int W, int Cin
   p.split_k = 1;
   p.out = dx;
   p.add = reinterpret_cast<const __nv_bfloat16*>(add);
-  const int BN = (Cin <= 64) ? 64 : 128;
+  const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const bool pair = conv_pair_enabled() && Cin % 128 == 0 && pix_tiles >= 2;
+  const int BN = pair ? (Cin % 256 == 0 ? 256 : 128) : ((Cin <= 64) ? 64 : 128);
   CUtensorMap ta, tb;
   if ((rc = make_tmap_nhwc(&ta, dy, N, H, W, Cout, 64, p.bw, p.bh, p.bn, 1))) return rc;
   if ((rc = make_tmap_2d(&tb, wt, 2, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, 64, 64))) return rc;
-  const int units = p.tiles_w * p.tiles_h * p.tiles_n * ((Cin + BN - 1) / BN);
+  if (pair) {
+    const int units = ((pix_tiles + 1) / 2) * (Cin / BN);
+    return BN == 256 ? launch_conv<256, 1, true>(ta, tb, p, units, stream)
+                     : launch_conv<128, 1, true>(ta, tb, p, units, stream);
+  }
+  const int units = pix_tiles * ((Cin + BN - 1) / BN);
   return BN == 64 ? launch_conv<64, 1>(ta, tb, p, units, stream) : launch_conv<128, 1>(ta, tb, p, units, stream);
 }
 
@@ -406,17 +481,21 @@ int conv_same_wgrad(const void* dy, const void* x, int N, int H, int W, int Cin,
   plan_box(H, W, 64, &p.bw, &p.bh, &p.bn);
   p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
   p.out = dw;
-  const int BN = (Cin <= 64) ? 64 : 128;
-  const int num_m = (Cout + kCBM - 1) / kCBM, num_n = (Cin + BN - 1) / BN;
+  const bool pair = conv_pair_enabled() && Cout % 256 == 0 && Cin % 128 == 0;
+  const int BN = pair ? (Cin % 256 == 0 ? 256 : 128) : ((Cin <= 64) ? 64 : 128);
+  const int num_m = pair ? Cout / 256 : (Cout + kCBM - 1) / kCBM, num_n = (Cin + BN - 1) / BN;
   const int base_units = num_m * num_n * R * S;
   const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   // whole waves of units (see plan_split_k in gemm_tc.cu); at least 8 pixel tiles per split
-  const int split = plan_split_k(base_units, pix_tiles, 8, 4.0);
+  const int split = plan_split_k(base_units, pix_tiles, 8, 4.0, pair ? sm_count() / 2 : 0);
   p.split_k = split;
   CUtensorMap ta, tb;
   if ((rc = make_tmap_nhwc(&ta, dy, N, H, W, Cout, 64, p.bw, p.bh, p.bn, 1))) return rc;
   if ((rc = make_tmap_nhwc(&tb, x, N, H, W, Cin, 64, p.bw, p.bh, p.bn, 1))) return rc;
   const int units = base_units * split;
+  if (pair)
+    return BN == 256 ? launch_conv<256, 2, true>(ta, tb, p, units, stream)
+                     : launch_conv<128, 2, true>(ta, tb, p, units, stream);
   return BN == 64 ? launch_conv<64, 2>(ta, tb, p, units, stream) : launch_conv<128, 2>(ta, tb, p, units, stream);
 }
 

@@ -56,8 +56,8 @@ int gemm_tile_n(int N, int K) {
 // (~4 k-block times, calibrated on the ResNet101 / BERT shapes with scripts/sweep_wgrad.py): pick the split with the
 // smallest waves * (k-blocks per unit + epilogue).  The earlier "two waves of 128-wide tiles" rule produced e.g.
 // 152 units on 148 SMs for the 23 + 22 1x1 convolutions of ResNet101's layer 3 (a second wave for 4 units).
-int plan_split_k(long long tiles, long long nkb, long long min_per, double epi_kb) {
-  const long long sms = sm_count();
+int plan_split_k(long long tiles, long long nkb, long long min_per, double epi_kb, int workers) {
+  const long long sms = workers > 0 ? workers : sm_count();
   long long max_split = nkb / (min_per > 0 ? min_per : 1);
   if (max_split < 1) max_split = 1;
   if (max_split > 4 * sms) max_split = 4 * sms;
@@ -169,6 +169,16 @@ int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long l
   if (lean_common && p.tma_out && !a_mn && (p.add == nullptr || add_tma) && (p.stats == nullptr || !b_mn) &&
       (p.bias == nullptr || (p.stats == nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)))
     return launch_gemm_store(BN, b_mn != 0, add_tma, p.stats != nullptr, pair, ta, tb, tc, td, p, stream);
+  // GELU (forward, K-major B, optional pre-activation output) / dGELU (data gradient, MN-major B) on 256-wide tiles
+  if (gemm_lean_enabled() && BN == 256 && p.tma_out && !a_mn && p.alpha == 1.0f && p.drop.rng == nullptr &&
+      p.add == nullptr && p.stats == nullptr && (p.N & 31) == 0 &&
+      (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
+    if (p.act == 1 && !b_mn && (p.out2 == nullptr || ((reinterpret_cast<uintptr_t>(p.out2) & 15) == 0 && (p.ldo2 & 7) == 0)))
+      return launch_gemm_gelu(false, pair, ta, tb, tc, td, p, stream);
+    if (p.act == 4 && b_mn && p.out2 == nullptr && p.bias == nullptr && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0 &&
+        (p.ld_aux & 7) == 0)
+      return launch_gemm_gelu(true, pair, ta, tb, tc, td, p, stream);
+  }
   if (lean_common && a_mn && b_mn && !p.out_bf16 && (p.split_k > 1 || p.atomic_out) && p.bias == nullptr &&
       p.add == nullptr && (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
     return launch_gemm_atomic(BN, pair, ta, tb, tc, td, p, stream);

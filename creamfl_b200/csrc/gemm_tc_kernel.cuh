@@ -20,6 +20,8 @@ constexpr int kGemmThreads = 384;   // 4 control warps + 8 epilogue warps
 constexpr int kEpiGeneral = 0;
 constexpr int kEpiStore = 1;    // bf16 tile -> swizzled staging -> TMA store; alpha = 1, optional bias, optional TMA residual,
                                 // optional BatchNorm statistics; N % 32 == 0
+constexpr int kEpiStoreGelu = 3;   // kEpiStore + erf-GELU of (acc + bias); optional second output = the pre-activation
+constexpr int kEpiStoreDgelu = 4;  // kEpiStore + multiply by GELU'(aux) (aux = bf16 pre-activation of the forward pass)
 constexpr int kEpiAtomic = 2;   // fp32 red.global.add.v4 (split-K weight gradients); alpha = 1, nothing else; N % 32 == 0
 
 // ADD_TMA: the bf16 residual operand of the epilogue (`add`) is prefetched tile by tile into shared memory by the
@@ -248,7 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-   if constexpr (EPI == kEpiStore) {
+   if constexpr (EPI == kEpiStore || EPI == kEpiStoreGelu || EPI == kEpiStoreDgelu) {
     // ------------------------------------------------------------ specialised epilogue: bf16 tile -> TMA store
     // (alpha = 1, N % 32 == 0, optional bias / TMA-staged residual / BatchNorm statistics; checked by the host)
     constexpr int HC = BN / 2;             // columns per thread
@@ -299,6 +301,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         acc_n_blk = n_blk;
       }
+      // dGELU: this thread's 32 pre-activations of a chunk (64 contiguous bytes) are fetched one chunk ahead, the
+      // first chunk before the accumulator is ready
+      const int row = m_blk * kBM + rloc;
+      const bool row_ok = row < p.M;
+      const __nv_bfloat16* aux_row = nullptr;
+      uint4 aux_v[2][4];
+      if constexpr (EPI == kEpiStoreDgelu) {
+        aux_row = p.aux + (long long)row * p.ld_aux + n_blk * BN + half * HC;
+        if (row_ok && n_blk * BN + half * HC < p.N) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) aux_v[0][j] = __ldg(reinterpret_cast<const uint4*>(aux_row) + j);
+        }
+      }
       if (ADD_TMA) mbar_wait(&dfull[buf], bphase);
       mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
@@ -310,6 +325,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_wait();
         if (c + 1 < NCH) {
           tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);     // in flight while chunk c is processed
+          if constexpr (EPI == kEpiStoreDgelu) {
+            if (row_ok && n_blk * BN + half * HC + (c + 1) * 32 < p.N) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                aux_v[(c + 1) & 1][j] = __ldg(reinterpret_cast<const uint4*>(aux_row + (c + 1) * 32) + j);
+            }
+          }
         } else {
           // the accumulator now lives in registers: hand the TMEM buffer back before the arithmetic
           tc_fence_before();
@@ -327,6 +349,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 8; ++j) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
             f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+          }
+        }
+        if constexpr (EPI == kEpiStoreGelu) {
+          if (p.out2 != nullptr && row_ok && col0 < p.N) {      // pre-activation for the backward pass
+            uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + (long long)row * p.ldo2 + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o2[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                 pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+        }
+        if constexpr (EPI == kEpiStoreDgelu) {
+          if (row_ok && col0 < p.N) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 pk = aux_v[c & 1][j];
+              const uint32_t r4[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                f[8 * j + 2 * i] *= dgelu_fast(__uint_as_float(r4[i] << 16));
+                f[8 * j + 2 * i + 1] *= dgelu_fast(__uint_as_float(r4[i] & 0xffff0000u));
+              }
+            }
           }
         }
         const uint32_t region = static_cast<uint32_t>(ctile >> 6) * (kBM * 128) + rloc * 128u;
@@ -817,6 +864,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 int launch_gemm_store(int BN, bool b_mn, bool add_tma, bool stats, bool pair, const CUtensorMap& ta,
                       const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td, const GemmParams& p,
                       cudaStream_t stream);
+int launch_gemm_gelu(bool dgelu, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                     const CUtensorMap& td, const GemmParams& p, cudaStream_t stream);      // 256-wide tiles
 int launch_gemm_atomic(int BN, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                        const CUtensorMap& td, const GemmParams& p, cudaStream_t stream);
 bool gemm_lean_enabled();

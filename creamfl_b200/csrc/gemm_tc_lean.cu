@@ -38,6 +38,18 @@ int launch_gemm_store(int BN, bool b_mn, bool add_tma, bool stats, bool pair, co
   return store_pair<128, false, false, false>(pair, ta, tb, tc, td, p, stream);
 }
 
+// BERT FFN: forward GELU (K-major weights, + pre-activation output) and the data gradient through it (MN-major
+// weights, multiply by GELU'(pre-activation)); 256-wide tiles (N = 3072, K >= 512)
+int launch_gemm_gelu(bool dgelu, bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                     const CUtensorMap& td, const GemmParams& p, cudaStream_t stream) {
+  if (dgelu) {
+    if (pair) return launch_gemm<256, false, true, false, false, true, kEpiStoreDgelu>(ta, tb, tc, td, p, stream);
+    return launch_gemm<256, false, true, false, false, false, kEpiStoreDgelu>(ta, tb, tc, td, p, stream);
+  }
+  if (pair) return launch_gemm<256, false, false, false, false, true, kEpiStoreGelu>(ta, tb, tc, td, p, stream);
+  return launch_gemm<256, false, false, false, false, false, kEpiStoreGelu>(ta, tb, tc, td, p, stream);
+}
+
 template <int BN>
 static int atomic_pair(bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                        const CUtensorMap& td, const GemmParams& p, cudaStream_t stream) {

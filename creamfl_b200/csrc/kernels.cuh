@@ -29,7 +29,7 @@ struct GemmParams {
 int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, GemmParams p,
               cudaStream_t stream);
 int gemm_tile_n(int N, int K);
-int plan_split_k(long long tiles, long long nkb, long long min_per, double epi_kb);
+int plan_split_k(long long tiles, long long nkb, long long min_per, double epi_kb, int workers = 0);
 int gemm_plan_split(int M, int N, int K);
 // sim_tc.cu
 size_t rowlse_workspace_bytes(int M, int N);
