@@ -87,6 +87,52 @@ int creamfl_conv2d_fprop(const void* x, const void* w, int N, int H, int W, int 
   return gemm_bf16(ws, c.ldc, 0, w, w_pitch, 0, p, S(stream));
 }
 
+int creamfl_conv2d_fprop_affine(const void* x, const void* w, int N, int H, int W, int Cin, int Cout, int R, int S_,
+                                int stride, int pad, int64_t w_pitch, const float* bias, const void* add, int relu,
+                                void* y, void* ws, size_t ws_bytes, void* stream) {
+  const ConvShape c = shape_of(N, H, W, Cin, Cout, R, S_, stride, pad);
+  int rc = check_shape("conv2d_fprop_affine", c);
+  if (rc) return rc;
+  if (!x || !w || !y) {
+    set_error("conv2d_fprop_affine: null pointer");
+    return CFL_EINVAL;
+  }
+  if (c.is_same && w_pitch == c.kcols)
+    return conv_same_fprop(x, w, N, H, W, Cin, Cout, R, S_, y, S(stream), bias, add, relu);
+  GemmParams p{};
+  p.M = (int)c.P_out; p.N = Cout; p.split_k = 1;
+  p.out = y; p.ldo = Cout; p.out_bf16 = 1; p.alpha = 1.0f;
+  p.bias = bias;
+  p.add = add; p.ld_add = Cout; p.add_bf16 = 1;
+  p.act = relu ? 2 : 0;
+  if (c.is_1x1) {
+    p.K = Cin;
+    return gemm_bf16(x, Cin, 0, w, w_pitch, 0, p, S(stream));
+  }
+  const size_t need = (size_t)c.P_out * c.ldc * 2;
+  if (!ws || ws_bytes < need) {
+    set_error("conv2d_fprop_affine: workspace %zu B < %zu B", ws_bytes, need);
+    return CFL_EWORKSPACE;
+  }
+  if (w_pitch < c.ldc) {
+    set_error("conv2d_fprop_affine: filter pitch %lld < padded patch width %d", (long long)w_pitch, c.ldc);
+    return CFL_EINVAL;
+  }
+  if ((rc = im2col_nhwc(x, N, H, W, Cin, R, S_, stride, pad, c.ldc, ws, S(stream)))) return rc;
+  p.K = c.ldc;
+  return gemm_bf16(ws, c.ldc, 0, w, w_pitch, 0, p, S(stream));
+}
+
+int creamfl_bn_fold_layers(const int64_t* layers, const int64_t* row_start, int n_layers, int64_t total_rows, float eps,
+                           void* stream) {
+  if (!layers || !row_start || n_layers <= 0 || total_rows <= 0) {
+    set_error("bn_fold_layers: null pointer / empty table");
+    return CFL_EINVAL;
+  }
+  return bn_fold_layers(reinterpret_cast<const long long*>(layers), reinterpret_cast<const long long*>(row_start),
+                        n_layers, total_rows, eps, S(stream));
+}
+
 int creamfl_conv2d_dgrad(const void* dy, const void* w, int N, int H, int W, int Cin, int Cout, int R, int S_,
                          int stride, int pad, int64_t w_pitch, const void* add, void* dx, void* ws, size_t ws_bytes,
                          void* stream) {

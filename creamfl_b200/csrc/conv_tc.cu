@@ -30,6 +30,8 @@ struct ConvParams {
   int split_k;           // wgrad only
   void* out;             // bf16 [N,H,W,Cout|Cin] (fprop/dgrad) or fp32 [Cout, R*S*Cin] accumulated (wgrad)
   const __nv_bfloat16* add;  // optional bf16 tensor added to the fprop/dgrad output (same layout as out)
+  const float* bias;         // optional per-output-channel bias (fprop: folded eval-mode BatchNorm shift)
+  int relu;                  // fprop: ReLU after bias / residual
 };
 
 constexpr int kCBM = 128;
@@ -292,31 +294,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (col0 + j < n_extent) atomicAdd(o + j, __uint_as_float(v[j]));
             }
           } else {
+            // channel counts are multiples of 64 (check_conv): every 32-column chunk inside the extent is complete,
+            // and this thread's 32 outputs are 64 contiguous, 16-byte aligned bytes
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + col0;
-            if (p.add != nullptr) {
-              const __nv_bfloat16* ar = p.add + row_off + col0;
+            float f[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < n_extent) v[j] = __float_as_uint(__uint_as_float(v[j]) + __bfloat162float(ar[j]));
-            }
-            if (col0 + 32 <= n_extent) {
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(o + j) = pk;
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
               }
-            } else {
+            }
+            if (p.add != nullptr) {
+              const uint4* ar = reinterpret_cast<const uint4*>(p.add + row_off + col0);
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < n_extent) o[j] = __float2bfloat16(__uint_as_float(v[j]));
+              for (int j = 0; j < 4; ++j) {
+                const uint4 pk = __ldg(ar + j);
+                const uint32_t r4[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  f[8 * j + 2 * i] += __uint_as_float(r4[i] << 16);
+                  f[8 * j + 2 * i + 1] += __uint_as_float(r4[i] & 0xffff0000u);
+                }
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j + 0], f[j + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&h0);
+              pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2);
+              pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(o + j) = pk;
             }
           }
         }
@@ -419,7 +438,7 @@ static int check_conv(const char* who, int N, int H, int W, int Cin, int Cout, i
 
 // Y = conv(X, Wt), stride 1, padding (R/2, S/2).  X [N,H,W,Cin], Wt [Cout,R,S,Cin], Y [N,H,W,Cout], all bf16.
 int conv_same_fprop(const void* x, const void* wt, int N, int H, int W, int Cin, int Cout, int R, int S, void* y,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const float* bias, const void* add, int relu) {
   int rc = check_conv("conv_fprop", N, H, W, Cin, Cout, R, S);
   if (rc) return rc;
   ConvParams p{};
@@ -428,6 +447,9 @@ int conv_same_fprop(const void* x, const void* wt, int N, int H, int W, int Cin,
   p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
   p.split_k = 1;
   p.out = y;
+  p.bias = bias;
+  p.add = reinterpret_cast<const __nv_bfloat16*>(add);
+  p.relu = relu;
   const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const bool pair = conv_pair_enabled() && Cout % 128 == 0 && pix_tiles >= 2;
   const int BN = pair ? (Cout % 256 == 0 ? 256 : 128) : ((Cout <= 64) ? 64 : 128);

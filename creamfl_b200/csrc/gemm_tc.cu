@@ -164,9 +164,10 @@ int gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long l
     return bn_stats_only(p.out, p.M, p.N, stats, stream);
   }
   // specialised epilogues (gemm_tc_lean.cu) for the launches that dominate a training step
-  const bool lean_common = gemm_lean_enabled() && p.alpha == 1.0f && p.drop.rng == nullptr && p.out2 == nullptr &&
-                           p.act == 0 && (p.N & 31) == 0;
-  if (lean_common && p.tma_out && !a_mn && (p.add == nullptr || add_tma) && (p.stats == nullptr || !b_mn) &&
+  const bool lean_base = gemm_lean_enabled() && p.alpha == 1.0f && p.drop.rng == nullptr && p.out2 == nullptr &&
+                         (p.N & 31) == 0;
+  const bool lean_common = lean_base && p.act == 0;
+  if (lean_base && (p.act == 0 || (p.act == 2 && p.stats == nullptr)) && p.tma_out && !a_mn && (p.add == nullptr || add_tma) && (p.stats == nullptr || !b_mn) &&
       (p.bias == nullptr || (p.stats == nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)))
     return launch_gemm_store(BN, b_mn != 0, add_tma, p.stats != nullptr, pair, ta, tb, tc, td, p, stream);
   // GELU (forward, K-major B, optional pre-activation output) / dGELU (data gradient, MN-major B) on 256-wide tiles

@@ -392,6 +392,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        if (EPI == kEpiStore && p.act == 2) {      // ReLU after the residual (eval-mode conv + folded BatchNorm)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint4 pk = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),

@@ -62,7 +62,8 @@ int recall_ranks(const float*, const float*, const long long*, const long long*,
 
 namespace cfl {
 // conv_tc.cu
-int conv_same_fprop(const void*, const void*, int, int, int, int, int, int, int, void*, cudaStream_t);
+int conv_same_fprop(const void*, const void*, int, int, int, int, int, int, int, void*, cudaStream_t,
+                    const float* bias = nullptr, const void* add = nullptr, int relu = 0);
 int conv_same_dgrad(const void*, const void*, int, int, int, int, int, int, int, void*, const void*, cudaStream_t);
 int conv_same_wgrad(const void*, const void*, int, int, int, int, int, int, int, float*, cudaStream_t);
 // stem_tc.cu
@@ -73,6 +74,7 @@ int stem_wgrad(const float* x, const void* dy, int N, int H, int W, float* dw, c
 int bn_train_fwd(const void*, long long, int, const float*, const float*, float, float, float*, float*, double*,
                  float*, float*, float*, float*, const void*, int, int, long long*, void*, cudaStream_t);
 int bn_stats_only(const void*, long long, int, double*, cudaStream_t);
+int bn_fold_layers(const long long*, const long long*, int, long long, float, cudaStream_t);
 int bn_eval_fwd(const void*, long long, int, const float*, const float*, float, const float*, const float*, float*,
                 float*, const void*, int, void*, cudaStream_t);
 int bn_train_bwd(const void*, const void*, const void*, long long, int, const float*, const float*, int, const float*,

@@ -433,6 +433,35 @@ int bn_train_bwd(const void* dy, const void* y_or_null, const void* x, long long
   return check_launch("bn_train_bwd");
 }
 
+// Eval-mode BatchNorm folded into the filters that feed it: one block per filter (output channel), all layers of a
+// network in one launch (the layer of a block is found by bisection of the row prefix sums).
+__global__ void __launch_bounds__(128)
+bn_fold_layers_kernel(const long long* __restrict__ layers, const long long* __restrict__ row_start, int n_layers,
+                      float eps) {
+  const long long b = blockIdx.x;
+  int lo = 0, hi = n_layers;          // row_start[lo] <= b < row_start[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (row_start[mid] <= b) lo = mid; else hi = mid;
+  }
+  const long long* e = layers + 10ll * lo;
+  const long long c = b - row_start[lo];
+  const float* w = reinterpret_cast<const float*>(e[0]);
+  const long long k = e[1];
+  __nv_bfloat16* w_out = reinterpret_cast<__nv_bfloat16*>(e[3]) + c * e[4];
+  const float s = reinterpret_cast<const float*>(e[5])[c] * rsqrtf(reinterpret_cast<const float*>(e[8])[c] + eps);
+  if (threadIdx.x == 0)
+    reinterpret_cast<float*>(e[9])[c] = reinterpret_cast<const float*>(e[6])[c] - reinterpret_cast<const float*>(e[7])[c] * s;
+  const float* wr = w + c * k;
+  for (long long i = threadIdx.x; i < k; i += blockDim.x) w_out[i] = __float2bfloat16(wr[i] * s);
+}
+
+int bn_fold_layers(const long long* layers, const long long* row_start, int n_layers, long long total_rows, float eps,
+                   cudaStream_t st) {
+  bn_fold_layers_kernel<<<(unsigned)total_rows, 128, 0, st>>>(layers, row_start, n_layers, eps);
+  return check_launch("bn_fold_layers");
+}
+
 // ------------------------------------------------------------------------------------------------ max pooling
 // 3x3, stride 2, pad 1 (torchvision ResNet stem).  idx stores the winning tap (0..8) per output element.
 __global__ void __launch_bounds__(256)

@@ -108,6 +108,32 @@ def conv_fprop(x: torch.Tensor, w2d: torch.Tensor, r: int, s: int, stride: int, 
     return y
 
 
+def conv_fprop_affine(x: torch.Tensor, w2d: torch.Tensor, r: int, s: int, stride: int, pad: int, bias: torch.Tensor,
+                      add: Optional[torch.Tensor] = None, relu: bool = True) -> torch.Tensor:
+    """Inference convolution with the following BatchNorm folded in: y = [relu](conv(x, w2d) + bias [+ add])
+    (w2d / bias from bn_fold_layers)."""
+    _need_cuda(x, w2d, bias, add)
+    n, h, w, cin = x.shape
+    cout = w2d.shape[0]
+    ho, wo = conv_out_hw(h, w, r, s, stride, pad)
+    y = torch.empty((n, ho, wo, cout), dtype=BF16, device=x.device)
+    lib = _lib.load()
+    nb = lib.creamfl_conv2d_workspace_bytes(n, h, w, cin, cout, r, s, stride, pad)
+    ws = workspace(nb, x.device) if nb else None
+    _chk(lib.creamfl_conv2d_fprop_affine(_p(x), _p(w2d), n, h, w, cin, cout, r, s, stride, pad, w2d.stride(0), _p(bias),
+                                         _p(add), int(relu), _p(y), _p(ws), nb, _stream()), "conv2d_fprop_affine",
+         2 if nb else 1)
+    return y
+
+
+def bn_fold_layers(layers: torch.Tensor, row_start: torch.Tensor, total_rows: int, eps: float, pairs=None) -> None:
+    """layers [n, 10] int64 / row_start [n + 1] int64 device tables (include/creamfl_b200.h: creamfl_bn_fold_layers).
+    `pairs` (the modules behind the table) is unused here; the kernel reads the addresses in the table."""
+    _need_cuda(layers, row_start)
+    _chk(_lib.load().creamfl_bn_fold_layers(_p(layers), _p(row_start), layers.shape[0], int(total_rows), eps, _stream()),
+         "bn_fold_layers", 1)
+
+
 def conv_dgrad(dy: torch.Tensor, w2d: torch.Tensor, x_shape, r: int, s: int, stride: int, pad: int,
                add: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(dy, w2d, add)

@@ -339,6 +339,13 @@ class Bottleneck(nn.Module):
             return y, (x, o1, a1, s1, o2, a2, s2, o3, s3, od, sd, y)
         return y, None
 
+    def run_eval(self, x, fold):
+        """Inference: every BatchNorm folded into its convolution (ResNet.fold_eval), ReLU / residual in the epilogues."""
+        a1 = fold.conv(self.conv1, x, relu=True)
+        a2 = fold.conv(self.conv2, a1, relu=True)
+        idn = x if self.downsample is None else fold.conv(self.downsample[0], x, relu=False)
+        return fold.conv(self.conv3, a2, add=idn, relu=True)
+
     def run_bwd(self, saved, dy):
         x, o1, a1, s1, o2, a2, s2, o3, s3, od, sd, y = saved
         do3, g = self.bn3.bwd(dy, y, o3, s3, want_g=True)
@@ -381,6 +388,11 @@ class BasicBlock(nn.Module):
         if save:
             return y, (x, o1, a1, s1, o2, s2, od, sd, y)
         return y, None
+
+    def run_eval(self, x, fold):
+        a1 = fold.conv(self.conv1, x, relu=True)
+        idn = x if self.downsample is None else fold.conv(self.downsample[0], x, relu=False)
+        return fold.conv(self.conv2, a1, add=idn, relu=True)
 
     def run_bwd(self, saved, dy):
         x, o1, a1, s1, o2, s2, od, sd, y = saved
@@ -453,10 +465,57 @@ class _StemFn(torch.autograd.Function):
         return (None, None) + (None,) * (len(ctx.needs_input_grad) - 2)
 
 
+class _EvalFold:
+    """Folded inference weights of a ResNet (one bf16 copy of every block convolution scaled by the BatchNorm that
+    follows it + the per-channel shifts) and the device tables creamfl_bn_fold_layers reads.  The fold is ONE launch
+    and runs at the start of every inference forward, so it always sees the current masters / running statistics
+    (also inside a captured CUDA graph)."""
+
+    def __init__(self, net: 'ResNet'):
+        pairs = net.block_conv_bn_pairs()
+        dev = pairs[0][0].weight.device
+        total_w = sum(c.weight.numel() for c, _ in pairs)
+        total_c = sum(c.weight.shape[0] for c, _ in pairs)
+        self.w16 = torch.empty(total_w, dtype=BF16, device=dev)
+        self.bias = torch.empty(total_c, dtype=torch.float32, device=dev)
+        self.views, self.pairs, rows, start = {}, [], [], [0]
+        ow = oc = 0
+        for conv, bn in pairs:
+            o = conv.weight.shape[0]
+            k = conv.weight.numel() // o
+            wv, bv = self.w16[ow:ow + o * k].view(o, k), self.bias[oc:oc + o]
+            self.views[id(conv)] = (wv, bv)
+            self.pairs.append((conv, bn, wv, bv))
+            rows.append([conv.weight.data_ptr(), k, o, wv.data_ptr(), k, bn.weight.data_ptr(), bn.bias.data_ptr(),
+                         bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bv.data_ptr()])
+            start.append(start[-1] + o)
+            ow += o * k
+            oc += o
+        self.layers = torch.tensor(rows, dtype=torch.int64).to(dev)
+        self.row_start = torch.tensor(start, dtype=torch.int64).to(dev)
+        self.total_rows = start[-1]
+        self.eps = pairs[0][1].eps
+        self.key = _EvalFold.key_of(pairs)
+
+    @staticmethod
+    def key_of(pairs):
+        (c0, b0), (c1, b1) = pairs[0], pairs[-1]
+        return (c0.weight.data_ptr(), b0.running_var.data_ptr(), c1.weight.data_ptr(), b1.running_var.data_ptr(),
+                b1.weight.data_ptr())
+
+    def refresh(self):
+        T.bn_fold_layers(self.layers, self.row_start, self.total_rows, self.eps, self.pairs)
+
+    def conv(self, c: 'Conv', x, add=None, relu=True):
+        w, b = self.views[id(c)]
+        return T.conv_fprop_affine(x, w, c.k, c.k, c.stride, c.pad, b, add=add, relu=relu)
+
+
 class ResNet(nn.Module):
     """torchvision.models.resnet{18,101} without avgpool/fc (image_encoder.py:24-32): images fp32 NCHW in,
     final feature map NHWC bf16 out."""
 
+    fold_eval_bn = True      # class-level switch (tests compare against the un-folded inference path)
     CFG = {'resnet18': (BasicBlock, [2, 2, 2, 2]), 'resnet34': (BasicBlock, [3, 4, 6, 3]),
            'resnet50': (Bottleneck, [3, 4, 6, 3]), 'resnet101': (Bottleneck, [3, 4, 23, 3]),
            'resnet152': (Bottleneck, [3, 8, 36, 3])}
@@ -487,8 +546,45 @@ class ResNet(nn.Module):
         """[64, 152] bf16 filter matrix of the stem (147 columns padded to a 16-byte pitch by the ParamStore)."""
         return self.conv1.weight._w16
 
+    def block_conv_bn_pairs(self):
+        """(convolution, BatchNorm that follows it) of every residual block, in execution order (the stem keeps its
+        own path: conv -> BatchNorm -> ReLU -> maxpool)."""
+        pairs = []
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for blk in layer:
+                pairs.append((blk.conv1, blk.bn1))
+                pairs.append((blk.conv2, blk.bn2))
+                if hasattr(blk, 'conv3'):
+                    pairs.append((blk.conv3, blk.bn3))
+                if blk.downsample is not None:
+                    pairs.append((blk.downsample[0], blk.downsample[1]))
+        return pairs
+
+    def eval_fold(self) -> '_EvalFold':
+        fold = self.__dict__.get('_fold')
+        if fold is None or fold.key != _EvalFold.key_of(self.block_conv_bn_pairs()):
+            fold = self.__dict__['_fold'] = _EvalFold(self)
+        return fold
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == '_fold' else copy.deepcopy(v, memo)
+        return new
+
     def forward(self, images):
         x = _StemFn.apply(images, self, self.conv1.weight, self.bn1.weight, self.bn1.bias)
+        if not self.training and not torch.is_grad_enabled() and self.fold_eval_bn:
+            # inference (public-feature extraction, the clients' old model): BatchNorm folded into the convolutions,
+            # no normalisation pass between them
+            fold = self.eval_fold()
+            fold.refresh()
+            for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+                for blk in layer:
+                    x = blk.run_eval(x, fold)
+            return x
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
             for blk in layer:
                 x = blk(x)

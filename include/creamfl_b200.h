@@ -135,6 +135,22 @@ size_t creamfl_conv2d_workspace_bytes(int N, int H, int W, int Cin, int Cout, in
 int creamfl_conv2d_fprop(const void* x_bf16, const void* w_bf16, int N, int H, int W, int Cin, int Cout, int R, int S,
                          int stride, int pad, int64_t w_pitch, void* y_bf16, double* bn_sums, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* Inference-mode convolution with the BatchNorm that follows folded in (torchvision ResNet under model.eval():
+ * image_encoder.py:24,55 reached from MMFL.py:194-221 / MMClientTrainer.py:326-359 / the old model of
+ * MMClientTrainer.py:154-167): y = [relu]( conv(x, w_folded) + bias [+ add] ), w_folded = w * gamma / sqrt(var + eps)
+ * per output channel and bias = beta - mean * gamma / sqrt(var + eps) (creamfl_bn_fold_rows).  add (optional) is a bf16
+ * tensor shaped like y (the residual).  Same three strategies and workspace as creamfl_conv2d_fprop. */
+int creamfl_conv2d_fprop_affine(const void* x_bf16, const void* w_bf16, int N, int H, int W, int Cin, int Cout, int R,
+                                int S, int stride, int pad, int64_t w_pitch, const float* bias, const void* add_bf16,
+                                int relu, void* y_bf16, void* workspace, size_t workspace_bytes, void* stream);
+/* Fold eval-mode BatchNorm layers into the filters of the convolutions that feed them, all layers in one launch.
+ * layers: device table [n_layers, 10] int64, one entry per convolution:
+ *   {w_f32 (address of the fp32 filters, [Cout, K] contiguous), K = R*S*Cin, Cout, w_out_bf16 (address), pitch of w_out
+ *    in elements (>= K), gamma, beta, running_mean, running_var (addresses of the C-float vectors), bias_out (address)}
+ * row_start: device [n_layers + 1] int64 prefix sums of Cout (row_start[n_layers] = total filter count).
+ * w_out[c, k] = bf16( w[c, k] * s_c ), bias_out[c] = beta[c] - mean[c] * s_c,  s_c = gamma[c] / sqrt(var[c] + eps). */
+int creamfl_bn_fold_layers(const int64_t* layers, const int64_t* row_start, int n_layers, int64_t total_rows, float eps,
+                           void* stream);
 /* dx = conv_transpose(dy, w) [+ add] ; add (optional) is a bf16 tensor shaped like dx (residual-branch gradient) */
 int creamfl_conv2d_dgrad(const void* dy_bf16, const void* w_bf16, int N, int H, int W, int Cin, int Cout, int R, int S,
                          int stride, int pad, int64_t w_pitch, const void* add_bf16, void* dx_bf16, void* workspace,

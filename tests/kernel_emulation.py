@@ -412,6 +412,29 @@ def bn_eval_fwd(x, gamma, beta, running_mean, running_var, sc, eps, res=None, re
     return y.to(BF16)
 
 
+def bn_fold_layers(layers, row_start, total_rows, eps, pairs=None):
+    """creamfl_bn_fold_layers: w_out[c, :] = w[c, :] * s_c, bias[c] = beta[c] - mean[c] * s_c (the table rows hold the
+    addresses of exactly these tensors; the emulation walks the modules behind them)."""
+    assert layers.shape == (len(pairs), 10) and int(row_start[-1]) == total_rows
+    with torch.no_grad():
+        for conv, bn, wv, bv in pairs:
+            o = conv.weight.shape[0]
+            s = bn.weight * torch.rsqrt(bn.running_var + eps)
+            wv.copy_((conv.weight.permute(0, 2, 3, 1).reshape(o, -1) * s[:, None]).to(wv.dtype))
+            bv.copy_(bn.bias - bn.running_mean * s)
+
+
+def conv_fprop_affine(x, w2d, r, s_, stride, pad, bias, add=None, relu=True):
+    n, h, w, cin = x.shape
+    cout = w2d.shape[0]
+    y = F.conv2d(_nchw(x), _filters(w2d, cout, r, s_, cin), stride=stride, padding=pad).permute(0, 2, 3, 1).float() + bias
+    if add is not None:
+        y = y + add.float()
+    if relu:
+        y = torch.relu(y)
+    return y.to(BF16)
+
+
 def bn_train_bwd(dy, y_mask, x, gamma, mean, rstd, sc, dgamma, dbeta, want_g=False, beta=None, relu_from_x=False):
     c = x.shape[-1]
     xhat = (x.float() - mean) * rstd
@@ -536,7 +559,8 @@ _TOWER_OPS = ('wemb_gather', 'wemb_scatter', 'gru_fwd', 'gru_bwd', 'seq_pool_fwd
               'scale_relu_bwd', 'layernorm_fwd', 'layernorm_bwd', 'act_bwd', 'colsum_into', 'relu_inplace', 'conv_fprop',
               'conv_dgrad', 'conv_wgrad', 'im2col_images', 'bn_train_fwd', 'bn_eval_fwd', 'bn_train_bwd', 'maxpool_fwd',
               'maxpool_bwd', 'embed_fwd', 'embed_bwd', 'attn_fwd', 'attn_bwd', 'pie_pool_fwd', 'pie_pool_bwd',
-              'avgpool_fwd', 'avgpool_bwd', 'gemm_drop', 'stem_supported', 'stem_fprop', 'stem_wgrad')
+              'avgpool_fwd', 'avgpool_bwd', 'gemm_drop', 'stem_supported', 'stem_fprop', 'stem_wgrad', 'bn_fold_layers',
+              'conv_fprop_affine')
 
 
 def install(monkeypatch, exact=False):

@@ -107,6 +107,27 @@ def test_pcme_eval_forward_exact(monkeypatch):
         o = mine(images, None, {'input_ids': ids, 'attention_mask': mask}, None)
     assert _rel(o['image_features'], o_ref['image_features']) < 1e-4
     assert _rel(o['caption_features'], o_ref['caption_features']) < 1e-4
+    # the inference path folds every block BatchNorm into its convolution (towers._EvalFold); the un-folded path
+    # (BatchNorm as its own pass) gives the same features, and the fold follows the parameters / running statistics
+    from creamfl_b200 import towers
+    assert mine.img_enc.cnn.__dict__.get('_fold') is not None
+    monkeypatch.setattr(towers.ResNet, 'fold_eval_bn', False)
+    with torch.no_grad():
+        o_plain = mine(images, None, {'input_ids': ids, 'attention_mask': mask}, None)
+    assert _rel(o['image_features'], o_plain['image_features']) < 1e-5
+    monkeypatch.setattr(towers.ResNet, 'fold_eval_bn', True)
+    with torch.no_grad():
+        blk = mine.img_enc.cnn.layer2[0]
+        blk.bn1.running_var.mul_(1.7)
+        blk.conv2.weight.mul_(0.6)
+        blk.bn2.bias.add_(0.05)
+        ref.img_enc.cnn.layer2[0].bn1.running_var.mul_(1.7)
+        ref.img_enc.cnn.layer2[0].conv2.weight.mul_(0.6)
+        ref.img_enc.cnn.layer2[0].bn2.bias.add_(0.05)
+        o2 = mine(images, None, {'input_ids': ids, 'attention_mask': mask}, None)
+        o2_ref = ref(images, ids, mask, torch.zeros_like(ids))
+    assert _rel(o2['image_features'], o2_ref['image_features']) < 1e-4
+    assert _rel(o2['image_features'], o['image_features']) > 1e-3
 
 
 def test_pcme_bf16_layout_rules(monkeypatch):

@@ -171,6 +171,41 @@ def test_image_tower_eval_and_deepcopy(env):
     assert old.store() is not mine.store()
 
 
+@pytest.mark.parametrize('arch', ['resnet18', 'resnet101'])
+def test_eval_fold_matches_unfolded_inference(env, arch, monkeypatch):
+    """Inference folds every block BatchNorm into its convolution (creamfl_bn_fold_layers + creamfl_conv2d_fprop_affine):
+    same features as the un-folded path (BatchNorm as its own pass) up to bf16 rounding of the folded filters
+    (cos >= 0.9995 per row), before and after a training step moved the masters and the running statistics."""
+    towers, RT = env
+    ref = RT.RefEncoderImage(arch, 256)
+    RT.fill_deterministic(ref, seed=13)
+    mine = towers.ImageModel({'embed_dim': 256, 'cnn_type': arch})
+    mine.img_enc.load_state_dict(ref.state_dict())
+    mine = mine.cuda()
+    images = torch.randn(8, 3, 224, 224, generator=torch.Generator().manual_seed(14)).cuda()
+
+    def both():
+        mine.eval()
+        with torch.no_grad():
+            monkeypatch.setattr(towers.ResNet, 'fold_eval_bn', True)
+            a = mine(images).clone()
+            monkeypatch.setattr(towers.ResNet, 'fold_eval_bn', False)
+            b = mine(images).clone()
+        monkeypatch.setattr(towers.ResNet, 'fold_eval_bn', True)
+        return a, b
+    a, b = both()
+    assert min(cos(a[i], b[i]) for i in range(8)) >= 0.9995
+    mine.train()
+    mine.store().zero_grad()
+    mine(images).square().sum().backward()                      # running statistics move
+    with torch.no_grad():
+        mine.store().flat.add_(-1e-3 * mine.store().grad.sign())     # masters move
+    mine.sync_shadow()
+    a2, b2 = both()
+    assert min(cos(a2[i], b2[i]) for i in range(8)) >= 0.9995
+    assert cos(a2, a) < 0.99999
+
+
 @pytest.mark.parametrize('batch,seq', [(8, 16), (4, 32)])
 def test_pcme_train_step(env, batch, seq):
     towers, RT = env
