@@ -208,9 +208,30 @@ def test_conw_vs_oracle(ops, O, n, d, c):
     assert rel_l2(agg_g, agg_o) < 1e-4
 
 
+def test_conw_full_size_d256_vs_oracle(ops, O):
+    """N = 50000 (the size the reference hard-codes, MMFL.py:302) at the embedding width of the benchmark, D = 256,
+    two clients, against the oracle on the same bf16-rounded operands (fp32 on the host: bf16 products are exact in
+    fp32, the 256-term sums and the 50000-term log-sum-exp carry ~1e-6): scores abs 3e-4, weights abs 2e-4,
+    aggregate rel-L2 2e-4."""
+    n, d, c = 50000, 256, 2
+    g_img, g_txt, i_vecs, _ = conw_inputs(77, n, d, c)
+    G = bf16_round(T(g_txt)).float()
+    vo = [bf16_round(T(v)).float() for v in i_vecs]
+    so = torch.stack([O.conw_scores(v, G) for v in vo]).double()
+    wo = torch.softmax(so, 0)
+    agg_o = sum(T(v).double() * wo[k][:, None] for k, v in enumerate(i_vecs))
+    vg = [T(v).cuda() for v in i_vecs]
+    gb = ops.to_bf16(T(g_txt).cuda())
+    sg = torch.stack([ops.conw_score(ops.to_bf16(v), gb) for v in vg])
+    agg_g, wg = ops.conw_reduce(vg, sg, want_weights=True)
+    assert (sg.cpu().double() - so).abs().max().item() < 3e-4
+    assert (wg.cpu().double() - wo).abs().max().item() < 2e-4
+    assert rel_l2(agg_g, agg_o) < 2e-4
+
+
 def test_conw_full_size_golden(ops, golden):
-    """N = 50000, D = 256, the size the reference hard-codes (MMFL.py:302): rows of the reference's own
-    aggregation() output.  bf16 operands vs the reference's fp32: weights shift by <= 2e-3, so the
+    """N = 50000 (the size the reference hard-codes, MMFL.py:302), D = 64, three clients (the golden's own n, d, c;
+    D = 256 is covered against the oracle above): rows of the reference's own aggregation() output.  bf16 operands vs the reference's fp32: weights shift by <= 2e-3, so the
     aggregated rows agree to abs 2e-4 (unit-norm rows, entries ~0.06)."""
     g = golden('conw')
     n, d, c = int(g['n']), int(g['d']), int(g['c'])

@@ -241,3 +241,69 @@ def test_text_tower_restatement_matches_reference_modules(golden):
     client.is_train = False
     with torch.no_grad():
         np.testing.assert_allclose(client(x, lengths).numpy(), g['uni_embedding'], rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------- AdamP pinning
+# The adamp==0.3.0 package is absent (reference requirements.txt:1), so `adamp_step` cannot be pinned against it as a
+# whole.  What can be pinned: (1) without a projection AdamP IS Adam - checked against torch.optim.Adam in fp64;
+# (2) the projection branch against a known-answer case worked out by hand from Algorithm 1 of the paper
+# (Heo et al., ICLR 2021): cosine test `max_rows |<g, w>| / (|g| |w|) < delta / sqrt(dim)`, projected update
+# `u - w_hat <w_hat, u>`, weight-decay ratio wd_ratio.
+def test_adamp_without_projection_is_torch_adam():
+    from oracle import creamfl_oracle as O
+    g = torch.Generator().manual_seed(3)
+    shapes = [(7,), (5, 3), (4, 2, 3, 3)]
+    ps = [torch.randn(s, generator=g, dtype=torch.float64) for s in shapes]
+    ref = [torch.nn.Parameter(p.clone()) for p in ps]
+    adam = torch.optim.Adam(ref, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, foreach=False)
+    ms, vs = [torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps]
+    for step in range(1, 6):
+        # gradients with a large component along the weights: the cosine test never fires
+        grads = [0.5 * p + 0.3 * torch.randn(p.shape, generator=g, dtype=torch.float64) for p in ps]
+        for r, gr in zip(ref, grads):
+            r.grad = gr.clone()
+        adam.step()
+        fired = O.adamp_step(ps, grads, ms, vs, step, 2e-4)
+        assert fired == [0, 0, 0]
+        for p, r in zip(ps, ref):
+            # same arithmetic up to the association of (m / denom) * step_size: a few fp64 ulps
+            assert float((p - r.detach()).abs().max()) <= 4 * torch.finfo(torch.float64).eps * float(p.abs().max())
+
+
+def test_adamp_projection_known_answer():
+    from oracle import creamfl_oracle as O
+    lr, wd, eps, delta, wd_ratio = 0.01, 0.5, 1e-8, 0.1, 0.1
+    w = torch.tensor([[1.0, 0.0], [0.0, 2.0]], dtype=torch.float64)
+    g = torch.tensor([[0.05, 1.0], [-3.0, 0.1]], dtype=torch.float64)
+    # row cosines: 0.05 / sqrt(1.0025) = 0.04994 and 0.2 / (2 * sqrt(9.01)) = 0.03331, both < delta / sqrt(2) = 0.0707
+    m, v = torch.zeros_like(w), torch.zeros_like(w)
+    p = w.clone()
+    fired = O.adamp_step([p], [g], [m], [v], 1, lr, (0.9, 0.999), eps, wd, delta, wd_ratio)
+    assert fired == [1]                                    # the channel-wise test fires first
+    # step 1 by hand: m = 0.1 g, v = 0.001 g^2, denom = |g| + eps, lr / bias_correction1 = lr / 0.1, so the Adam
+    # direction is u = g / (|g| + eps) element-wise (scaled by 0.1, undone by the bias correction)
+    exp = torch.empty_like(w)
+    for r in range(2):
+        u = [g[r, c].item() / (abs(g[r, c].item()) + eps) for c in range(2)]
+        norm = (w[r, 0].item() ** 2 + w[r, 1].item() ** 2) ** 0.5 + eps
+        wh = [w[r, c].item() / norm for c in range(2)]
+        dot = wh[0] * u[0] + wh[1] * u[1]
+        for c in range(2):
+            exp[r, c] = w[r, c].item() * (1 - lr * wd * wd_ratio) - lr * (u[c] - wh[c] * dot)
+    assert float((p - exp).abs().max()) < 1e-15
+    # the radial component of the update is gone (that is the point of AdamP): <w_hat, p_new - w (1 - lr wd ratio)> = 0
+    upd = p - w * (1 - lr * wd * wd_ratio)
+    assert float((upd * w).sum(1).abs().max()) < 1e-9
+    # row 0 one notch above the channel threshold (cosine 0.0797 > 0.0707): the channel test fails, the layer-wise test
+    # |<g, w>| / (|g| |w|) = 0.28 / (3.1649 * 2.2361) = 0.0396 < delta / sqrt(4) = 0.05 fires instead
+    g2 = torch.tensor([[0.08, 1.0], [-3.0, 0.1]], dtype=torch.float64)
+    p2, m2, v2 = w.clone(), torch.zeros_like(w), torch.zeros_like(w)
+    assert O.adamp_step([p2], [g2], [m2], [v2], 1, lr, (0.9, 0.999), eps, wd, delta, wd_ratio) == [2]
+    upd2 = p2 - w * (1 - lr * wd * wd_ratio)
+    assert abs(float((upd2 * w).sum())) < 1e-9                    # radial component w.r.t. the whole tensor removed
+    # well above both thresholds nothing fires: plain Adam step with the full weight decay
+    g3 = torch.tensor([[1.0, 1.0], [-3.0, 2.0]], dtype=torch.float64)
+    p3, m3, v3 = w.clone(), torch.zeros_like(w), torch.zeros_like(w)
+    assert O.adamp_step([p3], [g3], [m3], [v3], 1, lr, (0.9, 0.999), eps, wd, delta, wd_ratio) == [0]
+    exp3 = w * (1 - lr * wd) - lr * g3 / (g3.abs() + eps)
+    assert float((p3 - exp3).abs().max()) < 1e-15
