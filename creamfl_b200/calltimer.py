@@ -46,10 +46,10 @@ def _conv_cost(name, args):
 
 
 def _bn_cost(name, args):
-    if name == 'creamfl_bn_train_fwd' or name == 'creamfl_bn_eval_fwd':
+    if name in ('creamfl_bn_train_fwd', 'creamfl_bn_eval_fwd', 'creamfl_bn_train_fwd_mask'):
         p, c = int(args[1]), int(args[2])
         return 'bn_fwd', 0.0, 2.0 * p * c * 2, f'{p}x{c}'
-    p, c = int(args[3]), int(args[4])                # bn_train_bwd(dy, y, x, p, c, ...)
+    p, c = int(args[3]), int(args[4])                # bn_train_bwd[_mask](dy, y | mask, x, p, c, ...)
     return 'bn_bwd', 0.0, 2.0 * p * c * 3, f'{p}x{c}'
 
 
@@ -71,7 +71,8 @@ def classify(name: str, args) -> Tuple[str, float, float, str]:
         return _gemm_cost(args)
     if name.startswith('creamfl_conv2d_') and not name.endswith('bytes'):
         return _conv_cost(name, args)
-    if name in ('creamfl_bn_train_fwd', 'creamfl_bn_eval_fwd', 'creamfl_bn_train_bwd'):
+    if name in ('creamfl_bn_train_fwd', 'creamfl_bn_eval_fwd', 'creamfl_bn_train_bwd', 'creamfl_bn_train_fwd_mask',
+                'creamfl_bn_train_bwd_mask'):
         return _bn_cost(name, args)
     return _FAMILY.get(name, 'other'), 0.0, 0.0, ''
 

@@ -214,6 +214,29 @@ int creamfl_bn_train_fwd(const void* x, int64_t P, int C, const float* gamma, co
                       res, relu, stats_ready, reinterpret_cast<long long*>(num_batches_tracked), y, S(stream));
 }
 
+int creamfl_bn_train_fwd_mask(const void* x, int64_t P, int C, const float* gamma, const float* beta, float eps,
+                              float momentum, float* running_mean, float* running_var, double* sums, float* mean,
+                              float* rstd, float* scale, float* shift, const void* res, int relu, int stats_ready,
+                              int64_t* num_batches_tracked, void* y, void* relu_mask, void* stream) {
+  if (!x || !gamma || !beta || !sums || !mean || !rstd || !scale || !shift || !y || !relu_mask) {
+    set_error("bn_train_fwd_mask: null pointer");
+    return CFL_EINVAL;
+  }
+  return bn_train_fwd(x, P, C, gamma, beta, eps, momentum, running_mean, running_var, sums, mean, rstd, scale, shift,
+                      res, relu, stats_ready, reinterpret_cast<long long*>(num_batches_tracked), y, S(stream), relu_mask);
+}
+
+int creamfl_bn_train_bwd_mask(const void* dy, const void* relu_mask, const void* x, int64_t P, int C, const float* gamma,
+                              const float* mean, const float* rstd, double* sums, float* coef, float* dgamma,
+                              float* dbeta, void* dx, void* g_out, void* stream) {
+  if (!dy || !relu_mask || !x || !gamma || !mean || !rstd || !sums || !coef || !dx) {
+    set_error("bn_train_bwd_mask: null pointer");
+    return CFL_EINVAL;
+  }
+  return bn_train_bwd(dy, nullptr, x, P, C, gamma, nullptr, 0, mean, rstd, sums, coef, dgamma, dbeta, dx, g_out,
+                      S(stream), relu_mask);
+}
+
 int creamfl_bn_stats(const void* x, int64_t P, int C, double* sums, void* stream) {
   if (!x || !sums) {
     set_error("bn_stats: null pointer");

@@ -72,13 +72,15 @@ int stem_fprop(const float* x, const void* wt, long long ldw, int N, int H, int 
 int stem_wgrad(const float* x, const void* dy, int N, int H, int W, float* dw, cudaStream_t stream);
 // nn_ops.cu
 int bn_train_fwd(const void*, long long, int, const float*, const float*, float, float, float*, float*, double*,
-                 float*, float*, float*, float*, const void*, int, int, long long*, void*, cudaStream_t);
+                 float*, float*, float*, float*, const void*, int, int, long long*, void*, cudaStream_t,
+                 void* relu_mask = nullptr);
 int bn_stats_only(const void*, long long, int, double*, cudaStream_t);
 int bn_fold_layers(const long long*, const long long*, int, long long, float, cudaStream_t);
 int bn_eval_fwd(const void*, long long, int, const float*, const float*, float, const float*, const float*, float*,
                 float*, const void*, int, void*, cudaStream_t);
 int bn_train_bwd(const void*, const void*, const void*, long long, int, const float*, const float*, int, const float*,
-                 const float*, double*, float*, float*, float*, void*, void*, cudaStream_t);
+                 const float*, double*, float*, float*, float*, void*, void*, cudaStream_t,
+                 const void* relu_mask = nullptr);
 int maxpool_fwd(const void*, int, int, int, int, void*, void*, cudaStream_t);
 int maxpool_bwd(const void*, const void*, int, int, int, int, void*, cudaStream_t);
 int im2col_nhwc(const void*, int, int, int, int, int, int, int, int, int, void*, cudaStream_t);

@@ -148,10 +148,11 @@ __device__ __forceinline__ void load_coef8(const float* __restrict__ a, int c0, 
   o[0] = lo.x; o[1] = lo.y; o[2] = lo.z; o[3] = lo.w; o[4] = hi.x; o[5] = hi.y; o[6] = hi.z; o[7] = hi.w;
 }
 
-__global__ void __launch_bounds__(kEwThreads)
+template <bool MASK>       // MASK: also emit the ReLU gate bits (separate instantiation: keeps the plain kernel's registers)
+__global__ void __launch_bounds__(kEwThreads, MASK ? 2 : 3)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                 const __nv_bfloat16* __restrict__ res, int relu, long long total8, int C,
-                __nv_bfloat16* __restrict__ y) {
+                __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ mask /* optional: bit i of byte t = (y[8t+i] > 0) */) {
   const long long stride = (long long)gridDim.x * kEwThreads;
   const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
   float sc[8], sf[8];
@@ -181,6 +182,12 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] += r[i];
       }
+      if (MASK) {      // the ReLU gate of the backward pass, 1 bit per element instead of re-reading y (16x smaller)
+        unsigned m = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m |= (f[i] > 0.0f ? 1u : 0u) << i;
+        mask[t] = (uint8_t)m;
+      }
       if (relu) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
@@ -191,8 +198,10 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s
 }
 
 // sums[0..C) += sum_p g ; sums[C..2C) += sum_p g * xhat    with g = dy * (y > 0 if relu)
-__global__ void __launch_bounds__(kBnThreads)
+template <bool MASK>
+__global__ void __launch_bounds__(kBnThreads, 2)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y /* null: no relu */,
+                     const uint8_t* __restrict__ mask /* alternative to y: gate bits written by the forward pass */,
                      const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                      int relu_from_x, long long P, int C, double* __restrict__ sums) {
@@ -215,13 +224,15 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     const long long stride = (long long)gridDim.x * rows;
     for (long long p = (long long)blockIdx.x * rows + r; p < P; p += 4 * stride) {
       bf16x8 rd[4], rx[4], ry[4];
+      unsigned mk[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {        // 8-12 independent 16-byte loads in flight per thread
         if (p + u * stride < P) {
           const long long o = (p + u * stride) * C + g * 8;
           rd[u] = *reinterpret_cast<const bf16x8*>(dy + o);
           rx[u] = *reinterpret_cast<const bf16x8*>(x + o);
-          if (y) ry[u] = *reinterpret_cast<const bf16x8*>(y + o);
+          if (!MASK && y) ry[u] = *reinterpret_cast<const bf16x8*>(y + o);
+          if (MASK) mk[u] = mask[o >> 3];
         }
       }
 #pragma unroll
@@ -230,7 +241,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
           float d[8], xv[8];
           unpack8(rd[u], d);
           unpack8(rx[u], xv);
-          if (y) {
+          if (MASK) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = ((mk[u] >> i) & 1u) ? d[i] : 0.0f;
+          } else if (y) {
             float yv[8];
             unpack8(ry[u], yv);
 #pragma unroll
@@ -290,9 +304,10 @@ __global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, long long P, i
 
 // dx = a*g + b*x + c0 ; optionally g itself is written out (gradient of the residual branch)
 constexpr int kBwdVec = 4;
-__global__ void __launch_bounds__(kEwThreads)
+template <bool MASK>
+__global__ void __launch_bounds__(kEwThreads, 2)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
-                    const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef,
+                    const uint8_t* __restrict__ mask, const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef,
                     const float* __restrict__ gate /* [2, C] affine of the ReLU gate, or null */, long long total8, int C,
                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ g_out) {
   const long long stride = (long long)gridDim.x * kEwThreads;
@@ -308,13 +323,15 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
   }
   for (long long t0 = first; t0 < total8; t0 += kBwdVec * stride) {
     bf16x8 rd[kBwdVec], rx[kBwdVec], ry[kBwdVec];
+    unsigned mk[kBwdVec];
 #pragma unroll
     for (int u = 0; u < kBwdVec; ++u) {
       const long long t = t0 + u * stride;
       if (t < total8) {
         rd[u] = reinterpret_cast<const bf16x8*>(dy)[t];
         rx[u] = reinterpret_cast<const bf16x8*>(x)[t];
-        if (y) ry[u] = reinterpret_cast<const bf16x8*>(y)[t];
+        if (!MASK && y) ry[u] = reinterpret_cast<const bf16x8*>(y)[t];
+        if (MASK) mk[u] = mask[t];
       }
     }
 #pragma unroll
@@ -324,7 +341,10 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
       float d[8], xv[8];
       unpack8(rd[u], d);
       unpack8(rx[u], xv);
-      if (y) {
+      if (MASK) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = ((mk[u] >> i) & 1u) ? d[i] : 0.0f;
+      } else if (y) {
         float yv[8];
         unpack8(ry[u], yv);
 #pragma unroll
@@ -386,16 +406,21 @@ int bn_stats_only(const void* x, long long P, int C, double* sums, cudaStream_t 
 int bn_train_fwd(const void* x, long long P, int C, const float* gamma, const float* beta, float eps, float momentum,
                  float* running_mean, float* running_var, double* sums, float* mean, float* rstd, float* scale,
                  float* shift, const void* res, int relu, int stats_ready, long long* num_batches_tracked, void* y,
-                 cudaStream_t st) {
+                 cudaStream_t st, void* relu_mask) {
   int rc = bn_check("bn_train_fwd", P, C);
   if (rc) return rc;
   if (!stats_ready && (rc = bn_stats_only(x, P, C, sums, st))) return rc;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, beta, eps, momentum, running_mean,
                                                        running_var, mean, rstd, scale, shift, num_batches_tracked);
   const long long total8 = P * C / 8;
-  bn_apply_kernel<<<ew_grid(total8, kEwVec), kEwThreads, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(res), relu,
-      total8, C, reinterpret_cast<__nv_bfloat16*>(y));
+  if (relu_mask)
+    bn_apply_kernel<true><<<ew_grid(total8, kEwVec), kEwThreads, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(res), relu,
+        total8, C, reinterpret_cast<__nv_bfloat16*>(y), reinterpret_cast<uint8_t*>(relu_mask));
+  else
+    bn_apply_kernel<false><<<ew_grid(total8, kEwVec), kEwThreads, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(res), relu,
+        total8, C, reinterpret_cast<__nv_bfloat16*>(y), nullptr);
   return check_launch("bn_train_fwd");
 }
 
@@ -406,28 +431,32 @@ int bn_eval_fwd(const void* x, long long P, int C, const float* gamma, const flo
   if (rc) return rc;
   bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, eps, running_mean, running_var, scale, shift);
   const long long total8 = P * C / 8;
-  bn_apply_kernel<<<ew_grid(total8, kEwVec), kEwThreads, 0, st>>>(
+  bn_apply_kernel<false><<<ew_grid(total8, kEwVec), kEwThreads, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(res), relu,
-      total8, C, reinterpret_cast<__nv_bfloat16*>(y));
+      total8, C, reinterpret_cast<__nv_bfloat16*>(y), nullptr);
   return check_launch("bn_eval_fwd");
 }
 
 int bn_train_bwd(const void* dy, const void* y_or_null, const void* x, long long P, int C, const float* gamma,
                  const float* beta, int relu_from_x, const float* mean, const float* rstd, double* sums, float* coef,
-                 float* dgamma, float* dbeta, void* dx, void* g_out, cudaStream_t st) {
+                 float* dgamma, float* dbeta, void* dx, void* g_out, cudaStream_t st, const void* relu_mask) {
   int rc = bn_check("bn_train_bwd", P, C);
   if (rc) return rc;
-  const int gate_from_x = (relu_from_x && y_or_null == nullptr && beta != nullptr) ? 1 : 0;
+  const uint8_t* mask = reinterpret_cast<const uint8_t*>(relu_mask);
+  if (mask) y_or_null = nullptr;
+  const int gate_from_x = (relu_from_x && y_or_null == nullptr && mask == nullptr && beta != nullptr) ? 1 : 0;
   const int rows = kBnThreads / (C >> 3);
   const size_t smem = (size_t)(rows > 0 ? rows : 1) * 2 * C * sizeof(float);
-  bn_bwd_reduce_kernel<<<bn_reduce_grid(P, C), kBnThreads, smem, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_or_null),
+  auto reduce = mask ? bn_bwd_reduce_kernel<true> : bn_bwd_reduce_kernel<false>;
+  auto apply = mask ? bn_bwd_apply_kernel<true> : bn_bwd_apply_kernel<false>;
+  reduce<<<bn_reduce_grid(P, C), kBnThreads, smem, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_or_null), mask,
       reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, gamma, beta, gate_from_x, P, C, sums);
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, mean, rstd, gate_from_x ? beta : nullptr,
                                                           dgamma, dbeta, coef);
   const long long total8 = P * C / 8;
-  bn_bwd_apply_kernel<<<ew_grid(total8, kBwdVec), kEwThreads, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_or_null),
+  apply<<<ew_grid(total8, kBwdVec), kEwThreads, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_or_null), mask,
       reinterpret_cast<const __nv_bfloat16*>(x), coef, gate_from_x ? coef + 3 * C : nullptr, total8, C,
       reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(g_out));
   return check_launch("bn_train_bwd");

@@ -206,16 +206,26 @@ class BNScratch:
 
 
 def bn_train_fwd(x, gamma, beta, running_mean, running_var, sc: BNScratch, eps, momentum, res=None, relu=True,
-                 stats_ready=False, num_batches_tracked=None):
+                 stats_ready=False, num_batches_tracked=None, want_mask=False):
+    """Returns (y, mean, rstd) or, with want_mask, (y, mean, rstd, mask): mask = uint8 [P*C/8], bit i of byte t =
+    (y[8t + i] > 0) - the ReLU gate for bn_train_bwd when a residual was added before the ReLU."""
     c = x.shape[-1]
     p = x.numel() // c
     mean = torch.empty(c, dtype=torch.float32, device=x.device)
     rstd = torch.empty(c, dtype=torch.float32, device=x.device)
     y = torch.empty_like(x)
-    _chk(_lib.load().creamfl_bn_train_fwd(_p(x), p, c, _p(gamma), _p(beta), eps, momentum, _p(running_mean),
-                                          _p(running_var), _p(sc.sums), _p(mean), _p(rstd), _p(sc.scale), _p(sc.shift),
-                                          _p(res), int(relu), int(stats_ready), _p(num_batches_tracked), _p(y),
-                                          _stream()), "bn_train_fwd",
+    lib = _lib.load()
+    if want_mask:
+        mask = torch.empty(p * c // 8, dtype=torch.uint8, device=x.device)
+        _chk(lib.creamfl_bn_train_fwd_mask(_p(x), p, c, _p(gamma), _p(beta), eps, momentum, _p(running_mean),
+                                           _p(running_var), _p(sc.sums), _p(mean), _p(rstd), _p(sc.scale), _p(sc.shift),
+                                           _p(res), int(relu), int(stats_ready), _p(num_batches_tracked), _p(y), _p(mask),
+                                           _stream()), "bn_train_fwd_mask", 2 if stats_ready else 3)
+        return y, mean, rstd, mask
+    _chk(lib.creamfl_bn_train_fwd(_p(x), p, c, _p(gamma), _p(beta), eps, momentum, _p(running_mean),
+                                  _p(running_var), _p(sc.sums), _p(mean), _p(rstd), _p(sc.scale), _p(sc.shift),
+                                  _p(res), int(relu), int(stats_ready), _p(num_batches_tracked), _p(y),
+                                  _stream()), "bn_train_fwd",
          2 if stats_ready else 3)
     return y, mean, rstd
 
@@ -231,16 +241,23 @@ def bn_eval_fwd(x, gamma, beta, running_mean, running_var, sc: BNScratch, eps, r
 
 
 def bn_train_bwd(dy, y_mask, x, gamma, mean, rstd, sc: BNScratch, dgamma, dbeta, want_g=False, beta=None,
-                 relu_from_x=False):
-    """Returns (dx, g) where g = dy * gate (only if want_g).  gate = (y_mask > 0) if y_mask is given; recomputed from
-    x (no residual, ReLU applied) if relu_from_x and beta are given; 1 otherwise."""
+                 relu_from_x=False, mask=None):
+    """Returns (dx, g) where g = dy * gate (only if want_g).  gate = the bits of `mask` (from bn_train_fwd(want_mask))
+    if given; (y_mask > 0) if y_mask is given; recomputed from x (no residual, ReLU applied) if relu_from_x and beta
+    are given; 1 otherwise."""
     c = x.shape[-1]
     p = x.numel() // c
     dx = torch.empty_like(x)
     g = torch.empty_like(x) if want_g else None
-    _chk(_lib.load().creamfl_bn_train_bwd(_p(dy), _p(y_mask), _p(x), p, c, _p(gamma), _p(beta), int(relu_from_x),
-                                          _p(mean), _p(rstd), _p(sc.sums), _p(sc.coef), _p(dgamma), _p(dbeta), _p(dx),
-                                          _p(g), _stream()),
+    lib = _lib.load()
+    if mask is not None:
+        _chk(lib.creamfl_bn_train_bwd_mask(_p(dy), _p(mask), _p(x), p, c, _p(gamma), _p(mean), _p(rstd), _p(sc.sums),
+                                           _p(sc.coef), _p(dgamma), _p(dbeta), _p(dx), _p(g), _stream()),
+             "bn_train_bwd_mask", 3)
+        return dx, g
+    _chk(lib.creamfl_bn_train_bwd(_p(dy), _p(y_mask), _p(x), p, c, _p(gamma), _p(beta), int(relu_from_x),
+                                  _p(mean), _p(rstd), _p(sc.sums), _p(sc.coef), _p(dgamma), _p(dbeta), _p(dx),
+                                  _p(g), _stream()),
          "bn_train_bwd", 3)
     return dx, g
 

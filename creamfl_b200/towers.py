@@ -273,25 +273,31 @@ class BN(nn.Module):
             new.__dict__[k] = None if k == '_scratch' else copy.deepcopy(v, memo)
         return new
 
-    def fwd(self, x, res=None, relu=True, stats_ready=False):
-        """Returns (y, saved) - saved is (mean, rstd) in training mode, None in eval mode.  stats_ready: the
-        producing convolution already accumulated the batch statistics into scratch().sums."""
+    def fwd(self, x, res=None, relu=True, stats_ready=False, keep_gate=False):
+        """Returns (y, saved) - saved is (mean, rstd, gate bits or None) in training mode, None in eval mode.
+        stats_ready: the producing convolution already accumulated the batch statistics into scratch().sums.
+        keep_gate (residual before the ReLU, backward pass will follow): the ReLU gate is kept as one bit per element
+        (1/16 of y) for bwd()."""
         if self.training:
-            y, mean, rstd = T.bn_train_fwd(x, self.weight, self.bias, self.running_mean, self.running_var,
-                                           self.scratch(), self.eps, self.momentum, res=res, relu=relu,
-                                           stats_ready=stats_ready, num_batches_tracked=self.num_batches_tracked)
-            return y, (mean, rstd)
+            want_mask = keep_gate and res is not None and relu
+            out = T.bn_train_fwd(x, self.weight, self.bias, self.running_mean, self.running_var,
+                                 self.scratch(), self.eps, self.momentum, res=res, relu=relu,
+                                 stats_ready=stats_ready, num_batches_tracked=self.num_batches_tracked,
+                                 want_mask=want_mask)
+            return out[0], (out[1], out[2], out[3] if want_mask else None)
         return T.bn_eval_fwd(x, self.weight, self.bias, self.running_mean, self.running_var, self.scratch(), self.eps,
                              res=res, relu=relu), None
 
     def bwd(self, dy, y_mask, x, saved, want_g=False, relu_from_x=False):
-        """`y_mask`: the forward output when a residual was added before the ReLU; `relu_from_x`: ReLU without
-        residual - the gate is recomputed from x inside the kernels and the output is not read."""
+        """`y_mask`: the forward output when a residual was added before the ReLU (read only if the forward pass kept
+        no gate bits); `relu_from_x`: ReLU without residual - the gate is recomputed from x inside the kernels and the
+        output is not read."""
         if saved is None:
             raise RuntimeError('BatchNorm backward needs a training-mode forward (batch statistics)')
-        mean, rstd = saved
-        return T.bn_train_bwd(dy, y_mask, x, self.weight, mean, rstd, self.scratch(), grad_target(self.weight),
-                              grad_target(self.bias), want_g=want_g, beta=self.bias, relu_from_x=relu_from_x)
+        mean, rstd, mask = saved
+        return T.bn_train_bwd(dy, None if mask is not None else y_mask, x, self.weight, mean, rstd, self.scratch(),
+                              grad_target(self.weight), grad_target(self.bias), want_g=want_g, beta=self.bias,
+                              relu_from_x=relu_from_x, mask=mask)
 
 
 def _conv_f(c: Conv, x, bn: 'BN' = None):
@@ -334,7 +340,7 @@ class Bottleneck(nn.Module):
             idn, sd = self.downsample[1].fwd(od, relu=False, stats_ready=True)
         else:
             od, idn, sd = None, x, None
-        y, s3 = self.bn3.fwd(o3, res=idn, relu=True, stats_ready=True)
+        y, s3 = self.bn3.fwd(o3, res=idn, relu=True, stats_ready=True, keep_gate=save)
         if save:
             return y, (x, o1, a1, s1, o2, a2, s2, o3, s3, od, sd, y)
         return y, None
@@ -384,7 +390,7 @@ class BasicBlock(nn.Module):
             idn, sd = self.downsample[1].fwd(od, relu=False, stats_ready=True)
         else:
             od, idn, sd = None, x, None
-        y, s2 = self.bn2.fwd(o2, res=idn, relu=True, stats_ready=True)
+        y, s2 = self.bn2.fwd(o2, res=idn, relu=True, stats_ready=True, keep_gate=save)
         if save:
             return y, (x, o1, a1, s1, o2, s2, od, sd, y)
         return y, None

@@ -197,6 +197,18 @@ int creamfl_bn_train_bwd(const void* dy_bf16, const void* y_bf16, const void* x_
                          double* sums, float* coef, float* dgamma, float* dbeta, void* dx_bf16, void* g_out_bf16,
                          void* stream);
 
+/* Same pair with the ReLU gate handed from the forward to the backward pass as one bit per element instead of the
+ * output tensor (needed when a residual was added before the ReLU: the gate is not a function of x alone):
+ * relu_mask is P*C/8 bytes, bit i of byte t = (y[8t + i] > 0).  The backward pass then reads dy, x and the mask
+ * (1/16 of y), which also lets the second read of a 14x14 layer's operands hit L2. */
+int creamfl_bn_train_fwd_mask(const void* x_bf16, int64_t P, int C, const float* gamma, const float* beta, float eps,
+                              float momentum, float* running_mean, float* running_var, double* sums, float* mean,
+                              float* rstd, float* scale, float* shift, const void* res_bf16, int relu, int stats_ready,
+                              int64_t* num_batches_tracked, void* y_bf16, void* relu_mask, void* stream);
+int creamfl_bn_train_bwd_mask(const void* dy_bf16, const void* relu_mask, const void* x_bf16, int64_t P, int C,
+                              const float* gamma, const float* mean, const float* rstd, double* sums, float* coef,
+                              float* dgamma, float* dbeta, void* dx_bf16, void* g_out_bf16, void* stream);
+
 /* ---- 3x3 / stride 2 / pad 1 max pooling (ResNet stem); idx: one byte per output element */
 int creamfl_maxpool_fwd(const void* x_bf16, int N, int H, int W, int C, void* y_bf16, void* idx_u8, void* stream);
 int creamfl_maxpool_bwd(const void* dy_bf16, const void* idx_u8, int N, int H, int W, int C, void* dx_bf16,

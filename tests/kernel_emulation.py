@@ -377,7 +377,7 @@ def stem_wgrad(images, dy, dw):
 
 
 def bn_train_fwd(x, gamma, beta, running_mean, running_var, sc, eps, momentum, res=None, relu=True, stats_ready=False,
-                 num_batches_tracked=None):
+                 num_batches_tracked=None, want_mask=False):
     c = x.shape[-1]
     x2 = x.double().reshape(-1, c)
     p = x2.shape[0]
@@ -397,9 +397,12 @@ def bn_train_fwd(x, gamma, beta, running_mean, running_var, sc, eps, momentum, r
     y = x.float() * scale + (beta - mean * scale)
     if res is not None:
         y = y + res.float()
+    if want_mask:                                # gate bits of the pre-ReLU value, 8 channels per byte, LSB first
+        bits = (y > 0).reshape(-1, 8).to(torch.uint8)
+        mask = (bits << torch.arange(8, dtype=torch.uint8)).sum(1).to(torch.uint8)
     if relu:
         y = torch.relu(y)
-    return y.to(BF16), mean, rstd
+    return (y.to(BF16), mean, rstd, mask) if want_mask else (y.to(BF16), mean, rstd)
 
 
 def bn_eval_fwd(x, gamma, beta, running_mean, running_var, sc, eps, res=None, relu=True):
@@ -435,11 +438,15 @@ def conv_fprop_affine(x, w2d, r, s_, stride, pad, bias, add=None, relu=True):
     return y.to(BF16)
 
 
-def bn_train_bwd(dy, y_mask, x, gamma, mean, rstd, sc, dgamma, dbeta, want_g=False, beta=None, relu_from_x=False):
+def bn_train_bwd(dy, y_mask, x, gamma, mean, rstd, sc, dgamma, dbeta, want_g=False, beta=None, relu_from_x=False,
+                 mask=None):
     c = x.shape[-1]
     xhat = (x.float() - mean) * rstd
     g = dy.float()
-    if y_mask is not None:
+    if mask is not None:
+        gate = ((mask[:, None] >> torch.arange(8, dtype=torch.uint8)) & 1).reshape(x.shape)
+        g = g * gate
+    elif y_mask is not None:
         g = g * (y_mask.float() > 0)
     elif relu_from_x and beta is not None:
         g = g * ((gamma * xhat + beta) > 0)

@@ -145,6 +145,19 @@ def test_batchnorm_train(T, shape, relu, with_res):
     assert rel_l2(dg - 0.25, g64.grad) < 1e-3 and rel_l2(db - 0.25, b64.grad) < 1e-3
     assert rel_l2(gout, dy.double() * (mask.permute(0, 2, 3, 1) if relu else 1.0)) < 1e-6
     assert torch.count_nonzero(sc.sums) == 0
+    if relu and with_res:
+        # gate handed over as one bit per element (creamfl_bn_train_fwd_mask / _bwd_mask): same forward output, the bits
+        # equal (y > 0) except where the fp32 pre-activation is positive but rounds to a bf16 zero, same backward
+        rm2, rv2 = rm.cuda(), rv.cuda()
+        y2, mean2, rstd2, bits = T.bn_train_fwd(x.cuda(), gamma.cuda(), beta.cuda(), rm2, rv2, sc, 1e-5, 0.1,
+                                                res=res.cuda(), relu=True, want_mask=True)
+        assert torch.equal(y2, y) and torch.equal(mean2, mean)
+        unpacked = ((bits[:, None] >> torch.arange(8, dtype=torch.uint8, device='cuda')) & 1).reshape(y.shape).bool()
+        assert (unpacked != (y > 0)).float().mean().item() < 1e-5
+        dg3, db3 = torch.full((c,), 0.25, device='cuda'), torch.full((c,), 0.25, device='cuda')
+        dx3, g3 = T.bn_train_bwd(dy.cuda(), None, x.cuda(), gamma.cuda(), mean, rstd, sc, dg3, db3, want_g=True, mask=bits)
+        assert rel_l2(dx3, dx) < 1e-4 and rel_l2(g3, gout) < 1e-4 and rel_l2(dg3, dg) < 1e-4 and rel_l2(db3, db) < 1e-4
+        assert torch.count_nonzero(sc.sums) == 0
 
 
 def test_batchnorm_eval(T):
