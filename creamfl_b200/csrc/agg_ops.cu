@@ -16,38 +16,55 @@ struct ClientPtrs {
 };
 
 // One thread handles 4 consecutive features of one public row: 16-byte loads of every client's row, weights
-// recomputed per thread from the [C, N] score matrix (C <= 32 scalars, L1/L2 resident).
+// recomputed per thread from the [C, N] score matrix (C <= 32 scalars, L1/L2 resident).  CT > 0: client count known at
+// compile time (1..8, the configurations of the reference) - weights and the C row vectors live in registers and all
+// C 16-byte loads are in flight before the first FMA; CT == 0: any C <= 32 (weights in local memory).
+template <int CT>
 __global__ void __launch_bounds__(256)
-conw_reduce_kernel(ClientPtrs vecs, const float* __restrict__ scores /* [C, N] */, int C, int N, int D,
+conw_reduce_kernel(ClientPtrs vecs, const float* __restrict__ scores /* [C, N] */, int C_rt, int N, int D,
                    float* __restrict__ out /* [N, D] */, float* __restrict__ weights /* [C, N] or null */) {
+  const int C = CT > 0 ? CT : C_rt;
   const int d4 = D >> 2;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)N * d4) return;
   const int n = (int)(t / d4), k4 = (int)(t % d4);
-  float w[kMaxClients];
+  constexpr int W = CT > 0 ? CT : kMaxClients;
+  float w[W];
+  float4 v[CT > 0 ? CT : 1];
+  if (CT > 0) {
+#pragma unroll
+    for (int c = 0; c < CT; ++c) v[c] = __ldg(reinterpret_cast<const float4*>(vecs.v[c] + (long long)n * D) + k4);
+  }
   float mx = -INFINITY;
-#pragma unroll 4
-  for (int c = 0; c < C; ++c) {
-    w[c] = scores[(long long)c * N + n];
-    mx = fmaxf(mx, w[c]);
+#pragma unroll
+  for (int c = 0; c < W; ++c) {
+    if (c < C) {
+      w[c] = __ldg(scores + (long long)c * N + n);
+      mx = fmaxf(mx, w[c]);
+    }
   }
   float den = 0.0f;
-#pragma unroll 4
-  for (int c = 0; c < C; ++c) {
-    w[c] = __expf(w[c] - mx);
-    den += w[c];
+#pragma unroll
+  for (int c = 0; c < W; ++c) {
+    if (c < C) {
+      w[c] = __expf(w[c] - mx);
+      den += w[c];
+    }
   }
   const float inv = 1.0f / den;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-  for (int c = 0; c < C; ++c) {
-    const float wc = w[c] * inv;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(vecs.v[c] + (long long)n * D) + k4);
-    acc.x = fmaf(wc, v.x, acc.x);
-    acc.y = fmaf(wc, v.y, acc.y);
-    acc.z = fmaf(wc, v.z, acc.z);
-    acc.w = fmaf(wc, v.w, acc.w);
-    if (weights != nullptr && k4 == 0) weights[(long long)c * N + n] = wc;
+#pragma unroll
+  for (int c = 0; c < W; ++c) {
+    if (c < C) {
+      const float wc = w[c] * inv;
+      const float4 x = CT > 0 ? v[CT > 0 ? c : 0]
+                              : __ldg(reinterpret_cast<const float4*>(vecs.v[c] + (long long)n * D) + k4);
+      acc.x = fmaf(wc, x.x, acc.x);
+      acc.y = fmaf(wc, x.y, acc.y);
+      acc.z = fmaf(wc, x.z, acc.z);
+      acc.w = fmaf(wc, x.w, acc.w);
+      if (weights != nullptr && k4 == 0) weights[(long long)c * N + n] = wc;
+    }
   }
   reinterpret_cast<float4*>(out + (long long)n * D)[k4] = acc;
 }
@@ -71,7 +88,13 @@ int conw_reduce(const float* const* vecs_host, const float* scores, int C, int N
     p.v[c] = vecs_host[c];
   }
   const long long threads = (long long)N * (D >> 2);
-  conw_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p, scores, C, N, D, out, weights);
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  switch (C) {
+#define CFL_CONW(K) case K: conw_reduce_kernel<K><<<grid, 256, 0, st>>>(p, scores, C, N, D, out, weights); break;
+    CFL_CONW(1) CFL_CONW(2) CFL_CONW(3) CFL_CONW(4) CFL_CONW(5) CFL_CONW(6) CFL_CONW(7) CFL_CONW(8)
+#undef CFL_CONW
+    default: conw_reduce_kernel<0><<<grid, 256, 0, st>>>(p, scores, C, N, D, out, weights);
+  }
   return check_launch("conw_reduce");
 }
 

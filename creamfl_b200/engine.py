@@ -57,13 +57,59 @@ def _features(output: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, torch.Tens
     return output['image_features'], output['caption_features']
 
 
-_POOLS: Dict[int, list] = {}          # device index -> [pool handle, number of live graphs in the pool]
+_POOLS: Dict[tuple, list] = {}        # (device index, lane) -> [pool handle, number of live graphs in the pool]
+
+
+class lane:
+    """`with lane(device, k): <steps>` - the steps are enqueued on lane k's own CUDA stream with lane-private scratch
+    buffers and graph memory pool, so steps of different lanes (different clients hosted by one GPU: they share
+    nothing inside a round, MMFL.py:226-247 trains them one after the other) may overlap on the device.  Steps of one
+    lane stay ordered.  `lane.fork` makes the lanes wait for the work already enqueued on the current stream,
+    `lane.join` makes the current stream wait for the lanes."""
+    _streams: Dict[tuple, torch.cuda.Stream] = {}
+
+    def __init__(self, device: torch.device, k: int):
+        self.device, self.k = device, int(k)
+
+    @staticmethod
+    def stream(device: torch.device, k: int) -> torch.cuda.Stream:
+        key = (device.index, int(k))
+        if key not in lane._streams:
+            lane._streams[key] = torch.cuda.Stream(device)
+        return lane._streams[key]
+
+    def __enter__(self):
+        from . import tower_ops
+        self.prev = tower_ops.set_lane(self.k)
+        self.ctx = torch.cuda.stream(lane.stream(self.device, self.k))
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        from . import tower_ops
+        self.ctx.__exit__(*exc)
+        tower_ops.set_lane(self.prev)
+        return False
+
+    @staticmethod
+    def fork(device: torch.device, lanes) -> None:
+        cur = torch.cuda.current_stream(device)
+        for k in lanes:
+            lane.stream(device, k).wait_stream(cur)
+
+    @staticmethod
+    def join(device: torch.device, lanes) -> None:
+        cur = torch.cuda.current_stream(device)
+        for k in lanes:
+            cur.wait_stream(lane.stream(device, k))
 
 
 def _graph_pool(device: torch.device) -> list:
-    """The memory pool shared by every captured step of a device.  A pool dies with its last graph, so the handle is
-    renewed once no graph of the previous pool is alive (engines come and go in tests)."""
-    key = device.index if device.index is not None else torch.cuda.current_device()
+    """The memory pool shared by every captured step of a (device, lane) - graphs of one pool must never replay
+    concurrently, graphs of different lanes may.  A pool dies with its last graph, so the handle is renewed once no
+    graph of the previous pool is alive (engines come and go in tests)."""
+    from . import tower_ops
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tower_ops.current_lane())
     entry = _POOLS.get(key)
     if entry is None or entry[1] == 0:
         entry = _POOLS[key] = [torch.cuda.graph_pool_handle(), 0]
@@ -127,7 +173,9 @@ class _GraphCache:
         self.graphs: 'OrderedDict[tuple, GraphedStep]' = OrderedDict()
 
     def run(self, name, fn, mutates: bool, **tensors):
-        key = (name, tuple((k, tuple(t.shape), t.dtype) for k, t in tensors.items()))
+        from . import tower_ops
+        # a graph bakes in its lane's scratch buffers and memory pool: one capture per lane the step is run in
+        key = (name, tower_ops.current_lane(), tuple((k, tuple(t.shape), t.dtype) for k, t in tensors.items()))
         own = self.owner
         if own.optimizer is not None:
             own.optimizer.prepare()          # hyper-parameters (lr schedule) reach the captured kernels: re-uploaded

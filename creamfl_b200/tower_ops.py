@@ -18,12 +18,28 @@ from .ops import _p, _stream, _need_cuda
 BF16 = torch.bfloat16
 
 _ws_cache: dict = {}
+_lane = 0
+
+
+def set_lane(k: int) -> int:
+    """Execution lane of the work enqueued from now on (engine.lane): scratch buffers and forked streams are per lane,
+    so that steps of different lanes - e.g. two clients hosted by one GPU - may run concurrently, also as replays of
+    captured graphs (a graph bakes in the addresses of the scratch buffers it was captured with).  Returns the
+    previous lane."""
+    global _lane
+    old, _lane = _lane, int(k)
+    return old
+
+
+def current_lane() -> int:
+    return _lane
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:
-    """Grow-only scratch buffer per (device, stream): reuse is stream-ordered (contents are dead once the consuming
-    kernel has been enqueued), and towers running concurrently on forked streams never share one."""
-    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream if device.type == 'cuda' else 0)
+    """Grow-only scratch buffer per (device, stream, lane): reuse is stream-ordered (contents are dead once the
+    consuming kernel has been enqueued), and towers running concurrently on forked streams never share one."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream if device.type == 'cuda' else 0,
+           _lane)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)

@@ -173,7 +173,7 @@ class fork_stream:
 
     def __enter__(self):
         if self.enabled:
-            key = (self.device.index, self.slot)
+            key = (self.device.index, self.slot, T.current_lane())
             if key not in fork_stream._streams:
                 fork_stream._streams[key] = torch.cuda.Stream(self.device)
             self.side, self.main = fork_stream._streams[key], torch.cuda.current_stream(self.device)

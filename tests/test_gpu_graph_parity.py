@@ -162,6 +162,18 @@ def test_client_graph_replay_equals_eager(engine):
     assert float(cl.optimizer._state[0]) == 6.0
 
 
+def test_clients_in_concurrent_lanes_equal_one_after_the_other(engine):
+    """bench.py runs the clients hosted by one GPU in concurrent execution lanes (engine.lane: own stream, scratch
+    buffers and graph pool per lane).  Three graphed clients stepping interleaved in three lanes end where the same
+    clients end when they run one after the other on the default stream (within the atomics noise of repeated runs):
+    no scratch buffer, graph pool or stream is shared across lanes.  Runs in a child process with a time limit
+    (tests/lanes_worker.py): a GPU-side hang must fail this test, not stall the suite."""
+    res = subprocess.run([sys.executable, str(ROOT / 'tests' / 'lanes_worker.py')], capture_output=True, text=True,
+                         timeout=600, cwd=str(ROOT))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert 'LANES OK' in res.stdout
+
+
 def test_banks_refreshed_in_place_reach_the_captured_contrast_step(engine):
     g = torch.Generator().manual_seed(2)
     unit = lambda x: x / x.norm(dim=-1, keepdim=True)
