@@ -27,9 +27,11 @@ def table(t, fams):
     return res
 
 
-FAMS = ['bn_bwd', 'bn_fwd', 'conv_fprop', 'conv_dgrad', 'conv_wgrad', 'gemm_fwd', 'gemm_dgrad', 'gemm_wgrad']
+FAMS = ['bn_bwd', 'bn_fwd', 'conv_tc_fwd', 'conv_tc_dgrad', 'conv_tc_wgrad', 'gemm_tc_fwd', 'gemm_tc_dgrad', 'gemm_tc_wgrad',
+        'gemm_tc_im2col_fwd', 'gemm_tc_im2col_dgrad', 'gemm_tc_im2col_wgrad']
 torch.manual_seed(0)
 server = engine.ServerEngine(256, 'resnet101', device=dev)
+server.model.overlap_towers = False
 txt = {'ids': pub['ids'][0], 'mask': pub['mask'][0]}
 for _ in range(3):
     server._train_step(pub['images'][0], txt)
@@ -42,6 +44,8 @@ del server
 torch.cuda.empty_cache()
 
 client = engine.MMClient(256, device=dev)
+client.overlap_old_model = False
+client.model.overlap_towers = False
 g_img, g_txt = bench.make_banks(dev, 3)
 client.begin_round()
 args = (pub['images'][0], pub['caps'][0], pub['cap_lens'][0], pub['d_idx'][0], g_img, g_txt)
