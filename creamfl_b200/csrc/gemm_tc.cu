@@ -48,7 +48,12 @@ bool gemm_lean_enabled() {
 
 // Tile width the launcher picks for an [M, N, K] problem (see gemm_bf16 below).
 int gemm_tile_n(int N, int K) {
-  return (N <= 64) ? 64 : ((((N >= 256 && N % 256 == 0) || N >= 1024) && K >= 512) ? 256 : 128);
+  static int min_k = -1;      // smallest K served by 256-wide tiles (CREAMFL_GEMM_BN256_MINK overrides: measurements)
+  if (min_k < 0) {
+    const char* e = getenv("CREAMFL_GEMM_BN256_MINK");
+    min_k = e ? atoi(e) : 512;
+  }
+  return (N <= 64) ? 64 : ((((N >= 256 && N % 256 == 0) || N >= 1024) && K >= min_k) ? 256 : 128);
 }
 
 // Split-K planner of the accumulating (weight-gradient) GEMMs.  A launch runs `tiles * split` units on sm_count()
