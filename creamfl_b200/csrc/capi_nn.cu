@@ -2,6 +2,7 @@
 // the choice between the three convolution strategies; no kernel code lives here.
 #include "../../include/creamfl_b200.h"
 #include "kernels.cuh"
+#include <stdlib.h>
 
 using namespace cfl;
 
@@ -15,9 +16,18 @@ struct ConvShape {
   int kcols;   // R*S*Cin
   int ldc;     // patch-matrix pitch
   bool is_1x1, is_same;
+  bool is_strided;   // stride-2 1x1 / 3x3 with padding R/2: implicit GEMM through TMA element strides (fprop, wgrad)
 };
+bool strided_tma_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CREAMFL_CONV_STRIDED_TMA");      // 0: explicit patch matrix + GEMM (A/B measurements)
+    on = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return on != 0;
+}
 ConvShape shape_of(int N, int H, int W, int Cin, int Cout, int R, int S_, int stride, int pad) {
-  ConvShape c{N, H, W, Cin, Cout, R, S_, stride, pad, 0, 0, 0, 0, 0, false, false};
+  ConvShape c{N, H, W, Cin, Cout, R, S_, stride, pad, 0, 0, 0, 0, 0, false, false, false};
   c.Ho = (H + 2 * pad - R) / stride + 1;
   c.Wo = (W + 2 * pad - S_) / stride + 1;
   c.P_out = (long long)N * c.Ho * c.Wo;
@@ -26,6 +36,8 @@ ConvShape shape_of(int N, int H, int W, int Cin, int Cout, int R, int S_, int st
   c.is_1x1 = (R == 1 && S_ == 1 && stride == 1 && pad == 0);
   c.is_same = (!c.is_1x1 && stride == 1 && (R & 1) && (S_ & 1) && pad == R / 2 && pad == S_ / 2 && Cin % 64 == 0 &&
                Cout % 64 == 0);
+  c.is_strided = (stride == 2 && R == S_ && (R == 1 || R == 3) && pad == R / 2 && Cin % 64 == 0 && Cout % 64 == 0 &&
+                  strided_tma_enabled());
   return c;
 }
 int check_shape(const char* who, const ConvShape& c) {
@@ -61,8 +73,8 @@ int creamfl_conv2d_fprop(const void* x, const void* w, int N, int H, int W, int 
     set_error("conv2d_fprop: null pointer");
     return CFL_EINVAL;
   }
-  if (c.is_same && w_pitch == c.kcols) {
-    if ((rc = conv_same_fprop(x, w, N, H, W, Cin, Cout, R, S_, y, S(stream)))) return rc;
+  if ((c.is_same || c.is_strided) && w_pitch == c.kcols) {
+    if ((rc = conv_same_fprop(x, w, N, H, W, Cin, Cout, R, S_, y, S(stream), nullptr, nullptr, 0, stride))) return rc;
     return bn_sums ? bn_stats_only(y, c.P_out, Cout, bn_sums, S(stream)) : CFL_OK;
   }
   GemmParams p{};
@@ -97,8 +109,8 @@ int creamfl_conv2d_fprop_affine(const void* x, const void* w, int N, int H, int 
     set_error("conv2d_fprop_affine: null pointer");
     return CFL_EINVAL;
   }
-  if (c.is_same && w_pitch == c.kcols)
-    return conv_same_fprop(x, w, N, H, W, Cin, Cout, R, S_, y, S(stream), bias, add, relu);
+  if ((c.is_same || c.is_strided) && w_pitch == c.kcols)
+    return conv_same_fprop(x, w, N, H, W, Cin, Cout, R, S_, y, S(stream), bias, add, relu, stride);
   GemmParams p{};
   p.M = (int)c.P_out; p.N = Cout; p.split_k = 1;
   p.out = y; p.ldo = Cout; p.out_bf16 = 1; p.alpha = 1.0f;
@@ -170,7 +182,7 @@ int creamfl_conv2d_wgrad(const void* dy, const void* x, const void* col, int N, 
     set_error("conv2d_wgrad: null pointer");
     return CFL_EINVAL;
   }
-  if (c.is_same && !col) return conv_same_wgrad(dy, x, N, H, W, Cin, Cout, R, S_, dw, S(stream));
+  if ((c.is_same || c.is_strided) && !col) return conv_same_wgrad(dy, x, N, H, W, Cin, Cout, R, S_, dw, S(stream), stride);
   GemmParams p{};
   p.M = Cout; p.K = (int)c.P_out; p.alpha = 1.0f; p.out = dw; p.ldo = c.kcols; p.out_bf16 = 0; p.atomic_out = 1;
   if (c.is_1x1 && !col) {

@@ -22,7 +22,9 @@
 namespace cfl {
 
 struct ConvParams {
-  int N, H, W;           // activation extent (input == output: stride 1, same padding)
+  int N, H, W;           // OUTPUT extent (== input extent for stride 1, same padding)
+  int stride;            // fprop / wgrad: input pixel = output pixel * stride + tap - pad (TMA element strides sample
+                         // the input box; dgrad is stride 1 only)
   int Cin, Cout;
   int R, S, pad_h, pad_w;
   int bw, bh, bn;        // pixel box of one tile (product 128 for fprop/dgrad, 64 for wgrad)
@@ -152,7 +154,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
             expect(stage);
-            load4(&tmA, stage, sa, c0, w0 + dw, h0 + dh, n0);
+            load4(&tmA, stage, sa, c0, w0 * p.stride + dw, h0 * p.stride + dh, n0);
             if (MODE == 0) {
               load2(&tmB, stage, sb, tap * p.Cin + c0, n_blk * BN + b_off);
             } else {
@@ -188,7 +190,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               load4(&tmA, stage, sa + j * 8192, m_blk * kCBM + j * 64, w0, h0, n0);
 #pragma unroll
             for (int j = 0; j < Cfg::kBRows / 64; ++j)
-              load4(&tmB, stage, sb + j * 8192, n_blk * BN + b_off + j * 64, w0 + dw, h0 + dh, n0);
+              load4(&tmB, stage, sb + j * 8192, n_blk * BN + b_off + j * 64, w0 * p.stride + dw, h0 * p.stride + dh, n0);
             if (++stage == Cfg::kStages) {
               stage = 0;
               phase ^= 1;
@@ -438,13 +440,16 @@ static int check_conv(const char* who, int N, int H, int W, int Cin, int Cout, i
 
 // Y = conv(X, Wt), stride 1, padding (R/2, S/2).  X [N,H,W,Cin], Wt [Cout,R,S,Cin], Y [N,H,W,Cout], all bf16.
 int conv_same_fprop(const void* x, const void* wt, int N, int H, int W, int Cin, int Cout, int R, int S, void* y,
-                    cudaStream_t stream, const float* bias, const void* add, int relu) {
+                    cudaStream_t stream, const float* bias, const void* add, int relu, int stride) {
   int rc = check_conv("conv_fprop", N, H, W, Cin, Cout, R, S);
   if (rc) return rc;
   ConvParams p{};
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad_h = R / 2; p.pad_w = S / 2;
-  plan_box(H, W, kCBM, &p.bw, &p.bh, &p.bn);
-  p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
+  // padding R/2: Ho = (H + 2 (R/2) - R) / stride + 1; the pixel tiling and the epilogue live in OUTPUT coordinates
+  const int Ho = (H + 2 * (R / 2) - R) / stride + 1, Wo = (W + 2 * (S / 2) - S) / stride + 1;
+  p.N = N; p.H = Ho; p.W = Wo; p.stride = stride;
+  p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad_h = R / 2; p.pad_w = S / 2;
+  plan_box(Ho, Wo, kCBM, &p.bw, &p.bh, &p.bn);
+  p.tiles_w = Wo / p.bw; p.tiles_h = Ho / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
   p.split_k = 1;
   p.out = y;
   p.bias = bias;
@@ -454,7 +459,9 @@ int conv_same_fprop(const void* x, const void* wt, int N, int H, int W, int Cin,
   const bool pair = conv_pair_enabled() && Cout % 128 == 0 && pix_tiles >= 2;
   const int BN = pair ? (Cout % 256 == 0 ? 256 : 128) : ((Cout <= 64) ? 64 : 128);
   CUtensorMap ta, tb;
-  if ((rc = make_tmap_nhwc(&ta, x, N, H, W, Cin, 64, p.bw, p.bh, p.bn, 1))) return rc;
+  // strided: the box spans (b - 1) * stride + 1 input pixels per dimension and keeps every stride-th one
+  if ((rc = make_tmap_nhwc(&ta, x, N, H, W, Cin, 64, (p.bw - 1) * stride + 1, (p.bh - 1) * stride + 1, p.bn, stride)))
+    return rc;
   if ((rc = make_tmap_2d(&tb, wt, 2, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, 64, pair ? BN / 2 : BN)))
     return rc;
   if (pair) {
@@ -472,7 +479,8 @@ int conv_same_dgrad(const void* dy, const void* wt, int N, int H, int W, int Cin
   int rc = check_conv("conv_dgrad", N, H, W, Cin, Cout, R, S);
   if (rc) return rc;
   ConvParams p{};
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad_h = R / 2; p.pad_w = S / 2;
+  p.N = N; p.H = H; p.W = W; p.stride = 1;
+  p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad_h = R / 2; p.pad_w = S / 2;
   plan_box(H, W, kCBM, &p.bw, &p.bh, &p.bn);
   p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
   p.split_k = 1;
@@ -495,13 +503,15 @@ int conv_same_dgrad(const void* dy, const void* wt, int N, int H, int W, int Cin
 
 // dW[Cout,R,S,Cin] (fp32) += dY^T * shifted X.
 int conv_same_wgrad(const void* dy, const void* x, int N, int H, int W, int Cin, int Cout, int R, int S, float* dw,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, int stride) {
   int rc = check_conv("conv_wgrad", N, H, W, Cin, Cout, R, S);
   if (rc) return rc;
   ConvParams p{};
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad_h = R / 2; p.pad_w = S / 2;
-  plan_box(H, W, 64, &p.bw, &p.bh, &p.bn);
-  p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
+  const int Ho = (H + 2 * (R / 2) - R) / stride + 1, Wo = (W + 2 * (S / 2) - S) / stride + 1;
+  p.N = N; p.H = Ho; p.W = Wo; p.stride = stride;
+  p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad_h = R / 2; p.pad_w = S / 2;
+  plan_box(Ho, Wo, 64, &p.bw, &p.bh, &p.bn);
+  p.tiles_w = Wo / p.bw; p.tiles_h = Ho / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
   p.out = dw;
   const bool pair = conv_pair_enabled() && Cout % 256 == 0 && Cin % 128 == 0;
   const int BN = pair ? (Cin % 256 == 0 ? 256 : 128) : ((Cin <= 64) ? 64 : 128);
@@ -512,8 +522,9 @@ int conv_same_wgrad(const void* dy, const void* x, int N, int H, int W, int Cin,
   const int split = plan_split_k(base_units, pix_tiles, 8, 4.0, pair ? sm_count() / 2 : 0);
   p.split_k = split;
   CUtensorMap ta, tb;
-  if ((rc = make_tmap_nhwc(&ta, dy, N, H, W, Cout, 64, p.bw, p.bh, p.bn, 1))) return rc;
-  if ((rc = make_tmap_nhwc(&tb, x, N, H, W, Cin, 64, p.bw, p.bh, p.bn, 1))) return rc;
+  if ((rc = make_tmap_nhwc(&ta, dy, N, Ho, Wo, Cout, 64, p.bw, p.bh, p.bn, 1))) return rc;
+  if ((rc = make_tmap_nhwc(&tb, x, N, H, W, Cin, 64, (p.bw - 1) * stride + 1, (p.bh - 1) * stride + 1, p.bn, stride)))
+    return rc;
   const int units = base_units * split;
   if (pair)
     return BN == 256 ? launch_conv<256, 2, true>(ta, tb, p, units, stream)
