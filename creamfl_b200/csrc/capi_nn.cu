@@ -156,6 +156,8 @@ int creamfl_conv2d_dgrad(const void* dy, const void* w, int N, int H, int W, int
     return CFL_EINVAL;
   }
   if (c.is_same && w_pitch == c.kcols) return conv_same_dgrad(dy, w, N, H, W, Cin, Cout, R, S_, dx, add, S(stream));
+  if (c.is_strided && R == 3 && !(H & 1) && !(W & 1) && w_pitch == c.kcols)
+    return conv_same_dgrad(dy, w, N, H, W, Cin, Cout, R, S_, dx, add, S(stream), stride);
   GemmParams p{};
   p.M = (int)c.P_out; p.K = Cout; p.split_k = 1; p.alpha = 1.0f; p.out_bf16 = 1;
   if (c.is_1x1) {

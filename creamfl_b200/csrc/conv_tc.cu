@@ -24,7 +24,11 @@ namespace cfl {
 struct ConvParams {
   int N, H, W;           // OUTPUT extent (== input extent for stride 1, same padding)
   int stride;            // fprop / wgrad: input pixel = output pixel * stride + tap - pad (TMA element strides sample
-                         // the input box; dgrad is stride 1 only)
+                         // the input box)
+  int up;                // dgrad of a stride-2 convolution (1: stride 1): N, H, W describe dY; dX is [N, 2H, 2W, Cin] and
+                         // splits into 4 parity classes (h % 2, w % 2), each a dense stride-1 problem over the taps
+                         // r = (parity + pad) mod 2, +2, ... that reach it: dX[2h'+ph, 2w'+pw] += dY[h' + dh, w' + dw] W[r, s]
+                         // with dh = (ph + pad - r) / 2.  A work unit = (pixel tile of dY, class, channel block).
   int Cin, Cout;
   int R, S, pad_h, pad_w;
   int bw, bh, bn;        // pixel box of one tile (product 128 for fprop/dgrad, 64 for wgrad)
@@ -53,6 +57,18 @@ struct ConvCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
   static constexpr uint32_t kTmemCols = (BN == 256) ? 512 : ((BN == 128) ? 256 : 128);
 };
+
+// taps of parity class (ph, pw) of a stride-2 data gradient: r = r0 + 2 i (i < nr), s = s0 + 2 j (j < ns)
+struct ClassTaps {
+  int ph, pw, r0, nr, s0, ns;
+};
+__device__ __forceinline__ ClassTaps class_taps(const ConvParams& p, int pc) {
+  ClassTaps c;
+  c.ph = pc >> 1; c.pw = pc & 1;
+  c.r0 = (c.ph + p.pad_h) & 1; c.nr = (p.R - c.r0 + 1) >> 1;
+  c.s0 = (c.pw + p.pad_w) & 1; c.ns = (p.S - c.s0 + 1) >> 1;
+  return c;
+}
 
 template <int BN, int MODE, bool CTA2>
 __global__ void __launch_bounds__(256, 1)
@@ -92,8 +108,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int cred = (MODE == 0) ? p.Cin : p.Cout;
     nkb = taps * (cred / kCBK);
     kb_per = nkb;
-    units = num_m * num_n;
+    units = num_m * num_n * ((MODE == 1 && p.up == 2) ? 4 : 1);
   }
+  const bool upx = (MODE == 1 && p.up == 2);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -138,18 +155,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int u = wid; u < units; u += wstride) {
         if (MODE != 2) {
           const int m_blk = CTA2 ? 2 * (u % num_m) + cta_rank : u % num_m;
-          const int n_blk = u / num_m;
+          const int rest = u / num_m;
+          const int n_blk = upx ? rest >> 2 : rest;
+          const ClassTaps ct = class_taps(p, upx ? rest & 3 : 0);
           const int w0 = (m_blk % p.tiles_w) * p.bw;
           const int h0 = ((m_blk / p.tiles_w) % p.tiles_h) * p.bh;
           const int n0 = (m_blk / (p.tiles_w * p.tiles_h)) * p.bn;
           const int cred = (MODE == 0) ? p.Cin : p.Cout;
           const int cchunks = cred / kCBK;
-          for (int kb = 0; kb < nkb; ++kb) {
-            const int tap = kb / cchunks;
+          const int nkb_u = upx ? ct.nr * ct.ns * cchunks : nkb;
+          for (int kb = 0; kb < nkb_u; ++kb) {
             const int c0 = (kb % cchunks) * kCBK;
-            const int r = tap / p.S, s = tap % p.S;
-            const int dh = (MODE == 0) ? (r - p.pad_h) : (p.pad_h - r);
-            const int dw = (MODE == 0) ? (s - p.pad_w) : (p.pad_w - s);
+            int tap = kb / cchunks, r, s, dh, dw;
+            if (upx) {
+              r = ct.r0 + 2 * (tap / ct.ns); s = ct.s0 + 2 * (tap % ct.ns);
+              tap = r * p.S + s;
+              dh = (ct.ph + p.pad_h - r) >> 1; dw = (ct.pw + p.pad_w - s) >> 1;
+            } else {
+              r = tap / p.S; s = tap % p.S;
+              dh = (MODE == 0) ? (r - p.pad_h) : (p.pad_h - r);
+              dw = (MODE == 0) ? (s - p.pad_w) : (p.pad_w - s);
+            }
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
@@ -214,6 +240,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int ks = u / (num_m * num_n * taps);
           kb0 = ks * kb_per;
           kb1 = min(nkb, kb0 + kb_per);
+        } else if (upx) {
+          const ClassTaps ct = class_taps(p, (u / num_m) & 3);
+          kb1 = ct.nr * ct.ns * (p.Cout / kCBK);
         }
         const int buf = it & 1;
         const uint32_t bphase = (it >> 1) & 1;
@@ -255,12 +284,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       bool has_k = true;
       if (MODE != 2) {
         const int m_blk = CTA2 ? 2 * (u % num_m) + cta_rank : u % num_m;
-        n_blk = u / num_m;
+        const int rest = u / num_m;
+        n_blk = upx ? rest >> 2 : rest;
         const int w = (m_blk % p.tiles_w) * p.bw + rloc % p.bw;
         const int h = ((m_blk / p.tiles_w) % p.tiles_h) * p.bh + (rloc / p.bw) % p.bh;
         const int n = (m_blk / (p.tiles_w * p.tiles_h)) * p.bn + rloc / (p.bw * p.bh);
         row_ok = (w < p.W) && (h < p.H) && (n < p.N);
-        row_off = (((long long)n * p.H + h) * p.W + w) * n_extent;
+        if (upx) {       // this class's pixel of the up-sampled gradient map
+          const int ph = (rest & 3) >> 1, pw = rest & 1;
+          row_off = (((long long)n * (2 * p.H) + 2 * h + ph) * (2 * p.W) + 2 * w + pw) * n_extent;
+        } else {
+          row_off = (((long long)n * p.H + h) * p.W + w) * n_extent;
+        }
       } else {
         int t = u;
         const int m_blk = CTA2 ? 2 * (t % num_m) + cta_rank : t % num_m; t /= num_m;
@@ -475,11 +510,20 @@ int conv_same_fprop(const void* x, const void* wt, int N, int H, int W, int Cin,
 
 // dX = conv_transpose(dY, Wt).  dY [N,H,W,Cout], Wt [Cout,R,S,Cin], dX [N,H,W,Cin], all bf16.
 int conv_same_dgrad(const void* dy, const void* wt, int N, int H, int W, int Cin, int Cout, int R, int S, void* dx,
-                    const void* add, cudaStream_t stream) {
+                    const void* add, cudaStream_t stream, int stride) {
   int rc = check_conv("conv_dgrad", N, H, W, Cin, Cout, R, S);
   if (rc) return rc;
+  if (stride != 1 && (stride != 2 || (H & 1) || (W & 1) || R != 3 || S != 3)) {
+    set_error("conv_dgrad: implicit path serves stride 1, or 3x3 stride 2 on even maps (got %dx%d stride %d, %dx%d)", R, S,
+              stride, H, W);
+    return CFL_EINVAL;
+  }
   ConvParams p{};
-  p.N = N; p.H = H; p.W = W; p.stride = 1;
+  if (stride == 2) {     // tile dY; every tile serves the four parity classes of dX
+    H /= 2;
+    W /= 2;
+  }
+  p.N = N; p.H = H; p.W = W; p.stride = 1; p.up = stride;
   p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.pad_h = R / 2; p.pad_w = S / 2;
   plan_box(H, W, kCBM, &p.bw, &p.bh, &p.bn);
   p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
@@ -492,12 +536,13 @@ int conv_same_dgrad(const void* dy, const void* wt, int N, int H, int W, int Cin
   CUtensorMap ta, tb;
   if ((rc = make_tmap_nhwc(&ta, dy, N, H, W, Cout, 64, p.bw, p.bh, p.bn, 1))) return rc;
   if ((rc = make_tmap_2d(&tb, wt, 2, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, 64, 64))) return rc;
+  const int classes = stride == 2 ? 4 : 1;
   if (pair) {
-    const int units = ((pix_tiles + 1) / 2) * (Cin / BN);
+    const int units = ((pix_tiles + 1) / 2) * (Cin / BN) * classes;
     return BN == 256 ? launch_conv<256, 1, true>(ta, tb, p, units, stream)
                      : launch_conv<128, 1, true>(ta, tb, p, units, stream);
   }
-  const int units = pix_tiles * ((Cin + BN - 1) / BN);
+  const int units = pix_tiles * ((Cin + BN - 1) / BN) * classes;
   return BN == 64 ? launch_conv<64, 1>(ta, tb, p, units, stream) : launch_conv<128, 1>(ta, tb, p, units, stream);
 }
 

@@ -64,7 +64,8 @@ namespace cfl {
 // conv_tc.cu
 int conv_same_fprop(const void*, const void*, int, int, int, int, int, int, int, void*, cudaStream_t,
                     const float* bias = nullptr, const void* add = nullptr, int relu = 0, int stride = 1);
-int conv_same_dgrad(const void*, const void*, int, int, int, int, int, int, int, void*, const void*, cudaStream_t);
+int conv_same_dgrad(const void*, const void*, int, int, int, int, int, int, int, void*, const void*, cudaStream_t,
+                    int stride = 1);
 int conv_same_wgrad(const void*, const void*, int, int, int, int, int, int, int, float*, cudaStream_t, int stride = 1);
 // stem_tc.cu
 bool stem_supported(int C, int H, int W, int R, int S, int stride, int pad, int Cout);
