@@ -280,6 +280,48 @@ int creamfl_bn_train_bwd(const void* dy, const void* y, const void* x, int64_t P
                       S(stream));
 }
 
+int creamfl_bn_train_stats(const void* x, int64_t P, int C, const float* gamma, const float* beta, float eps,
+                           float momentum, float* running_mean, float* running_var, double* sums, float* mean,
+                           float* rstd, float* scale, float* shift, int stats_ready, int64_t* num_batches_tracked,
+                           void* stream) {
+  if (!x || !gamma || !beta || !sums || !mean || !rstd || !scale || !shift) {
+    set_error("bn_train_stats: null pointer");
+    return CFL_EINVAL;
+  }
+  return bn_train_fwd(x, P, C, gamma, beta, eps, momentum, running_mean, running_var, sums, mean, rstd, scale, shift,
+                      nullptr, 0, stats_ready, reinterpret_cast<long long*>(num_batches_tracked), nullptr, S(stream));
+}
+
+int creamfl_bn_eval_affine(int C, const float* gamma, const float* beta, float eps, const float* running_mean,
+                           const float* running_var, float* scale, float* shift, void* stream) {
+  if (!gamma || !beta || !running_mean || !running_var || !scale || !shift) {
+    set_error("bn_eval_affine: null pointer");
+    return CFL_EINVAL;
+  }
+  return bn_eval_fwd(nullptr, 1, C, gamma, beta, eps, running_mean, running_var, scale, shift, nullptr, 0, nullptr,
+                     S(stream));
+}
+
+int creamfl_maxpool_affine_fwd(const void* x, const float* scale, const float* shift, int N, int H, int W, int C,
+                               void* y, void* idx, void* stream) {
+  if (!x || !y || !scale || !shift) {
+    set_error("maxpool_affine_fwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return maxpool_fwd(x, N, H, W, C, y, idx, S(stream), scale, shift);
+}
+
+int creamfl_bn_pool_bwd(const void* dy_pooled, const void* idx, const void* x, int N, int H, int W, int C,
+                        const float* gamma, const float* beta, const float* mean, const float* rstd, double* sums,
+                        float* coef, float* dgamma, float* dbeta, void* dx, void* stream) {
+  if (!dy_pooled || !idx || !x || !gamma || !beta || !mean || !rstd || !sums || !coef || !dx) {
+    set_error("bn_pool_bwd: null pointer");
+    return CFL_EINVAL;
+  }
+  return bn_train_bwd(dy_pooled, nullptr, x, (long long)N * H * W, C, gamma, beta, 1, mean, rstd, sums, coef, dgamma,
+                      dbeta, dx, nullptr, S(stream), nullptr, idx, H, W);
+}
+
 int creamfl_maxpool_fwd(const void* x, int N, int H, int W, int C, void* y, void* idx, void* stream) {
   if (!x || !y) {
     set_error("maxpool_fwd: null pointer");

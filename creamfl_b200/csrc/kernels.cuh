@@ -81,8 +81,9 @@ int bn_eval_fwd(const void*, long long, int, const float*, const float*, float, 
                 float*, const void*, int, void*, cudaStream_t);
 int bn_train_bwd(const void*, const void*, const void*, long long, int, const float*, const float*, int, const float*,
                  const float*, double*, float*, float*, float*, void*, void*, cudaStream_t,
-                 const void* relu_mask = nullptr);
-int maxpool_fwd(const void*, int, int, int, int, void*, void*, cudaStream_t);
+                 const void* relu_mask = nullptr, const void* pool_idx = nullptr, int H = 0, int W = 0);
+int maxpool_fwd(const void*, int, int, int, int, void*, void*, cudaStream_t, const float* scale = nullptr,
+                const float* shift = nullptr);
 int maxpool_bwd(const void*, const void*, int, int, int, int, void*, cudaStream_t);
 int im2col_nhwc(const void*, int, int, int, int, int, int, int, int, int, void*, cudaStream_t);
 int im2col_nchw_f32(const float*, int, int, int, int, int, int, int, int, int, void*, cudaStream_t);

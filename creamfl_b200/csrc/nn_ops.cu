@@ -197,14 +197,51 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s
   }
 }
 
+// 3x3 / stride 2 / pad 1 max-pooling backward in gather form (see maxpool_bwd_kernel): gradient of 8 channels of one
+// input pixel from the pooled gradient and the winning taps.  Also the gradient SOURCE of the fused stem backward
+// (SRC == 2 below): the up-sampled gradient map is never written.
+__device__ __forceinline__ void pool_gather8(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx, int n,
+                                             int h, int w, int g, int C, int Ho, int Wo, float (&acc)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int hn = h + 1 - r;
+    if (hn < 0 || (hn & 1)) continue;
+    const int ho = hn >> 1;
+    if (ho >= Ho) continue;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int wn = w + 1 - s;
+      if (wn < 0 || (wn & 1)) continue;
+      const int wo = wn >> 1;
+      if (wo >= Wo) continue;
+      const long long o = (((long long)n * Ho + ho) * Wo + wo) * C + g * 8;
+      const uint2 pk = *reinterpret_cast<const uint2*>(idx + o);
+      float d[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dy + o), d);
+      const int tap = r * 3 + s;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int who = ((i < 4 ? pk.x : pk.y) >> (8 * (i & 3))) & 0xff;
+        if (who == tap) acc[i] += d[i];
+      }
+    }
+  }
+}
+
 // sums[0..C) += sum_p g ; sums[C..2C) += sum_p g * xhat    with g = dy * (y > 0 if relu)
-template <bool MASK>
+// SRC: 0 dy as given (gate from y / from x / none), 1 gate bits in `mask`, 2 dy = max-pooling backward of the pooled
+// gradient `dy` with winning taps `mask` over an [N, H, W, C] map (gate from x)
+template <int SRC>
 __global__ void __launch_bounds__(kBnThreads, 2)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y /* null: no relu */,
                      const uint8_t* __restrict__ mask /* alternative to y: gate bits written by the forward pass */,
                      const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                     int relu_from_x, long long P, int C, double* __restrict__ sums) {
+                     int relu_from_x, long long P, int C, double* __restrict__ sums, int H, int W) {
+  constexpr bool MASK = SRC == 1;
+  constexpr bool POOL = SRC == 2;
   extern __shared__ float sh[];
   const int groups = C >> 3;
   const int rows = kBnThreads / groups;
@@ -229,9 +266,9 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       for (int u = 0; u < 4; ++u) {        // 8-12 independent 16-byte loads in flight per thread
         if (p + u * stride < P) {
           const long long o = (p + u * stride) * C + g * 8;
-          rd[u] = *reinterpret_cast<const bf16x8*>(dy + o);
+          if (!POOL) rd[u] = *reinterpret_cast<const bf16x8*>(dy + o);
           rx[u] = *reinterpret_cast<const bf16x8*>(x + o);
-          if (!MASK && y) ry[u] = *reinterpret_cast<const bf16x8*>(y + o);
+          if (!MASK && !POOL && y) ry[u] = *reinterpret_cast<const bf16x8*>(y + o);
           if (MASK) mk[u] = mask[o >> 3];
         }
       }
@@ -239,12 +276,18 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       for (int u = 0; u < 4; ++u) {
         if (p + u * stride < P) {
           float d[8], xv[8];
-          unpack8(rd[u], d);
+          if (POOL) {
+            const long long pp = p + u * stride;
+            const int w = (int)(pp % W), h = (int)((pp / W) % H), nn = (int)(pp / ((long long)W * H));
+            pool_gather8(dy, mask, nn, h, w, g, C, (H + 1) / 2, (W + 1) / 2, d);
+          } else {
+            unpack8(rd[u], d);
+          }
           unpack8(rx[u], xv);
           if (MASK) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) d[i] = ((mk[u] >> i) & 1u) ? d[i] : 0.0f;
-          } else if (y) {
+          } else if (!POOL && y) {
             float yv[8];
             unpack8(ry[u], yv);
 #pragma unroll
@@ -304,12 +347,14 @@ __global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, long long P, i
 
 // dx = a*g + b*x + c0 ; optionally g itself is written out (gradient of the residual branch)
 constexpr int kBwdVec = 4;
-template <bool MASK>
+template <int SRC>
 __global__ void __launch_bounds__(kEwThreads, 2)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                     const uint8_t* __restrict__ mask, const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef,
                     const float* __restrict__ gate /* [2, C] affine of the ReLU gate, or null */, long long total8, int C,
-                    __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ g_out) {
+                    __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ g_out, int H, int W) {
+  constexpr bool MASK = SRC == 1;
+  constexpr bool POOL = SRC == 2;
   const long long stride = (long long)gridDim.x * kEwThreads;
   const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
   float ca[8], cb[8], cc[8], gs[8], gb[8];
@@ -328,9 +373,9 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
     for (int u = 0; u < kBwdVec; ++u) {
       const long long t = t0 + u * stride;
       if (t < total8) {
-        rd[u] = reinterpret_cast<const bf16x8*>(dy)[t];
+        if (!POOL) rd[u] = reinterpret_cast<const bf16x8*>(dy)[t];
         rx[u] = reinterpret_cast<const bf16x8*>(x)[t];
-        if (!MASK && y) ry[u] = reinterpret_cast<const bf16x8*>(y)[t];
+        if (!MASK && !POOL && y) ry[u] = reinterpret_cast<const bf16x8*>(y)[t];
         if (MASK) mk[u] = mask[t];
       }
     }
@@ -339,12 +384,19 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
       const long long t = t0 + u * stride;
       if (t >= total8) continue;
       float d[8], xv[8];
-      unpack8(rd[u], d);
+      if (POOL) {
+        const int groups = C >> 3;
+        const long long pp = t / groups;
+        const int w = (int)(pp % W), h = (int)((pp / W) % H), nn = (int)(pp / ((long long)W * H));
+        pool_gather8(dy, mask, nn, h, w, (int)(t % groups), C, (H + 1) / 2, (W + 1) / 2, d);
+      } else {
+        unpack8(rd[u], d);
+      }
       unpack8(rx[u], xv);
       if (MASK) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[i] = ((mk[u] >> i) & 1u) ? d[i] : 0.0f;
-      } else if (y) {
+      } else if (!POOL && y) {
         float yv[8];
         unpack8(ry[u], yv);
 #pragma unroll
@@ -412,6 +464,7 @@ int bn_train_fwd(const void* x, long long P, int C, const float* gamma, const fl
   if (!stats_ready && (rc = bn_stats_only(x, P, C, sums, st))) return rc;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, beta, eps, momentum, running_mean,
                                                        running_var, mean, rstd, scale, shift, num_batches_tracked);
+  if (y == nullptr) return check_launch("bn_train_stats");      // statistics + affine only (the consumer applies it)
   const long long total8 = P * C / 8;
   if (relu_mask)
     bn_apply_kernel<true><<<ew_grid(total8, kEwVec), kEwThreads, 0, st>>>(
@@ -430,6 +483,7 @@ int bn_eval_fwd(const void* x, long long P, int C, const float* gamma, const flo
   int rc = bn_check("bn_eval_fwd", P, C);
   if (rc) return rc;
   bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, eps, running_mean, running_var, scale, shift);
+  if (y == nullptr) return check_launch("bn_eval_affine");      // affine only
   const long long total8 = P * C / 8;
   bn_apply_kernel<false><<<ew_grid(total8, kEwVec), kEwThreads, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, reinterpret_cast<const __nv_bfloat16*>(res), relu,
@@ -439,26 +493,31 @@ int bn_eval_fwd(const void* x, long long P, int C, const float* gamma, const flo
 
 int bn_train_bwd(const void* dy, const void* y_or_null, const void* x, long long P, int C, const float* gamma,
                  const float* beta, int relu_from_x, const float* mean, const float* rstd, double* sums, float* coef,
-                 float* dgamma, float* dbeta, void* dx, void* g_out, cudaStream_t st, const void* relu_mask) {
+                 float* dgamma, float* dbeta, void* dx, void* g_out, cudaStream_t st, const void* relu_mask,
+                 const void* pool_idx, int H, int W) {
   int rc = bn_check("bn_train_bwd", P, C);
   if (rc) return rc;
-  const uint8_t* mask = reinterpret_cast<const uint8_t*>(relu_mask);
+  const uint8_t* mask = reinterpret_cast<const uint8_t*>(pool_idx ? pool_idx : relu_mask);
   if (mask) y_or_null = nullptr;
-  const int gate_from_x = (relu_from_x && y_or_null == nullptr && mask == nullptr && beta != nullptr) ? 1 : 0;
+  if (pool_idx && (H <= 0 || W <= 0 || P % ((long long)H * W) != 0 || !relu_from_x || beta == nullptr)) {
+    set_error("bn_train_bwd: pooled source needs the map extent and the ReLU gate from x");
+    return CFL_EINVAL;
+  }
+  const int gate_from_x = (relu_from_x && y_or_null == nullptr && (mask == nullptr || pool_idx) && beta != nullptr) ? 1 : 0;
   const int rows = kBnThreads / (C >> 3);
   const size_t smem = (size_t)(rows > 0 ? rows : 1) * 2 * C * sizeof(float);
-  auto reduce = mask ? bn_bwd_reduce_kernel<true> : bn_bwd_reduce_kernel<false>;
-  auto apply = mask ? bn_bwd_apply_kernel<true> : bn_bwd_apply_kernel<false>;
+  auto reduce = pool_idx ? bn_bwd_reduce_kernel<2> : (mask ? bn_bwd_reduce_kernel<1> : bn_bwd_reduce_kernel<0>);
+  auto apply = pool_idx ? bn_bwd_apply_kernel<2> : (mask ? bn_bwd_apply_kernel<1> : bn_bwd_apply_kernel<0>);
   reduce<<<bn_reduce_grid(P, C), kBnThreads, smem, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_or_null), mask,
-      reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, gamma, beta, gate_from_x, P, C, sums);
+      reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, gamma, beta, gate_from_x, P, C, sums, H, W);
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, P, C, gamma, mean, rstd, gate_from_x ? beta : nullptr,
                                                           dgamma, dbeta, coef);
   const long long total8 = P * C / 8;
   apply<<<ew_grid(total8, kBwdVec), kEwThreads, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y_or_null), mask,
       reinterpret_cast<const __nv_bfloat16*>(x), coef, gate_from_x ? coef + 3 * C : nullptr, total8, C,
-      reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(g_out));
+      reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(g_out), H, W);
   return check_launch("bn_train_bwd");
 }
 
@@ -493,9 +552,13 @@ int bn_fold_layers(const long long* layers, const long long* row_start, int n_la
 
 // ------------------------------------------------------------------------------------------------ max pooling
 // 3x3, stride 2, pad 1 (torchvision ResNet stem).  idx stores the winning tap (0..8) per output element.
+// AFFINE: the input is a raw convolution output; relu(scale[c] * x + shift[c]) (BatchNorm + ReLU) is applied to every
+// element as it is read, so the normalised map is never written (ResNet stem: 205 MB per batch of 128 at 112 x 112 x 64).
+template <bool AFFINE>
 __global__ void __launch_bounds__(256)
-maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int Ho, int Wo,
-                   __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx) {
+maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                   int N, int H, int W, int C, int Ho, int Wo, __nv_bfloat16* __restrict__ y,
+                   uint8_t* __restrict__ idx) {
   const int groups = C >> 3;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)N * Ho * Wo * groups;
@@ -507,6 +570,11 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int
   const int n = (int)(pix / Ho);
   float best[8];
   int bi[8];
+  float sc[8], sf[8];
+  if (AFFINE) {
+    load_coef8(scale, g * 8, sc);
+    load_coef8(shift, g * 8, sf);
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; bi[i] = 0; }
 #pragma unroll
@@ -519,6 +587,10 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int
       if (w < 0 || w >= W) continue;
       float f[8];
       unpack8(*reinterpret_cast<const bf16x8*>(x + (((long long)n * H + h) * W + w) * C + g * 8), f);
+      if (AFFINE) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fmaxf(fmaf(f[i], sc[i], sf[i]), 0.0f);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (f[i] > best[i]) { best[i] = f[i]; bi[i] = r * 3 + s; }
@@ -575,15 +647,17 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
   *reinterpret_cast<bf16x8*>(dx + ((((long long)n * H + h) * W + w) * C + g * 8)) = pack8(acc);
 }
 
-int maxpool_fwd(const void* x, int N, int H, int W, int C, void* y, void* idx, cudaStream_t st) {
+int maxpool_fwd(const void* x, int N, int H, int W, int C, void* y, void* idx, cudaStream_t st, const float* scale,
+                const float* shift) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7)) {
     set_error("maxpool_fwd: bad shape");
     return CFL_EINVAL;
   }
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)N * Ho * Wo * (C >> 3);
-  maxpool_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, Ho, Wo, reinterpret_cast<__nv_bfloat16*>(y),
+  auto kern = (scale && shift) ? maxpool_fwd_kernel<true> : maxpool_fwd_kernel<false>;
+  kern<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), scale, shift, N, H, W, C, Ho, Wo, reinterpret_cast<__nv_bfloat16*>(y),
       reinterpret_cast<uint8_t*>(idx));
   return check_launch("maxpool_fwd");
 }

@@ -288,6 +288,45 @@ def maxpool_fwd(x, want_idx=True):
     return y, idx
 
 
+def stem_tail_fwd(o, bn, training: bool, want_idx: bool):
+    """Fused BatchNorm -> ReLU -> maxpool 3x3/2 of the stem's raw convolution output `o` [N, H, W, C]: the normalised
+    map is never written.  bn: towers.BN.  Returns (pooled y, winning taps or None, (mean, rstd) or None)."""
+    n, h, w, c = o.shape
+    sc = bn.scratch()
+    lib = _lib.load()
+    saved = None
+    if training:
+        mean = torch.empty(c, dtype=torch.float32, device=o.device)
+        rstd = torch.empty(c, dtype=torch.float32, device=o.device)
+        _chk(lib.creamfl_bn_train_stats(_p(o), n * h * w, c, _p(bn.weight), _p(bn.bias), bn.eps, bn.momentum,
+                                        _p(bn.running_mean), _p(bn.running_var), _p(sc.sums), _p(mean), _p(rstd),
+                                        _p(sc.scale), _p(sc.shift), 0, _p(bn.num_batches_tracked), _stream()),
+             "bn_train_stats", 2)
+        saved = (mean, rstd)
+    else:
+        _chk(lib.creamfl_bn_eval_affine(c, _p(bn.weight), _p(bn.bias), bn.eps, _p(bn.running_mean), _p(bn.running_var),
+                                        _p(sc.scale), _p(sc.shift), _stream()), "bn_eval_affine", 1)
+    ho, wo = conv_out_hw(h, w, 3, 3, 2, 1)
+    y = torch.empty((n, ho, wo, c), dtype=BF16, device=o.device)
+    idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=o.device) if want_idx else None
+    _chk(lib.creamfl_maxpool_affine_fwd(_p(o), _p(sc.scale), _p(sc.shift), n, h, w, c, _p(y), _p(idx), _stream()),
+         "maxpool_affine_fwd")
+    return y, idx, saved
+
+
+def stem_tail_bwd(dy, idx, o, bn, saved, dgamma, dbeta):
+    """Backward of stem_tail_fwd: d(raw convolution output) from the pooled gradient; the 112 x 112 gradient map of the
+    pooling input is gathered on the fly inside the BatchNorm backward kernels."""
+    n, h, w, c = o.shape
+    mean, rstd = saved
+    sc = bn.scratch()
+    do = torch.empty_like(o)
+    _chk(_lib.load().creamfl_bn_pool_bwd(_p(dy), _p(idx), _p(o), n, h, w, c, _p(bn.weight), _p(bn.bias), _p(mean),
+                                         _p(rstd), _p(sc.sums), _p(sc.coef), _p(dgamma), _p(dbeta), _p(do), _stream()),
+         "bn_pool_bwd", 3)
+    return do
+
+
 def maxpool_bwd(dy, idx, x_shape):
     n, h, w, c = x_shape
     dx = torch.empty((n, h, w, c), dtype=BF16, device=dy.device)

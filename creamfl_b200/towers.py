@@ -449,19 +449,28 @@ class _StemFn(torch.autograd.Function):
             col = T.im2col_images(images, 7, 7, 2, 3, w16.shape[1])
             ho, wo = T.conv_out_hw(h, w, 7, 7, 2, 3)
             o = ops.gemm_bf16(col, w16).view(n, ho, wo, 64)
-        a, s = net.bn1.fwd(o)
-        y, idx = T.maxpool_fwd(a, want_idx=need)
+        # BatchNorm -> ReLU -> maxpool in one pass over the raw convolution output (the normalised 112 x 112 map is
+        # never written; the backward pass gathers the pooling gradient inside the BatchNorm backward kernels)
+        y, idx, s = T.stem_tail_fwd(o, net.bn1, net.bn1.training, want_idx=need)
         ctx.net = net
-        ctx.saved = (images if fused else col, fused, o, a, s, idx) if need else None
+        ctx.saved = (images if fused else col, fused, o, s, idx) if need else None
         return y
 
     @staticmethod
     def backward(ctx, dy):
         net = ctx.net
-        src, fused, o, a, s, idx = ctx.saved
+        src, fused, o, s, idx = ctx.saved
         ctx.saved = None
-        da = T.maxpool_bwd(dy.contiguous(), idx, a.shape)
-        do, _ = net.bn1.bwd(da, None, o, s, relu_from_x=True)
+        if s is None:
+            raise RuntimeError('BatchNorm backward needs a training-mode forward (batch statistics)')
+        if net.fused_stem_backward:
+            do = T.stem_tail_bwd(dy.contiguous(), idx, o, net.bn1, s, grad_target(net.bn1.weight),
+                                 grad_target(net.bn1.bias))
+        else:
+            # measured: gathering the pooling gradient inside BOTH BatchNorm backward passes costs more than writing the
+            # 112 x 112 gradient map once (client phase 389 -> 410 ms per mini-round), so the backward stays in two steps
+            da = T.maxpool_bwd(dy.contiguous(), idx, o.shape)
+            do, _ = net.bn1.bwd(da, None, o, s + (None,), relu_from_x=True)
         g = grad_target(net.conv1.weight)                         # [64, 147] fp32
         if fused:
             T.stem_wgrad(src, do, g)                              # patches re-assembled in shared memory from the images
@@ -522,6 +531,7 @@ class ResNet(nn.Module):
     final feature map NHWC bf16 out."""
 
     fold_eval_bn = True      # class-level switch (tests compare against the un-folded inference path)
+    fused_stem_backward = False   # creamfl_bn_pool_bwd (kept, tested; slower than maxpool backward + BatchNorm backward)
     CFG = {'resnet18': (BasicBlock, [2, 2, 2, 2]), 'resnet34': (BasicBlock, [3, 4, 6, 3]),
            'resnet50': (Bottleneck, [3, 4, 6, 3]), 'resnet101': (Bottleneck, [3, 4, 23, 3]),
            'resnet152': (Bottleneck, [3, 8, 36, 3])}

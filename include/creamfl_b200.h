@@ -209,6 +209,25 @@ int creamfl_bn_train_bwd_mask(const void* dy_bf16, const void* relu_mask, const 
                               const float* gamma, const float* mean, const float* rstd, double* sums, float* coef,
                               float* dgamma, float* dbeta, void* dx_bf16, void* g_out_bf16, void* stream);
 
+/* ---- fused tail of the ResNet stem: conv -> BatchNorm -> ReLU -> maxpool 3x3/2 (torchvision resnet.py via
+ * image_encoder.py:24) without ever writing the normalised 112 x 112 map.
+ *   forward : creamfl_bn_train_stats (batch statistics of the raw conv output + running-stat update + scale / shift;
+ *             creamfl_bn_eval_affine in inference mode), then creamfl_maxpool_affine_fwd:
+ *             y = maxpool(relu(scale * x + shift)), idx = winning tap per output element;
+ *   backward: creamfl_bn_pool_bwd = creamfl_bn_train_bwd with the ReLU gate recomputed from x, whose incoming gradient
+ *             is the max-pooling backward of dy_pooled gathered on the fly (x is the raw conv output [N, H, W, C]). */
+int creamfl_bn_train_stats(const void* x_bf16, int64_t P, int C, const float* gamma, const float* beta, float eps,
+                           float momentum, float* running_mean, float* running_var, double* sums, float* mean,
+                           float* rstd, float* scale, float* shift, int stats_ready, int64_t* num_batches_tracked,
+                           void* stream);
+int creamfl_bn_eval_affine(int C, const float* gamma, const float* beta, float eps, const float* running_mean,
+                           const float* running_var, float* scale, float* shift, void* stream);
+int creamfl_maxpool_affine_fwd(const void* x_bf16, const float* scale, const float* shift, int N, int H, int W, int C,
+                               void* y_bf16, void* idx_u8, void* stream);
+int creamfl_bn_pool_bwd(const void* dy_pooled_bf16, const void* idx_u8, const void* x_bf16, int N, int H, int W, int C,
+                        const float* gamma, const float* beta, const float* mean, const float* rstd, double* sums,
+                        float* coef, float* dgamma, float* dbeta, void* dx_bf16, void* stream);
+
 /* ---- 3x3 / stride 2 / pad 1 max pooling (ResNet stem); idx: one byte per output element */
 int creamfl_maxpool_fwd(const void* x_bf16, int N, int H, int W, int C, void* y_bf16, void* idx_u8, void* stream);
 int creamfl_maxpool_bwd(const void* dy_bf16, const void* idx_u8, int N, int H, int W, int C, void* dx_bf16,

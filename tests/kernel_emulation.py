@@ -415,6 +415,27 @@ def bn_eval_fwd(x, gamma, beta, running_mean, running_var, sc, eps, res=None, re
     return y.to(BF16)
 
 
+def stem_tail_fwd(o, bn, training, want_idx):
+    """creamfl_bn_train_stats / creamfl_bn_eval_affine + creamfl_maxpool_affine_fwd: maxpool(relu(BatchNorm(o)))."""
+    c = o.shape[-1]
+    if training:
+        a, mean, rstd = bn_train_fwd(o, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.scratch(), bn.eps,
+                                     bn.momentum, relu=True, num_batches_tracked=bn.num_batches_tracked)
+        saved = (mean, rstd)
+    else:
+        a, saved = bn_eval_fwd(o, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.scratch(), bn.eps, relu=True), None
+    y, idx = maxpool_fwd(a, want_idx=want_idx)
+    return y, idx, saved
+
+
+def stem_tail_bwd(dy, idx, o, bn, saved, dgamma, dbeta):
+    """creamfl_bn_pool_bwd: BatchNorm backward (ReLU gate from x) of the max-pooling backward of dy."""
+    mean, rstd = saved
+    da = maxpool_bwd(dy, idx, o.shape)
+    do, _ = bn_train_bwd(da, None, o, bn.weight, mean, rstd, bn.scratch(), dgamma, dbeta, beta=bn.bias, relu_from_x=True)
+    return do
+
+
 def bn_fold_layers(layers, row_start, total_rows, eps, pairs=None):
     """creamfl_bn_fold_layers: w_out[c, :] = w[c, :] * s_c, bias[c] = beta[c] - mean[c] * s_c (the table rows hold the
     addresses of exactly these tensors; the emulation walks the modules behind them)."""
@@ -567,7 +588,7 @@ _TOWER_OPS = ('wemb_gather', 'wemb_scatter', 'gru_fwd', 'gru_bwd', 'seq_pool_fwd
               'conv_dgrad', 'conv_wgrad', 'im2col_images', 'bn_train_fwd', 'bn_eval_fwd', 'bn_train_bwd', 'maxpool_fwd',
               'maxpool_bwd', 'embed_fwd', 'embed_bwd', 'attn_fwd', 'attn_bwd', 'pie_pool_fwd', 'pie_pool_bwd',
               'avgpool_fwd', 'avgpool_bwd', 'gemm_drop', 'stem_supported', 'stem_fprop', 'stem_wgrad', 'bn_fold_layers',
-              'conv_fprop_affine')
+              'conv_fprop_affine', 'stem_tail_fwd', 'stem_tail_bwd')
 
 
 def install(monkeypatch, exact=False):

@@ -316,3 +316,49 @@ def test_fused_stem_refuses_wide_images(T):
     assert not T.stem_supported(300, 300) and not T.stem_supported(64, 130)     # rows travel as 16-byte chunks
     with pytest.raises(RuntimeError):
         T.stem_fprop(torch.randn(1, 3, 300, 300).cuda(), torch.zeros(64, 152, dtype=torch.bfloat16).cuda())
+
+
+@pytest.mark.parametrize('shape,training', [((4, 112, 112, 64), True), ((3, 32, 32, 64), True), ((2, 14, 10, 64), True),
+                                            ((4, 112, 112, 64), False)])
+def test_fused_stem_tail_matches_unfused_sequence(T, shape, training):
+    """creamfl_bn_train_stats / _eval_affine + creamfl_maxpool_affine_fwd and creamfl_bn_pool_bwd against the separate
+    passes they replace (BatchNorm apply + ReLU -> maxpool; maxpool backward -> BatchNorm backward with the gate from
+    x).  Forward: the un-fused path rounds the normalised map to bf16 before pooling, the fused one pools fp32 values:
+    equal up to one bf16 rounding (rel-L2 4e-3), winning taps equal except near-ties (< 0.5 %).  Backward: the
+    un-fused path rounds the up-sampled gradient to bf16, rel-L2 6e-3; parameter gradients 2e-3."""
+    from creamfl_b200 import towers
+    n, h, w, c = shape
+    x = (rnd(*shape, seed=51, scale=1.5) + 0.25).cuda()
+    bn_a, bn_b = towers.BN(c).cuda(), towers.BN(c).cuda()
+    g = torch.Generator().manual_seed(52)
+    for bn in (bn_a, bn_b):
+        bn.weight.data.copy_(torch.rand(c, generator=torch.Generator().manual_seed(53)) + 0.5)
+        bn.bias.data.copy_(torch.randn(c, generator=torch.Generator().manual_seed(54)) * 0.2)
+        bn.running_mean.copy_(torch.randn(c, generator=torch.Generator().manual_seed(55)) * 0.1)
+        bn.running_var.copy_(torch.rand(c, generator=torch.Generator().manual_seed(56)) + 0.5)
+        bn.train(training)
+    # un-fused reference sequence
+    if training:
+        a, mean, rstd = T.bn_train_fwd(x, bn_a.weight, bn_a.bias, bn_a.running_mean, bn_a.running_var, bn_a.scratch(),
+                                       bn_a.eps, bn_a.momentum, relu=True, num_batches_tracked=bn_a.num_batches_tracked)
+    else:
+        a = T.bn_eval_fwd(x, bn_a.weight, bn_a.bias, bn_a.running_mean, bn_a.running_var, bn_a.scratch(), bn_a.eps, relu=True)
+    y_ref, idx_ref = T.maxpool_fwd(a, want_idx=True)
+    y, idx, saved = T.stem_tail_fwd(x, bn_b, training, want_idx=True)
+    assert rel_l2(y, y_ref) < 4e-3
+    assert (idx != idx_ref).float().mean().item() < 5e-3
+    if not training:
+        assert saved is None
+        return
+    assert torch.equal(saved[0], mean) and torch.equal(saved[1], rstd)
+    assert torch.equal(bn_a.running_var, bn_b.running_var) and int(bn_b.num_batches_tracked) == 1
+    dy = rnd(*y.shape, seed=57).cuda()
+    dg_ref, db_ref = torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
+    da = T.maxpool_bwd(dy, idx, a.shape)                 # same winning taps on both sides
+    do_ref, _ = T.bn_train_bwd(da, None, x, bn_a.weight, mean, rstd, bn_a.scratch(), dg_ref, db_ref, beta=bn_a.bias,
+                               relu_from_x=True)
+    dg, db = torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
+    do = T.stem_tail_bwd(dy, idx, x, bn_b, saved, dg, db)
+    assert rel_l2(do, do_ref) < 6e-3
+    assert rel_l2(dg, dg_ref) < 2e-3 and rel_l2(db, db_ref) < 2e-3
+    assert torch.count_nonzero(bn_b.scratch().sums) == 0
