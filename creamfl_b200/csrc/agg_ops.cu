@@ -159,13 +159,16 @@ recall_tile_kernel(const float* __restrict__ Q, const float* __restrict__ G, con
       }
     } else {
       int bits = q_ok ? best_bits[q] : 0;
+      // no positive in the gallery (the reference's evaluator raises there): every gallery item outranks the missing
+      // positive, rank = Ng - never a silent perfect hit
+      const bool none = bits == (int)0x80000000;
       bits = bits >= 0 ? bits : bits ^ 0x7fffffff;
       const float best = __int_as_float(bits);
       int cnt = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int g = g0 + tx * 4 + j;
-        if (q_ok && g < Ng && acc[i][j] > best) ++cnt;
+        if (q_ok && g < Ng && (none || acc[i][j] > best)) ++cnt;
       }
       // 16 threads (tx) share a query row inside a half-warp: reduce before the atomic
 #pragma unroll

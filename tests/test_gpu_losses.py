@@ -292,3 +292,14 @@ def test_recall_coco1k_shape_vs_oracle(ops, O):
         a, b = O.recall_scores(want), O.recall_scores(got)
         for k in ('recall_1', 'recall_5', 'recall_10'):
             assert abs(a[k] - b[k]) <= 0.2
+
+
+def test_recall_query_without_positive_ranks_last(ops):
+    """A query whose label has no match in the gallery gets rank Ng (worse than every hit), not a silent rank 0 - the
+    reference's evaluator raises there (eval_coco.py:311-317 indexes an empty np.where)."""
+    g = torch.Generator().manual_seed(3)
+    q, gal = unit(torch.randn(70, 64, generator=g)).cuda(), unit(torch.randn(150, 64, generator=g)).cuda()
+    ql, gl = torch.arange(70), torch.arange(150) % 60           # labels 60..69 never occur in the gallery
+    ranks = ops.recall_ranks(q, gal, ql.cuda(), gl.cuda()).cpu()
+    assert bool((ranks[60:] == 150).all()) and bool((ranks[:60] < 150).all())
+
