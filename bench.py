@@ -641,6 +641,9 @@ def run_ours(args):
                             f'algorithmic FLOPs of all its launches / their summed CUDA-event time)',
                             'achieved': round(ach, 1), 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': round(ach / peak_tf, 4),
                             'traffic': ncu_traffic_bytes(ROOT / 'profiles' / 'r02_ncu_dominant.csv'),
+                            'traffic_of': 'one launch of the family\'s top kernel by time, gemm_tc_kernel<256,1,1,0,0,1,2> '
+                                          '(split-K weight gradient 1024x256x25088, 65.3 MB algorithmic: both operands '
+                                          'once + the fp32 output), ncu --set full capture profiles/r02_ncu_dominant.csv',
                             'avg_launch_ms': round(tc[dom]['ms'] / tc[dom]['calls'], 4),
                             'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback'}
         if 'bn' in fam:

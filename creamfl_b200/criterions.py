@@ -76,7 +76,22 @@ class MCSoftContrastiveLoss(nn.Module):
         self.num_samples = get('num_samples', 1)
 
     def match_prob(self, image_features, caption_features, image_logsigma=None, caption_logsigma=None, **kw):
-        raise NotImplementedError('match_prob is not on the training hot path')
+        """probemb.py:210-219 (+ batchwise_cdist :7-45): matching probability sigma(-a d + b) with the reference's
+        sigma(x) = e^x / (e^x + e^-x), averaged over the K x K embedding pairs of each row.  Inputs [N, K, D] (2-D
+        inputs mean K = 1); the row counts must be equal or one of them 1 (a query broadcast against the gallery, the
+        way MatchingProbModule calls it, eval_coco.py:66-69).  Evaluation-only and not on the hot path (both yaml
+        configurations evaluate with 'matmul'): a handful of device tensor ops, no kernel of its own.  Written as
+        sigmoid(2x), which equals the reference's quotient wherever that does not overflow to inf / inf."""
+        a, b = image_features, caption_features
+        if a.dim() != 3 or b.dim() != 3:
+            a, b = a.unsqueeze(1), b.unsqueeze(1)
+        na, nb = a.size(0), b.size(0)
+        if not (na == nb or na == 1 or nb == 1):
+            raise RuntimeError(f'samples1 ({a.size()}) and samples2 ({b.size()}) dimensionalities '
+                               'are non-broadcastable.')
+        dist = torch.sqrt(((a.unsqueeze(1) - b.unsqueeze(2)) ** 2).sum(-1) + 1e-6).reshape(max(na, nb), -1)
+        logits = -self.negative_scale * dist.to(self.negative_scale.device).float() + self.shift
+        return torch.sigmoid(2.0 * logits).mean(dim=1)
 
     def forward(self, image_features, caption_features, image_logsigma=None, caption_logsigma=None, **kwargs):
         loss, parts = ops.pcme_loss(image_features, caption_features, self.shift, self.negative_scale)

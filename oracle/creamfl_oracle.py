@@ -70,6 +70,20 @@ def pcme_loss(img, txt, shift, negative_scale) -> Tuple[torch.Tensor, Dict[str, 
     return loss, info
 
 
+def pcme_match_prob(a: torch.Tensor, b: torch.Tensor, shift, negative_scale, eps: float = 1e-6) -> torch.Tensor:
+    """reference src/criterions/probemb.py:210-219 over batchwise_cdist (:7-45): a, b are [N, K, D] (2-D: K = 1) with
+    equal row counts or one of them 1; distance [N, K*K] rounded to fp32 as the reference does (:215), probability
+    e^l / (e^l + e^-l) of l = -scale * d + shift, mean over the K*K pairs."""
+    if a.dim() != 3 or b.dim() != 3:
+        a, b = a.unsqueeze(1), b.unsqueeze(1)
+    if not (a.size(0) == b.size(0) or a.size(0) == 1 or b.size(0) == 1):
+        raise RuntimeError('non-broadcastable')
+    n = max(a.size(0), b.size(0))
+    dist = torch.sqrt(((a.unsqueeze(1) - b.unsqueeze(2)) ** 2).sum(-1) + eps).view(n, -1).float()
+    logits = -negative_scale * dist + shift
+    return (torch.exp(logits) / (torch.exp(logits) + torch.exp(-logits))).mean(dim=1)
+
+
 # ------------------------------------------------------------------------------------------------- contrast
 def inter_infonce(q: torch.Tensor, bank: torch.Tensor, labels: torch.Tensor, tau: float = 0.5) -> torch.Tensor:
     """reference MMClientTrainer.py:194-200 / ClientTrainer.py:388,398-401:

@@ -10,6 +10,11 @@ import torch
 from creamfl_b200.engine import UnimodalClient
 from creamfl_b200.partition import distill_lookup
 
+try:                                                    # imported as the package src.algorithms
+    from .. import losses
+except (ImportError, ValueError):                       # `python src/main.py`: src/ itself is on the path
+    import losses
+
 
 class ClientTrainer:
     def __init__(self, args, dataset, dst, RGBmean, RGBstdv, data_dict, logger, global_test_set=None, inter_distance=4,
@@ -23,6 +28,7 @@ class ClientTrainer:
         self.local_epochs, self.local_epoch, self.cur_epoch = args.local_epochs, 0, 0
         self.classSize = {'Cifar100': 100, 'Cifar10': 10, 'AG_NEWS': 4, 'YelpReviewPolarity': 2}[dataset]
         self.is_image = dataset in ('Cifar100', 'Cifar10')
+        self.loss = loss
         self.setModel()
 
     def setModel(self):
@@ -32,6 +38,7 @@ class ClientTrainer:
                                     interintra_weight=self.args.interintra_weight, inter_distance=self.inter_distance,
                                     device=self.device, use_graphs=not getattr(self.args, 'no_cuda_graphs', True))
         self.model, self.optimizer = self._core.model, self._core.optimizer
+        self.criterion = losses.create(self.loss)           # :280,284; the engine's steps call the same kernel fused
 
     def lr_scheduler(self, epoch):
         """ClientTrainer.py:291-302 (FusedOptimizer reads param_groups['lr'] before every step / graph replay)."""

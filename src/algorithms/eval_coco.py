@@ -17,6 +17,8 @@ def recall_at_k(ranks, k):
 
 class COCOEvaluator:
     def __init__(self, eval_method='matmul', verbose=False, eval_device='cuda', n_crossfolds=5):
+        if eval_method not in ('matmul', 'matching_prob'):
+            raise ValueError(f'unknown eval_method {eval_method!r} (matmul | matching_prob, eval_coco.py:78)')
         self.eval_method, self.verbose, self.eval_device, self.n_crossfolds = eval_method, verbose, eval_device, n_crossfolds
         self.model = self.criterion = self.logger = None
 
@@ -55,13 +57,34 @@ class COCOEvaluator:
         if len(g_features) != len(g_labels):
             raise RuntimeError('length mismatch {}, {}'.format(g_features.shape, g_labels.shape))
         dev = q_features.device
-        ranks = ops.recall_ranks(q_features.float(), g_features.float(), q_labels.to(dev), g_labels.to(dev))
+        if self.eval_method == 'matching_prob':
+            ranks = self._ranks_by_matching_prob(q_features, g_features, q_labels.to(dev), g_labels.to(dev))
+        else:
+            ranks = ops.recall_ranks(q_features.float(), g_features.float(), q_labels.to(dev), g_labels.to(dev))
         best = ranks.cpu().numpy().astype(np.float64)
         scores = {'recall_1': recall_at_k(best, 1), 'recall_5': recall_at_k(best, 5), 'recall_10': recall_at_k(best, 10)}
         scores['rsum'] = scores['recall_1'] + scores['recall_5'] + scores['recall_10']
         scores['medr'] = float(np.floor(np.median(best)) + 1)
         scores['meanr'] = float(np.mean(best) + 1)
         return scores
+
+    def _ranks_by_matching_prob(self, q, g, q_labels, g_labels, chunk=64):
+        """eval_method 'matching_prob' (MatchingProbModule, eval_coco.py:54-72; neither yaml uses it): similarities are
+        criterion.match_prob(query, gallery); rank of the best positive = gallery items with a strictly higher
+        probability, the same rule as the rank kernel.  Plain device tensor ops, `chunk` queries at a time."""
+        if self.criterion is None:
+            raise RuntimeError("eval_method 'matching_prob' needs set_criterion()")
+        ranks = torch.empty(len(q), dtype=torch.int32, device=q.device)
+        gk = g if g.dim() == 3 else g.unsqueeze(1)
+        for s in range(0, len(q), chunk):
+            qs = q[s:s + chunk]
+            qk = qs if qs.dim() == 3 else qs.unsqueeze(1)
+            sims = torch.stack([self.criterion.match_prob(one.unsqueeze(0), gk, None, None) for one in qk])
+            pos = q_labels[s:s + chunk, None] == g_labels[None, :]
+            best = sims.masked_fill(~pos, float('-inf')).max(dim=1, keepdim=True).values
+            r = (sims > best).sum(dim=1).to(torch.int32)
+            ranks[s:s + chunk] = torch.where(pos.any(dim=1), r, torch.full_like(r, len(g)))
+        return ranks
 
     def evaluate_n_fold(self, extracted, n_crossfolds, n_images_per_crossfold, n_captions_per_crossfold):
         """eval_coco.py:336-390: COCO-1K protocol - average over folds of 1000 images / 5000 captions."""

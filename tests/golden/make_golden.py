@@ -514,8 +514,33 @@ def case_text_towers():
     np.savez_compressed(OUT / 'text_towers.npz', **out)
 
 
+def case_match_prob():
+    """criterion.match_prob (probemb.py:210-219) the way MatchingProbModule calls it (eval_coco.py:66-69): one query
+    [1, K, D] broadcast against the gallery [Ng, K, D], K = n_embeddings; plus the same-N and 2-D call forms."""
+    from criterions.probemb import MCSoftContrastiveLoss
+    out = {}
+    for tag, (nq, ng, k, d, s, b) in {'a': (1, 12, 3, 16, 15.0, 15.0), 'b': (7, 7, 2, 8, 3.0, 2.0),
+                                       'c': (9, 1, 1, 32, 5.0, 4.0)}.items():
+        g = torch.Generator().manual_seed(700 + ng)
+        q = unit(torch.randn(nq, k, d, generator=g, dtype=torch.float64))
+        gal = unit(torch.randn(ng, k, d, generator=g, dtype=torch.float64))
+        crit = MCSoftContrastiveLoss(Munch(init_shift=b, init_negative_scale=s, num_samples=k)).double()
+        with torch.no_grad():
+            prob = crit.match_prob(q, gal, None, None)
+        out.update({f'{tag}_q': q.numpy(), f'{tag}_g': gal.numpy(), f'{tag}_shift': np.float64(b),
+                    f'{tag}_scale': np.float64(s), f'{tag}_prob': prob.numpy()})
+    g = torch.Generator().manual_seed(77)
+    q2, g2 = unit(torch.randn(6, 16, generator=g, dtype=torch.float64)), unit(torch.randn(6, 16, generator=g, dtype=torch.float64))
+    crit = MCSoftContrastiveLoss(Munch(init_shift=1.5, init_negative_scale=2.5, num_samples=1)).double()
+    with torch.no_grad():
+        out.update({'d_q': q2.numpy(), 'd_g': g2.numpy(), 'd_shift': np.float64(1.5), 'd_scale': np.float64(2.5),
+                    'd_prob': crit.match_prob(q2, g2, None, None).numpy()})
+    np.savez_compressed(OUT / 'match_prob.npz', **out)
+
+
 CASES = {'towers': case_towers, 'text_towers': case_text_towers, 'pcme': case_pcme, 'mm_contrast': case_mm_contrast, 'uni_contrast': case_uni_contrast,
-         'recall': case_recall, 'partition': case_partition, 'conw': case_conw}
+         'recall': case_recall, 'partition': case_partition, 'conw': case_conw,
+         'match_prob': case_match_prob}
 
 if __name__ == '__main__':
     install_shims()

@@ -307,3 +307,18 @@ def test_adamp_projection_known_answer():
     assert O.adamp_step([p3], [g3], [m3], [v3], 1, lr, (0.9, 0.999), eps, wd, delta, wd_ratio) == [0]
     exp3 = w * (1 - lr * wd) - lr * g3 / (g3.abs() + eps)
     assert float((p3 - exp3).abs().max()) < 1e-15
+
+
+@pytest.mark.parametrize('tag', ['a', 'b', 'c', 'd'])
+def test_match_prob(golden, tag):
+    """criterion.match_prob of the reference (probemb.py:210-219), query-broadcast / same-N / gallery-of-one / 2-D."""
+    g = golden('match_prob')
+    shift = torch.tensor([float(g[f'{tag}_shift'])], dtype=torch.float64)
+    scale = torch.tensor([float(g[f'{tag}_scale'])], dtype=torch.float64)
+    prob = O.pcme_match_prob(T(g[f'{tag}_q']), T(g[f'{tag}_g']), shift, scale)
+    np.testing.assert_allclose(prob.numpy(), g[f'{tag}_prob'], rtol=1e-12, atol=0)
+
+
+def test_match_prob_rejects_non_broadcastable():
+    with pytest.raises(RuntimeError):
+        O.pcme_match_prob(torch.zeros(3, 2, 4), torch.zeros(2, 2, 4), torch.ones(1), torch.ones(1))
