@@ -119,6 +119,61 @@ def test_exchange_gloo_world2_matches_single_process_oracle():
         np.testing.assert_allclose(grad, np.full(5, 1.5))                       # mean of the rank gradients
 
 
+def _worker_absent_slots(rank, world, port, n, d, q):
+    """configs[2] on two ranks: each hosts 3 client slots, some without the modality (image-only / text-only clients
+    return None for the other one, ClientTrainer.py:622-629)."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sys.path.insert(0, str(ROOT / 'tests'))
+    import kernel_emulation as KE
+    from creamfl_b200 import engine, ops
+    from conftest import conw_inputs
+    for name in ('conw_score', 'conw_reduce', 'to_bf16'):         # test-only CPU stand-ins of the CUDA wrappers
+        setattr(ops, name, getattr(KE, name))
+    g_img, g_txt, vecs, _ = conw_inputs(23, n, d, 4)
+    layout = [[True, False, True], [False, False, True]]         # slot 1 is empty on every rank: it must not travel
+    clients = {(0, 0): 0, (0, 2): 1, (1, 2): 2}
+    own = [torch.from_numpy(vecs[clients[(rank, s)]]) if layout[rank][s] else None for s in range(3)]
+    g16 = torch.from_numpy(g_txt).to(torch.bfloat16)
+    agg_given = engine.exchange_and_aggregate_clients(own, g16, layout)
+    agg_found = engine.exchange_and_aggregate_clients(own, g16)          # layout exchanged by the function itself
+    none = engine.exchange_and_aggregate_clients([None, None, None], g16)
+    try:
+        engine.exchange_and_aggregate_clients(own, g16, [[True, True, True], [True, True, True]])
+        mismatch = False
+    except ValueError:
+        mismatch = True
+    q.put((rank, agg_given.numpy(), agg_found.numpy(), none is None, mismatch))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exchange_with_absent_modality_slots_gloo_world2():
+    """BASELINE configs[2] (image-only + text-only clients): the exchange aggregates over the clients that carry the
+    modality, wherever they are hosted (MMFL.py:226-247,298-331) - equal to the single-process aggregation of exactly
+    those clients."""
+    sys.path.insert(0, str(ROOT / 'tests'))
+    import kernel_emulation as KE
+    from conftest import conw_inputs
+    n, d, world = 256, 32, 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_absent_slots, args=(r, world, port, n, d, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g_img, g_txt, vecs, _ = conw_inputs(23, n, d, 4)
+    want = KE.conw_aggregate([torch.from_numpy(vecs[c]) for c in (0, 1, 2)], torch.from_numpy(g_txt)).numpy()
+    for rank, agg_given, agg_found, none_is_none, mismatch in results:
+        np.testing.assert_allclose(agg_given, want, rtol=1e-5, atol=1e-7)
+        np.testing.assert_array_equal(agg_given, agg_found)
+        assert none_is_none and mismatch
+
+
 def test_split_k_planner_fills_whole_waves():
     """Host logic of the accumulating (weight-gradient) GEMMs: `creamfl_plan_split_k` must return a distinct
     partition of the k-blocks (>= 4 per unit) whose tiles * split units fill whole waves of the 148 SMs on the shapes
