@@ -5,7 +5,9 @@ operation that creamfl_b200 implements in CUDA.  It exists so that tests can che
 product (creamfl_b200/, src/) may import it.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 `--impl reference` legs use it.
 
-Parity pinning: the reference ships no tests or golden vectors, so the oracle is pinned
+Parity pinning: the reference ships no tests; its only golden artefacts are index fixtures, of which
+data_partition/client_noniid_flicker30k.pkl is reproducible without a dataset - shard_partition() below and the
+product's reproduce it bit for bit (tests/test_cpu_partition.py).  Everything else is pinned
 against outputs of the reference's own modules executed in the build container: tests/golden/make_golden.py imports
 /root/reference (with import shims for packages absent from the image) and writes tests/golden/*.npz;
 tests/test_oracle_golden.py checks every function below against those files.  Functions whose reference code is

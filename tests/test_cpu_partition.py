@@ -24,6 +24,22 @@ def test_flickr_shards_bit_exact(golden):
     assert O.partition_digest(part) == str(g['f30k_sha256'])
 
 
+def test_flickr_shards_reproduce_the_fixture_the_reference_ships(golden):
+    """/root/reference/data_partition/client_noniid_flicker30k.pkl is the one index fixture of the reference that does
+    not depend on a dataset (flickr30k.py:79-102 needs only len(data) = 145 000 and numpy's legacy RNG at seed 2021):
+    its sha256 - taken over the pickle's own arrays by tests/golden/make_golden.py - must come out of the product's
+    and the oracle's shard partition.  (The CIFAR-100 / AG_NEWS fixtures were drawn from the real datasets' label
+    vectors, which are not on the box; their hashes are recorded in the golden file for a maintainer who has them.)"""
+    g = golden('partition')
+    shipped = str(g['fixture_client_noniid_flicker30k_sha256'])
+    assert shipped.startswith('fcd3455d84de4a2b')
+    assert list(g['fixture_client_noniid_flicker30k_sizes']) == [9660] * 14 + [9760]
+    assert O.partition_digest(P.shard_partition(145000, 15, 150, seed=2021)) == shipped
+    assert O.partition_digest(O.shard_partition(145000, 15, 150, seed=2021)) == shipped
+    for name, n in (('client_cifar100_noniid', 50000), ('client_AG_NEWS_noniid', 120000)):
+        assert int(g[f'fixture_{name}_sizes'].sum()) == n and len(g[f'fixture_{name}_sizes']) == 10
+
+
 def test_distill_lookup_matches_dict_semantics():
     rng = np.random.default_rng(0)
     distill_index = rng.permutation(5000)[:777].tolist()
