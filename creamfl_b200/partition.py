@@ -4,9 +4,12 @@ like the reference, so the index tensors are bit-identical):
   data_partitioner   - src/datasets/load_FL_datasets.py:79-122 ("hetero" Dirichlet, "homo"), without the pickle cache
   shard_partition    - src/datasets/flickr30k.py:79-102 (150 shards, 10 per client, leftovers to the last client)
   distill_lookup     - {dataset index -> row} of MMFL.py:343 / MMClientTrainer.py:152 as an int64 lookup table
+  public_subset_indices - src/utils/load_datasets.py:148-157: the sorted public subset of the 566 435 COCO training
+                       captions (Python's `random` at seed 2021 reproduces the `coco_subset_idx_file` the reference ships)
 """
 from __future__ import annotations
 
+import random
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -69,6 +72,22 @@ def shard_partition(n_items: int, num_users: int = 15, num_shards: int = 150,
             left = list(set(left) - set(block))
     users[last] = np.concatenate([users[last], left])
     return users
+
+
+COCO_TRAIN_CAPTIONS = 566435          # len(CocoCaptionsCap) of the training split (load_datasets.py:150)
+
+
+def public_subset_indices(subset_num: int = 50000, n_total: int = COCO_TRAIN_CAPTIONS, seed: int = 2021) -> List[int]:
+    """load_datasets.py:148-157: shuffle range(n_total) with Python's Mersenne Twister, keep the first `subset_num`,
+    sort.  With the defaults this IS the `coco_subset_idx_file` of the reference repository (sha256 of the int64
+    bytes 8ffcd824...; tests/test_cpu_partition.py) - the reference draws it once with whatever state `random` is in
+    and pickles it; the shipped file corresponds to seed 2021.  A private generator is used, the global `random`
+    state is left alone."""
+    if not 0 < subset_num <= n_total:
+        raise ValueError(f'public_subset_indices: subset_num {subset_num} outside (0, {n_total}]')
+    full = list(range(n_total))
+    random.Random(seed).shuffle(full)
+    return sorted(full[:subset_num])
 
 
 def distill_lookup(distill_index: Sequence[int], device=None) -> torch.Tensor:

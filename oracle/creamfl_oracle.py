@@ -6,8 +6,9 @@ product (creamfl_b200/, src/) may import it.  Only tests/, __graft_entry__.smoke
 `--impl reference` legs use it.
 
 Parity pinning: the reference ships no tests; its only golden artefacts are index fixtures, of which
-data_partition/client_noniid_flicker30k.pkl is reproducible without a dataset - shard_partition() below and the
-product's reproduce it bit for bit (tests/test_cpu_partition.py).  Everything else is pinned
+data_partition/client_noniid_flicker30k.pkl and coco_subset_idx_file are reproducible without a dataset -
+shard_partition() / public_subset_indices() below and the product's reproduce them bit for bit
+(tests/test_cpu_partition.py).  Everything else is pinned
 against outputs of the reference's own modules executed in the build container: tests/golden/make_golden.py imports
 /root/reference (with import shims for packages absent from the image) and writes tests/golden/*.npz;
 tests/test_oracle_golden.py checks every function below against those files.  Functions whose reference code is
@@ -231,6 +232,20 @@ def hetero_partition(dataset: str, num_samples: int, num_nets: int, alpha: float
         np.random.shuffle(idx_batch[j])
         out[j] = idx_batch[j]
     return out
+
+
+def public_subset_indices(subset_num: int = 50000, n_total: int = 566435, seed: int = 2021) -> List[int]:
+    """reference src/utils/load_datasets.py:148-157 (`random.shuffle(full_idx); idx = full_idx[0:50000]; idx.sort()`),
+    seeded; seed 2021 gives the coco_subset_idx_file the reference ships."""
+    import random
+    keep = random.getstate()
+    random.seed(seed)
+    full_idx = [i for i in range(n_total)]
+    random.shuffle(full_idx)
+    random.setstate(keep)                      # the oracle leaves the caller's global RNG as it found it
+    idx = full_idx[0:subset_num]
+    idx.sort()
+    return idx
 
 
 def partition_digest(part: Dict[int, Sequence[int]]) -> str:

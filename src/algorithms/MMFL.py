@@ -13,7 +13,7 @@ import time
 import torch
 
 from creamfl_b200 import engine as _engine, ops
-from creamfl_b200.partition import data_partitioner, distill_lookup, shard_partition
+from creamfl_b200.partition import data_partitioner, distill_lookup, public_subset_indices, shard_partition
 
 from .ClientTrainer import ClientTrainer
 from .MMClientTrainer import MMClientTrainer
@@ -67,8 +67,7 @@ class MMFL:
         """MMFL.py:90-114.  Public subset = `pub_data_num` pairs; test = COCO-1K shape folds."""
         n = args.pub_data_num
         bs = getattr(args, 'pub_batch_size', 128)
-        g = torch.Generator().manual_seed(2021)
-        subset = torch.sort(torch.randperm(566418, generator=g)[:n]).values.tolist()    # sorted ids like coco_subset_idx_file
+        subset = public_subset_indices(n)         # load_datasets.py:148-157; n = 50000: the shipped coco_subset_idx_file
         self.dataloaders_global = {
             f'train_subset_{n}': SyntheticPairs(subset, bs, seed=1, shuffle=True, image_size=args.image_size),
             f'train_subset_eval_{n}': SyntheticPairs(subset, 2 * bs, seed=1, image_size=args.image_size),

@@ -40,6 +40,24 @@ def test_flickr_shards_reproduce_the_fixture_the_reference_ships(golden):
         assert int(g[f'fixture_{name}_sizes'].sum()) == n and len(g[f'fixture_{name}_sizes']) == 10
 
 
+def test_public_subset_is_the_coco_subset_idx_file_the_reference_ships(golden):
+    """/root/reference/coco_subset_idx_file (50 000 sorted caption indices, load_datasets.py:148-157): sha256 of its
+    int64 bytes recorded by tests/golden/make_golden.py; product and oracle reproduce the file bit for bit."""
+    import hashlib
+    g = golden('partition')
+    want = str(g['fixture_coco_subset_sha256'])
+    assert want.startswith('8ffcd8243cd86772') and int(g['fixture_coco_subset_len']) == 50000        # SURVEY.md 8c
+    sha = lambda idx: hashlib.sha256(np.asarray(idx, dtype=np.int64).tobytes()).hexdigest()
+    mine = P.public_subset_indices()
+    assert len(mine) == 50000 and mine == sorted(mine) and mine[:8] == [9, 20, 33, 46, 76, 90, 97, 99]
+    assert sha(mine) == want
+    assert sha(O.public_subset_indices()) == want
+    small = P.public_subset_indices(256)
+    assert len(set(small)) == 256 and small == sorted(small) and max(small) < P.COCO_TRAIN_CAPTIONS
+    with pytest.raises(ValueError):
+        P.public_subset_indices(0)
+
+
 def test_distill_lookup_matches_dict_semantics():
     rng = np.random.default_rng(0)
     distill_index = rng.permutation(5000)[:777].tolist()
