@@ -16,10 +16,27 @@ except (ImportError, ValueError):                       # `python src/main.py`: 
     import losses
 
 
+def seed_torch(seed=2021):
+    """ClientTrainer.py:35-41."""
+    import os
+    import random
+    import numpy as np
+    random.seed(seed)
+    os.environ['PYTHONHASHSEED'] = str(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
 class ClientTrainer:
     def __init__(self, args, dataset, dst, RGBmean, RGBstdv, data_dict, logger, global_test_set=None, inter_distance=4,
                  loss='softmax', gpuid='cuda:0', num_epochs=30, init_lr=0.0001, decay=0.1, batch_size=512, imgsize=256,
                  num_workers=4, print_freq=10, save_step=10, scale=128, pool_type='max_avg', client_id=-1, wandb=None):
+        # ClientTrainer.py:140 - every unimodal client re-seeds ALL global generators to 2021 in its constructor: clients
+        # of one type start from identical weights, and the per-round `random.sample` of MMFL.py:191 no longer depends
+        # on --seed once a unimodal client exists (SURVEY.md appendix B); kept, because it decides who trains when
+        seed_torch()
         self.args, self.dset_name, self.logger, self.client_idx = args, dataset, logger, client_id
         self.train_loader = data_dict
         self.device = torch.device(gpuid)
