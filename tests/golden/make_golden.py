@@ -538,9 +538,34 @@ def case_match_prob():
     np.savez_compressed(OUT / 'match_prob.npz', **out)
 
 
+def case_uni_lr():
+    """ClientTrainer.lr_scheduler (ClientTrainer.py:291-302) called the way run() does (:198, with the round number a
+    selected client is handed, MMFL.py:229): learning rate of the SGD optimizer after every call, for a client that
+    trains every round and for one that is selected only now and then (the decay flags fire once each, late)."""
+    import io
+    import contextlib
+    import src.algorithms.ClientTrainer as CT
+    out = {}
+    for tag, epochs in {'every': list(range(30)), 'sparse': [0, 3, 14, 16, 23, 25, 29], 'late': [27, 28],
+                        'short': list(range(10))}.items():
+        tr = CT.ClientTrainer.__new__(CT.ClientTrainer)
+        tr.num_epochs = 10 if tag == 'short' else 30
+        tr.init_lr, tr.decay_rate, tr.decay_time = 1e-4, 0.1, [False, False]
+        tr.optimizer = torch.optim.SGD([nn.Parameter(torch.zeros(1))], lr=tr.init_lr, momentum=0.9, weight_decay=5e-5)
+        lrs = []
+        for e in epochs:
+            with contextlib.redirect_stdout(io.StringIO()):
+                tr.lr_scheduler(e)
+            lrs.append(tr.optimizer.param_groups[0]['lr'])
+        out[f'{tag}_epochs'] = np.asarray(epochs, dtype=np.int64)
+        out[f'{tag}_num_epochs'] = np.int64(tr.num_epochs)
+        out[f'{tag}_lr'] = np.asarray(lrs, dtype=np.float64)
+    np.savez_compressed(OUT / 'uni_lr.npz', **out)
+
+
 CASES = {'towers': case_towers, 'text_towers': case_text_towers, 'pcme': case_pcme, 'mm_contrast': case_mm_contrast, 'uni_contrast': case_uni_contrast,
          'recall': case_recall, 'partition': case_partition, 'conw': case_conw,
-         'match_prob': case_match_prob}
+         'match_prob': case_match_prob, 'uni_lr': case_uni_lr}
 
 if __name__ == '__main__':
     install_shims()
