@@ -82,6 +82,49 @@ def test_one_round_two_clients_on_cpu(monkeypatch, tmp_path):
         assert t._core.old_model is not None and t.local_epoch == 1
 
 
+def test_one_round_image_text_and_multimodal_client_on_cpu(monkeypatch, tmp_path):
+    """The mix tests/test_gpu_round.py runs on the GPU through `python src/main.py` (one CIFAR-shape image client, one
+    AG_NEWS-shape text client, one multimodal client), here through the same orchestrator on the CPU: unimodal
+    trainers (ClientTrainer.run / generate_logits with an absent modality), con_w over the clients that carry each
+    modality, distillation with the per-client-type term counts (2 + 2 with all three types, MMFL.py:361-378)."""
+    KE.install_engine(monkeypatch)
+    import random
+    random.seed(0)
+    torch.manual_seed(0)
+    MMFL = _mmfl()
+    args = _args(name=str(tmp_path / 'mix'), num_img_clients=1, num_txt_clients=1, num_mm_clients=1,
+                 client_num_per_round=3, private_samples=3000, client_image_size=32)
+    algo = MMFL(args, None)
+    algo.create_model(args)
+    algo.load_dataset(args)
+    for t in algo.total_local_trainers:                  # one private batch of 16 per client: a plumbing run
+        t.train_loader.indices = t.train_loader.indices[:16]
+        t.train_loader.batch_size = 16
+    kinds = [type(t).__name__ for t in algo.total_local_trainers]
+    assert kinds == ['ClientTrainer', 'ClientTrainer', 'MMClientTrainer']
+    assert [t.client_idx for t in algo.total_local_trainers] == [1, 2, 3]
+    # the public subset comes from the reference's index producer (sorted caption indices below 566 435)
+    pub = algo.dataloaders_global['train_subset_16'].indices
+    assert pub == sorted(pub) and len(set(pub)) == 16 and max(pub) < 566435
+    seen = {}
+    real_distill = algo.engine._core.distill_step
+
+    def spy(images, tokens, d_idx, agg_img, agg_txt, img_terms=1, txt_terms=1):
+        seen['terms'] = (img_terms, txt_terms)
+        return real_distill(images, tokens, d_idx, agg_img, agg_txt, img_terms=img_terms, txt_terms=txt_terms)
+    monkeypatch.setattr(algo.engine._core, 'distill_step', spy)
+    scores = algo.train(0)
+    assert seen['terms'] == (2, 2)
+    assert sorted(type(t).__name__ for t in algo.cur_trainers) == sorted(kinds)          # all three were selected
+    for agg in (algo.img_vec, algo.txt_vec):             # image client + mm client / text client + mm client
+        assert agg.shape == (16, 256) and torch.isfinite(agg).all() and float(agg.norm(dim=1).max()) <= 1.0 + 1e-4
+    img_t, txt_t, mm_t = algo.total_local_trainers
+    assert img_t.is_image and not txt_t.is_image
+    assert type(img_t.criterion).__name__ == 'CrossEntropyLoss'
+    assert img_t.local_epoch == txt_t.local_epoch == mm_t.local_epoch == 1
+    assert 0.0 <= scores['test']['i2t']['recall_1'] <= 100.0
+
+
 def test_orchestrator_refuses_cpu_without_emulation():
     MMFL = _mmfl()
     args = _args()
