@@ -239,6 +239,24 @@ def ncu_traffic_bytes(csv_path, column=0):
         return None
 
 
+def ncu_counters(csv_path, column=0):
+    """A few headline counters of launch `column` in a profiles/*_ncu_*.csv summary ({} if absent): evidence that
+    rides with the roofline entry, measured under ncu in an earlier call (never a timing of this run)."""
+    want = {'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed': 'tensor_pipe_pct_elapsed',
+            'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active': 'tensor_pipe_pct_active',
+            'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed': 'dram_pct',
+            'lts__t_sector_hit_rate.pct': 'l2_hit_pct', 'gpu__time_duration.sum': 'ncu_duration_us'}
+    out = {}
+    try:
+        for ln in Path(csv_path).read_text().splitlines():
+            k = ln.split(',')
+            if k[0] in want:
+                out[want[k[0]]] = round(float(k[2 + column]), 2)
+    except (OSError, ValueError, IndexError):
+        return {}
+    return out
+
+
 def load_peaks():
     try:
         return json.loads((ROOT / 'MEASURED_PEAKS.json').read_text())
@@ -641,6 +659,7 @@ def run_ours(args):
                             f'algorithmic FLOPs of all its launches / their summed CUDA-event time)',
                             'achieved': round(ach, 1), 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': round(ach / peak_tf, 4),
                             'traffic': ncu_traffic_bytes(ROOT / 'profiles' / 'r02_ncu_dominant.csv'),
+                            'ncu': ncu_counters(ROOT / 'profiles' / 'r02_ncu_dominant.csv'),
                             'traffic_of': 'one launch of the family\'s top kernel by time, gemm_tc_kernel<256,1,1,0,0,1,2> '
                                           '(split-K weight gradient 1024x256x25088, 65.3 MB algorithmic: both operands '
                                           'once + the fp32 output), ncu --set full capture profiles/r02_ncu_dominant.csv',
